@@ -1,0 +1,1024 @@
+// C ABI of the B200-native Starframe physics tick (include/starframe_gpu.h): world lifetime, slot-indexed
+// uploads, sfg_tick orchestration (broadphase -> constraint graph -> colouring -> XPBD substeps), readback,
+// batched casts and the parity hooks. There is NO CPU fallback: every entry point that computes needs a
+// CUDA device and reports SFG_E_NO_DEVICE / SFG_E_CUDA otherwise.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/starframe_gpu.h"
+#include "sfg_broadphase.cuh"
+#include "sfg_cast.cuh"
+#include "sfg_solver.cuh"
+#include "sfg_sort.cuh"
+
+using namespace sfg;
+
+namespace {
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct TickHeader {            // small device block read back once per tick phase
+    Bounds bounds;
+    uint32_t n_pairs;
+    uint32_t pad[3];
+};
+
+}  // namespace
+
+struct SfgWorld {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    SfgTuning tuning{};
+    uint64_t mask[64];
+    int n_sms = 148;
+    bool ticked = false;
+
+    // bodies
+    uint32_t n_bodies = 0;
+    DBuf<float4> P, Q, V, OV, MI;
+    DBuf<float2> EA, PCD, LAT;
+    DBuf<int> rope_next, rope_prev;
+    // colliders
+    uint32_t n_colls = 0;
+    DBuf<float4> CS, CL, CM, AABB;
+    DBuf<int4> CI;
+    // constraints (raw columns in host order)
+    uint32_t n_constraints = 0;
+    DBuf<int4> KI;
+    DBuf<float4> KA, KB;
+    // ropes
+    uint32_t n_ropes = 0, n_particles = 0, n_rope_units = 0, n_rope_damp = 0;
+    uint32_t rope_colour_start[4] = {0, 0, 0, 0}, damp_colour_start[3] = {0, 0, 0};
+    DBuf<int4> RU, RD;
+    DBuf<float4> RPA, RPB;
+    DBuf<int> rp_body, rp_rope;
+    // staging
+    DBuf<unsigned char> stage;
+    DBuf<unsigned long long> d_mask;
+    DBuf<TickHeader> hdr;
+    // broadphase scratch
+    GridParams grid{};
+    uint32_t n_live = 0;
+    DBuf<uint32_t> keys0, keys1, vals0, vals1, sort_tmp, cell_start, warp_counts, scan_tmp;
+    DBuf<float4> SA;
+    DBuf<int4> SI;
+    // pair units
+    uint32_t n_units = 0, n_unit_colours = 0;
+    std::vector<uint32_t> unit_colour_start;   // n_unit_colours + 1
+    DBuf<uint2> U_ids;
+    DBuf<int2> U_ub;
+    DBuf<uint32_t> U_prio, U_colour, deg, adj_start, adj, cursor, jp_counters, jp_hist, perm0, perm1, ckey0, ckey1;
+    DBuf<float4> H, S, G0, G1, L0, L1, M0, M1, M2;
+    DBuf<float2> LN;
+    // constraint units
+    uint32_t n_kunits = 0, n_k_colours = 0;
+    std::vector<uint32_t> k_colour_start;
+    DBuf<uint2> KU_ids;
+    DBuf<int2> KU_ub;
+    DBuf<uint32_t> KU_prio, KU_colour;
+    DBuf<float4> K0, K1, K2;
+    // persistent solver
+    DBuf<Stage> d_stages;
+    std::vector<Stage> h_stages;
+    // casts
+    DBuf<SfgRay> d_rays;
+    DBuf<SfgCastHit> d_hits;
+    // stats
+    SfgStats stats{};
+    uint32_t launches = 0;
+};
+
+namespace {
+
+int fail(SfgWorld* w, int code, const char* what, cudaError_t e = cudaSuccess) {
+    if (w) {
+        w->err = what;
+        if (e != cudaSuccess) { w->err += ": "; w->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+#define CK(call)                                                        \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return fail(w, SFG_E_CUDA, #call, e__); \
+    } while (0)
+#define CKL(w_)                                                                    \
+    do {                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                      \
+        if (e__ != cudaSuccess) return fail(w_, SFG_E_CUDA, "kernel launch", e__); \
+    } while (0)
+
+inline uint32_t nblk(uint32_t n, uint32_t t = 256) { return (n + t - 1) / t; }
+
+// ---- AoS <-> SoA on the device ----
+__global__ void k_unpack_bodies(const SfgBody* in, uint32_t n, uint32_t first, float4* P, float4* Q, float4* V, float4* MI) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SfgBody b = in[i];
+    const uint32_t s = first + i;
+    P[s] = make_float4(b.x, b.y, 0.f, 0.f);
+    Q[s] = make_float4(b.rot_s, b.rot_b, b.rot_s, b.rot_b);
+    V[s] = make_float4(b.vx, b.vy, b.w, 0.f);
+    MI[s] = make_float4((b.flags & SFG_BODY_MASS_FINITE) ? b.inv_mass : 0.f, (b.flags & SFG_BODY_INERTIA_FINITE) ? b.inv_inertia : 0.f,
+                        __uint_as_float(b.flags & 15u), 0.f);
+}
+__global__ void k_pack_bodies(SfgBody* out, uint32_t n, uint32_t first, const float4* P, const float4* Q, const float4* V, const float4* MI) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = first + i;
+    const float4 p = P[s], q = Q[s], v = V[s], m = MI[s];
+    SfgBody b;
+    b.x = p.x + p.z; b.y = p.y + p.w; b.rot_s = q.x; b.rot_b = q.y;
+    b.vx = v.x; b.vy = v.y; b.w = v.z;
+    b.flags = __float_as_uint(m.z);
+    b.inv_mass = m.x; b.inv_inertia = m.y;
+    b.reserved[0] = b.reserved[1] = 0;
+    out[i] = b;
+}
+__global__ void k_unpack_colliders(const SfgCollider* in, uint32_t n, uint32_t first, float4* CS, float4* CL, float4* CM, int4* CI) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SfgCollider c = in[i];
+    const uint32_t s = first + i;
+    CS[s] = make_float4(c.p0, c.p1, c.circle_r, __uint_as_float(c.kind));
+    CL[s] = make_float4(c.x, c.y, c.rot_s, c.rot_b);
+    CM[s] = make_float4(c.static_friction, c.dynamic_friction, c.restitution, __uint_as_float(c.flags & 15u));
+    CI[s] = make_int4(c.body, int(c.layer), int(c.domain), int(c.flags & 15u));
+}
+__global__ void k_unpack_constraints(const SfgConstraint* in, uint32_t n, int4* KI, float4* KA, float4* KB) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SfgConstraint c = in[i];
+    KI[i] = make_int4(c.owner, c.target, int(c.flags), 0);
+    KA[i] = make_float4(c.compliance, c.linear_damping, c.angular_damping, c.distance);
+    KB[i] = make_float4(c.off0x, c.off0y, c.off1x, c.off1y);
+}
+__global__ void k_collect_contacts(uint32_t n_entries, uint32_t n_units, const float2* LN, const float4* S, SfgContactInfo* out, uint32_t cap,
+                                   uint32_t* count) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const float2 n = LN[e];
+    if (isnan(n.x) && isnan(n.y)) return;
+    const uint32_t pos = atomicAdd(count, 1u);
+    if (pos >= cap) return;
+    const float4 s = S[e % n_units];
+    SfgContactInfo ci;
+    ci.collider0 = __float_as_uint(s.x); ci.collider1 = __float_as_uint(s.y); ci.nx = n.x; ci.ny = n.y;
+    out[pos] = ci;
+}
+__global__ void k_export_manifolds(uint32_t n_entries, uint32_t n_units, const float4* S, const float4* M0, const float4* M1, const float4* M2,
+                                   float* out) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const float4 s = S[e % n_units], m0 = M0[e];
+    const int count = __float_as_int(m0.x);
+    float* o = out + 14 * size_t(e);
+    o[0] = float(__float_as_uint(s.x)); o[1] = float(__float_as_uint(s.y));
+    o[2] = float(count); o[3] = count ? m0.y : 0.f; o[4] = count ? m0.z : 0.f; o[5] = count ? m0.w : 0.f;
+    float4 a = count >= 1 ? M1[e] : make_float4(0, 0, 0, 0), b = count >= 2 ? M2[e] : make_float4(0, 0, 0, 0);
+    o[6] = a.x; o[7] = a.y; o[8] = a.z; o[9] = a.w; o[10] = b.x; o[11] = b.y; o[12] = b.z; o[13] = b.w;
+}
+__global__ void k_export_units(uint32_t n_units, const float4* H, const float4* S, uint32_t* hi, uint32_t* lo_mult) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const float4 s = S[u];
+    hi[u] = __float_as_uint(s.x);
+    lo_mult[u] = __float_as_uint(s.y) | ((__float_as_uint(H[u].z) & UF_MULT2) ? 0x80000000u : 0u);
+}
+
+// standalone parity kernels
+__global__ void k_dbg_isect(uint32_t n, const float* poses, const float* shapes, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Iso p[2]; Shape s[2];
+    for (int k = 0; k < 2; ++k) {
+        const float* pp = poses + 8 * size_t(i) + 4 * k; const float* ss = shapes + 8 * size_t(i) + 4 * k;
+        p[k] = mkiso(mk(pp[0], pp[1]), mkrot(pp[2], pp[3]));
+        s[k].kind = uint32_t(ss[0]); s[k].p0 = ss[1]; s[k].p1 = ss[2]; s[k].r = ss[3];
+    }
+    Manifold m;
+    intersection_check(p, s, m);
+    float* o = out + 14 * size_t(i);
+    for (int k = 0; k < 14; ++k) o[k] = 0.f;
+    o[0] = float(m.count);
+    if (m.count) { o[2] = m.n.x; o[3] = m.n.y; }
+    for (int k = 0; k < m.count; ++k) { o[4 + 4 * k] = m.off[k][0].x; o[5 + 4 * k] = m.off[k][0].y; o[6 + 4 * k] = m.off[k][1].x; o[7 + 4 * k] = m.off[k][1].y; }
+}
+__global__ void k_dbg_cast(uint32_t n, const SfgRay* rays, const float* poses, const float* shapes, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* pp = poses + 4 * size_t(i); const float* ss = shapes + 4 * size_t(i);
+    Shape s; s.kind = uint32_t(ss[0]); s.p0 = ss[1]; s.p1 = ss[2]; s.r = ss[3];
+    const SfgRay r = rays[i];
+    Hit h = spherecast_collider(mk(r.sx, r.sy), mk(r.dx, r.dy), r.radius, mkiso(mk(pp[0], pp[1]), mkrot(pp[2], pp[3])), s);
+    float* o = out + 6 * size_t(i);
+    o[0] = h.hit ? 1.f : 0.f; o[1] = h.t; o[2] = h.n.x; o[3] = h.n.y; o[4] = h.p.x; o[5] = h.p.y;
+}
+__global__ void k_dbg_geometry(uint32_t op, uint32_t n, const float* args, const float* shapes, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* ss = shapes + 4 * size_t(i);
+    Shape s; s.kind = uint32_t(ss[0]); s.p0 = ss[1]; s.p1 = ss[2]; s.r = ss[3];
+    const V2 a = mk(args[2 * size_t(i)], args[2 * size_t(i) + 1]);
+    float* o = out + 7 * size_t(i);
+    for (int k = 0; k < 7; ++k) o[k] = 0.f;
+    if (op == 0) { bool in; V2 c = closest_boundary_point(s, a, &in); o[0] = c.x; o[1] = c.y; o[2] = in ? 1.f : 0.f; }
+    else if (op == 1) o[0] = projected_extent(s, a);
+    else if (op == 2) { PEdge e = supporting_edge(s, a); o[0] = e.n.x; o[1] = e.n.y; o[2] = e.e.start.x; o[3] = e.e.start.y; o[4] = e.e.dir.x; o[5] = e.e.dir.y; o[6] = e.e.len; }
+    else if (op == 3) o[0] = point_in_collider(a, mkiso(mk(0.f, 0.f), mkrot(1.f, 0.f)), s) ? 1.f : 0.f;
+}
+
+__global__ void k_iota(uint32_t* p, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+
+int ensure_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SFG_E_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return SFG_E_CUDA;
+    return SFG_OK;
+}
+
+// Colour a unit graph and return the sorted permutation + colour starts. Shared by pairs and constraints.
+int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub, const uint32_t* prio, DBuf<uint32_t>& colour,
+                 uint32_t** perm_out, std::vector<uint32_t>& colour_start, uint32_t* n_colours_out) {
+    cudaStream_t st = w->stream;
+    colour_start.clear();
+    *n_colours_out = 0;
+    *perm_out = nullptr;
+    if (n_units == 0) { colour_start.push_back(0); return SFG_OK; }
+    const uint32_t nb = w->n_bodies;
+    // adjacency (deg was accumulated by the unit-setup kernel)
+    CK(w->adj_start.ensure(nb + 2)); CK(w->cursor.ensure(nb + 1)); CK(w->adj.ensure(size_t(n_units) * 2 + 1));
+    CK(w->scan_tmp.ensure(scan_tmp_words(nb + 1)));
+    w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
+    CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
+    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, w->adj_start.p, w->cursor.p, w->adj.p); CKL(w); w->launches++;
+    // Jones-Plassmann in one cooperative launch
+    constexpr uint32_t HIST_CAP = 65536;
+    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(JP_MAX_ROUNDS + 1)); CK(w->jp_hist.ensure(HIST_CAP));
+    CK(cudaMemsetAsync(colour.p, 0xFF, size_t(n_units) * 4, st));
+    CK(cudaMemsetAsync(w->jp_counters.p, 0, (JP_MAX_ROUNDS + 1) * 4, st));
+    CK(cudaMemsetAsync(w->jp_hist.p, 0, HIST_CAP * 4, st));
+    {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jp_colour, 256, 0));
+        uint32_t grid = std::min<uint32_t>(uint32_t(per_sm * w->n_sms), std::max<uint32_t>(nblk(n_units), 1));
+        uint32_t hist_cap = HIST_CAP;
+        const uint32_t* adj_start = w->adj_start.p; const uint32_t* adj = w->adj.p;
+        uint32_t* col = colour.p; uint32_t* counters = w->jp_counters.p; uint32_t* hist = w->jp_hist.p;
+        void* args[] = {&n_units, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &counters, &hist, &hist_cap};
+        CK(cudaLaunchCooperativeKernel((void*)k_jp_colour, dim3(grid), dim3(256), args, 0, st));
+        w->launches++;
+    }
+    uint32_t n_colours = 0;
+    CK(cudaMemcpyAsync(&n_colours, w->jp_counters.p + JP_MAX_ROUNDS, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_colours == 0 || n_colours > HIST_CAP) return fail(w, SFG_E_CAPACITY, "colouring did not converge or needs > 65536 colours");
+    std::vector<uint32_t> hist(n_colours);
+    CK(cudaMemcpyAsync(hist.data(), w->jp_hist.p, size_t(n_colours) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    colour_start.resize(n_colours + 1);
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < n_colours; ++c) { colour_start[c] = run; run += hist[c]; }
+    colour_start[n_colours] = run;
+    if (run != n_units) return fail(w, SFG_E_CAPACITY, "colouring left units uncoloured");
+    // stable sort by colour: perm = unit indices in colour-major order
+    CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units)); CK(w->perm0.ensure(n_units)); CK(w->perm1.ensure(n_units));
+    CK(w->sort_tmp.ensure(sort_tmp_words(n_units)));
+    CK(cudaMemcpyAsync(w->ckey0.p, colour.p, size_t(n_units) * 4, cudaMemcpyDeviceToDevice, st));
+    k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
+    int bits = 1;
+    while ((1u << bits) < n_colours) ++bits;
+    int launches = 0;
+    int where = radix_sort_pairs(w->ckey0.p, w->perm0.p, w->ckey1.p, w->perm1.p, n_units, bits, w->sort_tmp.p, st, &launches);
+    w->launches += launches;
+    *perm_out = where ? w->perm1.p : w->perm0.p;
+    *n_colours_out = n_colours;
+    return SFG_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int sfg_abi_version(void) { return SFG_ABI_VERSION; }
+
+void sfg_default_tuning(SfgTuning* t) {   // physics.rs:338-349
+    memset(t, 0, sizeof(*t));
+    t->substeps = 10; t->sleep_vel_threshold = 0.001f; t->fall_asleep_frames = 10; t->max_expected_acceleration = 10.0f;
+}
+void sfg_default_mask_matrix(uint64_t out[64]) {   // collision.rs:132-140
+    for (int i = 0; i < 64; ++i) out[i] = ~0ull;
+    out[63] &= ~(1ull << 63);
+}
+
+int sfg_world_create(const SfgTuning* tuning, const uint64_t mask_matrix[64], int device, SfgWorld** out) {
+    if (!out) return SFG_E_INVALID;
+    *out = nullptr;
+    int rc = ensure_device(device);
+    if (rc != SFG_OK) return rc;
+    SfgWorld* w = new SfgWorld();
+    w->device = device;
+    if (tuning) w->tuning = *tuning; else sfg_default_tuning(&w->tuning);
+    if (mask_matrix) memcpy(w->mask, mask_matrix, sizeof(w->mask)); else sfg_default_mask_matrix(w->mask);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) w->n_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return SFG_E_CUDA; }
+    for (auto& e : w->ev) cudaEventCreate(&e);
+    if (w->d_mask.ensure(64) != cudaSuccess || w->hdr.ensure(1) != cudaSuccess) { delete w; return SFG_E_CUDA; }
+    cudaMemcpyAsync(w->d_mask.p, w->mask, sizeof(w->mask), cudaMemcpyHostToDevice, w->stream);
+    cudaStreamSynchronize(w->stream);
+    *out = w;
+    return SFG_OK;
+}
+
+void sfg_world_destroy(SfgWorld* w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    DBuf<float4>* f4[] = {&w->P, &w->Q, &w->V, &w->OV, &w->MI, &w->CS, &w->CL, &w->CM, &w->AABB, &w->KA, &w->KB, &w->RPA, &w->RPB, &w->SA,
+                          &w->H, &w->S, &w->G0, &w->G1, &w->L0, &w->L1, &w->M0, &w->M1, &w->M2, &w->K0, &w->K1, &w->K2};
+    for (auto* b : f4) b->release();
+    DBuf<float2>* f2[] = {&w->EA, &w->PCD, &w->LAT, &w->LN};
+    for (auto* b : f2) b->release();
+    DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->warp_counts, &w->scan_tmp, &w->U_prio,
+                            &w->U_colour, &w->deg, &w->adj_start, &w->adj, &w->cursor, &w->jp_counters, &w->jp_hist, &w->perm0, &w->perm1,
+                            &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour};
+    for (auto* b : u1) b->release();
+    DBuf<int>* i1[] = {&w->rope_next, &w->rope_prev, &w->rp_body, &w->rp_rope};
+    for (auto* b : i1) b->release();
+    DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
+    for (auto* b : i4) b->release();
+    w->U_ids.release(); w->KU_ids.release(); w->U_ub.release(); w->KU_ub.release();
+    w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
+    for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+int sfg_world_clear(SfgWorld* w) {   // physics.rs:386-393
+    if (!w) return SFG_E_INVALID;
+    w->n_bodies = w->n_colls = w->n_constraints = w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0;
+    w->n_units = w->n_kunits = 0;
+    w->ticked = false;
+    memset(&w->stats, 0, sizeof(w->stats));
+    return SFG_OK;
+}
+const char* sfg_last_error(const SfgWorld* w) { return w ? w->err.c_str() : "null world"; }
+
+int sfg_set_tuning(SfgWorld* w, const SfgTuning* t) {
+    if (!w || !t) return SFG_E_INVALID;
+    if (t->substeps == 0) return fail(w, SFG_E_INVALID, "substeps must be > 0");
+    w->tuning = *t;
+    return SFG_OK;
+}
+int sfg_set_mask_matrix(SfgWorld* w, const uint64_t m[64]) {
+    if (!w || !m) return SFG_E_INVALID;
+    cudaSetDevice(w->device);
+    memcpy(w->mask, m, sizeof(w->mask));
+    CK(cudaMemcpyAsync(w->d_mask.p, w->mask, sizeof(w->mask), cudaMemcpyHostToDevice, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return SFG_OK;
+}
+
+static int upload_bodies(SfgWorld* w, uint32_t first, uint32_t count, const SfgBody* b) {
+    if (count == 0) return SFG_OK;
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(count) * sizeof(SfgBody)));
+    CK(cudaMemcpyAsync(w->stage.p, b, size_t(count) * sizeof(SfgBody), cudaMemcpyHostToDevice, st));
+    k_unpack_bodies<<<nblk(count), 256, 0, st>>>((const SfgBody*)w->stage.p, count, first, w->P.p, w->Q.p, w->V.p, w->MI.p);
+    CKL(w);
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+int sfg_set_bodies(SfgWorld* w, uint32_t n, const SfgBody* b) {
+    if (!w || (n && !b)) return SFG_E_INVALID;
+    cudaSetDevice(w->device);
+    CK(w->P.ensure(n)); CK(w->Q.ensure(n)); CK(w->V.ensure(n)); CK(w->OV.ensure(n)); CK(w->MI.ensure(n)); CK(w->EA.ensure(n));
+    w->n_bodies = n;
+    return upload_bodies(w, 0, n, b);
+}
+int sfg_update_bodies(SfgWorld* w, uint32_t first, uint32_t count, const SfgBody* b) {
+    if (!w || (count && !b)) return SFG_E_INVALID;
+    if (uint64_t(first) + count > w->n_bodies) return fail(w, SFG_E_INVALID, "body slot range out of bounds");
+    cudaSetDevice(w->device);
+    return upload_bodies(w, first, count, b);
+}
+static int upload_colliders(SfgWorld* w, uint32_t first, uint32_t count, const SfgCollider* c) {
+    if (count == 0) return SFG_OK;
+    for (uint32_t i = 0; i < count; ++i) {
+        if (!(c[i].flags & SFG_COLL_ALIVE)) continue;
+        if (c[i].kind > SFG_POLY_HEXAGON) return fail(w, SFG_E_INVALID, "unknown collider polygon kind");
+        if (c[i].layer >= 64) return fail(w, SFG_E_INVALID, "collider layer must be < 64");
+        if (c[i].body >= 0 && uint32_t(c[i].body) >= w->n_bodies) return fail(w, SFG_E_INVALID, "collider body slot out of range (set bodies first)");
+    }
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(count) * sizeof(SfgCollider)));
+    CK(cudaMemcpyAsync(w->stage.p, c, size_t(count) * sizeof(SfgCollider), cudaMemcpyHostToDevice, st));
+    k_unpack_colliders<<<nblk(count), 256, 0, st>>>((const SfgCollider*)w->stage.p, count, first, w->CS.p, w->CL.p, w->CM.p, w->CI.p);
+    CKL(w);
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+int sfg_set_colliders(SfgWorld* w, uint32_t n, const SfgCollider* c) {
+    if (!w || (n && !c)) return SFG_E_INVALID;
+    cudaSetDevice(w->device);
+    CK(w->CS.ensure(n)); CK(w->CL.ensure(n)); CK(w->CM.ensure(n)); CK(w->CI.ensure(n)); CK(w->AABB.ensure(n));
+    w->n_colls = n;
+    w->ticked = false;
+    return upload_colliders(w, 0, n, c);
+}
+int sfg_update_colliders(SfgWorld* w, uint32_t first, uint32_t count, const SfgCollider* c) {
+    if (!w || (count && !c)) return SFG_E_INVALID;
+    if (uint64_t(first) + count > w->n_colls) return fail(w, SFG_E_INVALID, "collider slot range out of bounds");
+    cudaSetDevice(w->device);
+    return upload_colliders(w, first, count, c);
+}
+int sfg_set_constraints(SfgWorld* w, uint32_t n, const SfgConstraint* c) {
+    if (!w || (n && !c)) return SFG_E_INVALID;
+    cudaSetDevice(w->device);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (c[i].owner < 0 || uint32_t(c[i].owner) >= w->n_bodies) return fail(w, SFG_E_INVALID, "constraint owner slot out of range");
+        if (c[i].target >= 0 && uint32_t(c[i].target) >= w->n_bodies) return fail(w, SFG_E_INVALID, "constraint target slot out of range");
+        if ((c[i].flags & SFG_LIMIT_MASK) > SFG_LIMIT_GT) return fail(w, SFG_E_INVALID, "unknown constraint limit");
+    }
+    w->n_constraints = n;
+    if (n == 0) return SFG_OK;
+    cudaStream_t st = w->stream;
+    CK(w->KI.ensure(n)); CK(w->KA.ensure(n)); CK(w->KB.ensure(n));
+    CK(w->stage.ensure(size_t(n) * sizeof(SfgConstraint)));
+    CK(cudaMemcpyAsync(w->stage.p, c, size_t(n) * sizeof(SfgConstraint), cudaMemcpyHostToDevice, st));
+    k_unpack_constraints<<<nblk(n), 256, 0, st>>>((const SfgConstraint*)w->stage.p, n, w->KI.p, w->KA.p, w->KB.p);
+    CKL(w);
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+// Rope topology is turned into colour-major unit lists on the host (it only changes when the host edits ropes):
+// step units (curr, next, after) coloured i mod 3 (solver.rs:118-179 touches particles i, i+1, i+2) and damping
+// pairs coloured i mod 2 (solver.rs:722-740).
+int sfg_set_ropes(SfgWorld* w, uint32_t n_ropes, const SfgRope* ropes, uint32_t n_particles, const int32_t* particle_bodies) {
+    if (!w || (n_ropes && (!ropes || !particle_bodies))) return SFG_E_INVALID;
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    std::vector<int4> ru[3], rd[2];
+    std::vector<float4> pa(n_ropes), pb(n_ropes);
+    std::vector<int> rp_rope(n_particles, 0), next(w->n_bodies, -1), prev(w->n_bodies, -1);
+    for (uint32_t r = 0; r < n_ropes; ++r) {
+        const SfgRope& rp = ropes[r];
+        if (rp.particle_count < 2) return fail(w, SFG_E_INVALID, "Rope only had one particle");   // solver.rs:120 panics
+        if (uint64_t(rp.first_particle) + rp.particle_count > n_particles) return fail(w, SFG_E_INVALID, "rope particle range out of bounds");
+        pa[r] = make_float4(rp.spacing, rp.compliance, rp.bending_max_angle, rp.bending_compliance);
+        pb[r] = make_float4(rp.damping, 0.f, 0.f, 0.f);
+        const int32_t* p = particle_bodies + rp.first_particle;
+        for (uint32_t i = 0; i < rp.particle_count; ++i) {
+            if (p[i] < 0 || uint32_t(p[i]) >= w->n_bodies) return fail(w, SFG_E_INVALID, "rope particle body slot out of range");
+            rp_rope[rp.first_particle + i] = int(r);
+            if (i + 1 < rp.particle_count) {
+                next[p[i]] = p[i + 1]; prev[p[i + 1]] = p[i];
+                ru[i % 3].push_back(make_int4(p[i], p[i + 1], i + 2 < rp.particle_count ? p[i + 2] : -1, int(r)));
+                rd[i % 2].push_back(make_int4(p[i], p[i + 1], int(r), 0));
+            }
+        }
+    }
+    std::vector<int4> ru_all, rd_all;
+    for (int c = 0; c < 3; ++c) { w->rope_colour_start[c] = uint32_t(ru_all.size()); ru_all.insert(ru_all.end(), ru[c].begin(), ru[c].end()); }
+    w->rope_colour_start[3] = uint32_t(ru_all.size());
+    for (int c = 0; c < 2; ++c) { w->damp_colour_start[c] = uint32_t(rd_all.size()); rd_all.insert(rd_all.end(), rd[c].begin(), rd[c].end()); }
+    w->damp_colour_start[2] = uint32_t(rd_all.size());
+    w->n_ropes = n_ropes; w->n_particles = n_particles;
+    w->n_rope_units = uint32_t(ru_all.size()); w->n_rope_damp = uint32_t(rd_all.size());
+    CK(w->rope_next.ensure(w->n_bodies + 1)); CK(w->rope_prev.ensure(w->n_bodies + 1));
+    if (w->n_bodies) {
+        CK(cudaMemcpyAsync(w->rope_next.p, next.data(), size_t(w->n_bodies) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w->rope_prev.p, prev.data(), size_t(w->n_bodies) * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (n_ropes) {
+        CK(w->RU.ensure(ru_all.size())); CK(w->RD.ensure(rd_all.size())); CK(w->RPA.ensure(n_ropes)); CK(w->RPB.ensure(n_ropes));
+        CK(w->rp_body.ensure(n_particles)); CK(w->rp_rope.ensure(n_particles));
+        CK(w->PCD.ensure(w->n_bodies)); CK(w->LAT.ensure(w->n_bodies));
+        CK(cudaMemcpyAsync(w->RU.p, ru_all.data(), ru_all.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w->RD.p, rd_all.data(), rd_all.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w->RPA.p, pa.data(), size_t(n_ropes) * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w->RPB.p, pb.data(), size_t(n_ropes) * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w->rp_body.p, particle_bodies, size_t(n_particles) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w->rp_rope.p, rp_rope.data(), size_t(n_particles) * 4, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Choose the hierarchical grid from the measured bounds (host side, a few dozen flops per tick).
+void choose_grid(SfgWorld* w, const Bounds& b) {
+    GridParams& g = w->grid;
+    memset(&g, 0, sizeof(g));
+    const float min_x = ord2f_host(b.min_x), min_y = ord2f_host(b.min_y), max_x = ord2f_host(b.max_x), max_y = ord2f_host(b.max_y);
+    const float max_ext = ord2f_host(b.max_extent);
+    const double mean_ext = b.n_live ? b.sum_extent / double(b.n_live) : 1.0;
+    double c0 = w->tuning.cell_size > 0.f ? double(w->tuning.cell_size) : 2.0 * mean_ext;
+    if (!(c0 > 1e-6)) c0 = 1.0;
+    const double wx = std::max(double(max_x) - double(min_x), 0.0), wy = std::max(double(max_y) - double(min_y), 0.0);
+    g.ox = min_x; g.oy = min_y;
+    g.n_domains = b.max_domain + 1;
+    const double cap = std::min(double(1u << 26), 8.0 * double(b.n_live) + 4096.0);
+    for (;;) {
+        int nl = 1;
+        while (nl < MAX_LEVELS && c0 * std::pow(4.0, nl - 1) < double(max_ext)) ++nl;
+        double total = 0;
+        for (int l = 0; l < nl; ++l) {
+            const double cell = c0 * std::pow(4.0, l);
+            const double nx = std::floor(wx / cell) + 1.0, ny = std::floor(wy / cell) + 1.0;
+            total += nx * ny * double(g.n_domains);
+        }
+        if (total <= cap || c0 > 1e30) {
+            g.n_levels = nl;
+            uint32_t base = 0;
+            for (int l = 0; l < nl; ++l) {
+                const double cell = c0 * std::pow(4.0, l);
+                g.cell[l] = float(cell); g.inv_cell[l] = float(1.0 / cell);
+                g.nx[l] = int(std::floor(wx / cell) + 1.0); g.ny[l] = int(std::floor(wy / cell) + 1.0);
+                g.base[l] = base;
+                base += uint32_t(g.nx[l]) * uint32_t(g.ny[l]) * g.n_domains;
+            }
+            g.n_cells = base;
+            return;
+        }
+        c0 *= 1.5;
+    }
+}
+
+template <uint32_t KIND>
+int launch_stage(SfgWorld* w, const SolverCtx& ctx, uint32_t begin, uint32_t end, bool last) {
+    if (end <= begin) return SFG_OK;
+    k_stage<KIND><<<nblk(end - begin), 256, 0, w->stream>>>(ctx, begin, end, last ? 1 : 0);
+    CKL(w);
+    w->launches++;
+    return SFG_OK;
+}
+
+int launch_stage_dyn(SfgWorld* w, const SolverCtx& ctx, const Stage& s, bool last) {
+    switch (s.kind) {
+    case ST_INTEGRATE: return launch_stage<ST_INTEGRATE>(w, ctx, s.begin, s.end, last);
+    case ST_ROPE_STEP: return launch_stage<ST_ROPE_STEP>(w, ctx, s.begin, s.end, last);
+    case ST_CONSTRAINTS: return launch_stage<ST_CONSTRAINTS>(w, ctx, s.begin, s.end, last);
+    case ST_PRECONTACT: return launch_stage<ST_PRECONTACT>(w, ctx, s.begin, s.end, last);
+    case ST_CONTACTS: return launch_stage<ST_CONTACTS>(w, ctx, s.begin, s.end, last);
+    case ST_DERIVE: return launch_stage<ST_DERIVE>(w, ctx, s.begin, s.end, last);
+    case ST_CONTACT_VEL: return launch_stage<ST_CONTACT_VEL>(w, ctx, s.begin, s.end, last);
+    case ST_CONSTRAINT_DAMP: return launch_stage<ST_CONSTRAINT_DAMP>(w, ctx, s.begin, s.end, last);
+    case ST_ROPE_DAMP: return launch_stage<ST_ROPE_DAMP>(w, ctx, s.begin, s.end, last);
+    case ST_ROPE_LATERAL: return launch_stage<ST_ROPE_LATERAL>(w, ctx, s.begin, s.end, last);
+    default: return launch_stage<ST_FOLD>(w, ctx, s.begin, s.end, last);
+    }
+}
+
+int broadphase(SfgWorld* w, float frame_dt) {
+    cudaStream_t st = w->stream;
+    const uint32_t nc = w->n_colls;
+    w->n_units = 0; w->n_live = 0;
+    if (nc == 0) return SFG_OK;
+    // 1. boxes + bounds
+    TickHeader h0;
+    memset(&h0, 0, sizeof(h0));
+    h0.bounds.min_x = h0.bounds.min_y = 0x7FFFFFFF; h0.bounds.max_x = h0.bounds.max_y = int(0x80000000u); h0.bounds.max_extent = int(0x80000000u);
+    CK(cudaMemcpyAsync(w->hdr.p, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
+    const float pad = w->tuning.max_expected_acceleration * frame_dt;
+    k_aabb<<<nblk(nc), 256, 0, st>>>(nc, w->CS.p, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p, frame_dt, pad, w->AABB.p, &w->hdr.p->bounds);
+    CKL(w); w->launches++;
+    TickHeader h;
+    CK(cudaMemcpyAsync(&h, w->hdr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    w->n_live = h.bounds.n_live;
+    if (w->n_live == 0) { memset(&w->grid, 0, sizeof(w->grid)); return SFG_OK; }
+    choose_grid(w, h.bounds);
+    const GridParams& g = w->grid;
+    // 2. keys + sort
+    CK(w->keys0.ensure(nc)); CK(w->keys1.ensure(nc)); CK(w->vals0.ensure(nc)); CK(w->vals1.ensure(nc));
+    CK(w->sort_tmp.ensure(sort_tmp_words(nc)));
+    k_cell_keys<<<nblk(nc), 256, 0, st>>>(g, nc, w->AABB.p, w->CI.p, w->keys0.p, w->vals0.p);
+    CKL(w); w->launches++;
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) <= uint64_t(g.n_cells) + 1) ++bits;
+    // dead keys are 0xFFFFFFFF: sorting on the low `bits` bits would mix them in, so give them the top key of the range
+    // (n_cells + 1 fits in `bits` bits by construction) — k_cell_keys already wrote 0xFFFFFFFF; all low bits set >= n_cells + 1.
+    int launches = 0;
+    const int where = radix_sort_pairs(w->keys0.p, w->vals0.p, w->keys1.p, w->vals1.p, nc, bits, w->sort_tmp.p, st, &launches);
+    w->launches += launches;
+    const uint32_t* keys = where ? w->keys1.p : w->keys0.p;
+    const uint32_t* vals = where ? w->vals1.p : w->vals0.p;
+    // 3. sorted copies + cell starts
+    CK(w->SA.ensure(nc)); CK(w->SI.ensure(nc)); CK(w->cell_start.ensure(size_t(g.n_cells) + 2));
+    k_gather_sorted<<<nblk(nc), 256, 0, st>>>(g, nc, keys, vals, w->AABB.p, w->CI.p, w->SA.p, w->SI.p);
+    CKL(w); w->launches++;
+    k_cell_starts<<<nblk(nc + 1), 256, 0, st>>>(keys, nc, g.n_cells, w->cell_start.p);
+    CKL(w); w->launches++;
+    // 4. count, scan, emit
+    const uint32_t n_warps = (w->n_live + 31) / 32;
+    CK(w->warp_counts.ensure(n_warps + 1)); CK(w->scan_tmp.ensure(scan_tmp_words(n_warps + 1)));
+    k_pairs<false><<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, w->cell_start.p, w->d_mask.p, w->warp_counts.p, nullptr,
+                                                       nullptr, 0);
+    CKL(w); w->launches++;
+    w->launches += scan_exclusive(w->warp_counts.p, w->warp_counts.p, n_warps, w->scan_tmp.p, &w->hdr.p->n_pairs, st);
+    uint32_t n_pairs = 0;
+    CK(cudaMemcpyAsync(&n_pairs, &w->hdr.p->n_pairs, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    w->n_units = n_pairs;
+    if (n_pairs == 0) return SFG_OK;
+    CK(w->U_ids.ensure(n_pairs));
+    k_pairs<true><<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, w->cell_start.p, w->d_mask.p, nullptr, w->warp_counts.p,
+                                                      w->U_ids.p, n_pairs);
+    CKL(w); w->launches++;
+    return SFG_OK;
+}
+
+int build_graph(SfgWorld* w) {
+    cudaStream_t st = w->stream;
+    const uint32_t nb = w->n_bodies;
+    w->n_unit_colours = 0; w->n_k_colours = 0; w->n_kunits = 0;
+    w->unit_colour_start.assign(1, 0); w->k_colour_start.assign(1, 0);
+    CK(w->deg.ensure(nb + 2));
+    // ---- pair units
+    if (w->n_units) {
+        const uint32_t n = w->n_units;
+        CK(w->U_ub.ensure(n)); CK(w->U_prio.ensure(n));
+        CK(cudaMemsetAsync(w->deg.p, 0, size_t(nb + 2) * 4, st));
+        k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->U_ub.p, w->U_prio.p, w->deg.p);
+        CKL(w); w->launches++;
+        uint32_t* perm = nullptr;
+        int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours);
+        if (rc != SFG_OK) return rc;
+        CK(w->H.ensure(n)); CK(w->S.ensure(n)); CK(w->G0.ensure(n)); CK(w->G1.ensure(n)); CK(w->L0.ensure(n)); CK(w->L1.ensure(n));
+        CK(w->M0.ensure(size_t(n) * 2)); CK(w->M1.ensure(size_t(n) * 2)); CK(w->M2.ensure(size_t(n) * 2)); CK(w->LN.ensure(size_t(n) * 2));
+        k_build_pair_units<<<nblk(n), 256, 0, st>>>(n, perm, w->U_ids.p, w->CS.p, w->CL.p, w->CM.p, w->CI.p, w->MI.p,
+                                                    w->n_ropes ? w->rope_next.p : nullptr, w->n_ropes ? w->rope_prev.p : nullptr, w->H.p, w->S.p,
+                                                    w->G0.p, w->G1.p, w->L0.p, w->L1.p);
+        CKL(w); w->launches++;
+        CK(cudaMemsetAsync(w->LN.p, 0xFF, size_t(n) * 2 * sizeof(float2), st));
+        CK(cudaMemsetAsync(w->M0.p, 0, size_t(n) * 2 * sizeof(float4), st));
+    }
+    // ---- constraint units
+    if (w->n_constraints) {
+        const uint32_t n = w->n_constraints;
+        w->n_kunits = n;
+        CK(w->KU_ids.ensure(n)); CK(w->KU_ub.ensure(n)); CK(w->KU_prio.ensure(n));
+        CK(cudaMemsetAsync(w->deg.p, 0, size_t(nb + 2) * 4, st));
+        k_constraint_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->KI.p, w->MI.p, w->KU_ids.p, w->KU_ub.p, w->KU_prio.p, w->deg.p);
+        CKL(w); w->launches++;
+        uint32_t* perm = nullptr;
+        int rc = colour_units(w, n, w->KU_ids.p, w->KU_ub.p, w->KU_prio.p, w->KU_colour, &perm, w->k_colour_start, &w->n_k_colours);
+        if (rc != SFG_OK) return rc;
+        CK(w->K0.ensure(n)); CK(w->K1.ensure(n)); CK(w->K2.ensure(n));
+        k_build_constraint_units<<<nblk(n), 256, 0, st>>>(n, perm, w->KI.p, w->KA.p, w->KB.p, w->K0.p, w->K1.p, w->K2.p);
+        CKL(w); w->launches++;
+    }
+    return SFG_OK;
+}
+
+void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
+    memset(&c, 0, sizeof(c));
+    c.P = w->P.p; c.Q = w->Q.p; c.V = w->V.p; c.OV = w->OV.p; c.MI = w->MI.p; c.EA = w->EA.p; c.PCD = w->PCD.p;
+    c.rope_next = w->rope_next.p; c.rope_prev = w->rope_prev.p; c.n_bodies = w->n_bodies;
+    c.H = w->H.p; c.S = w->S.p; c.G0 = w->G0.p; c.G1 = w->G1.p; c.L0 = w->L0.p; c.L1 = w->L1.p;
+    c.M0 = w->M0.p; c.M1 = w->M1.p; c.M2 = w->M2.p; c.LN = w->LN.p; c.n_units = w->n_units;
+    c.K0 = w->K0.p; c.K1 = w->K1.p; c.K2 = w->K2.p; c.n_kunits = w->n_kunits;
+    c.RU = w->RU.p; c.RD = w->RD.p; c.RPA = w->RPA.p; c.RPB = w->RPB.p; c.rp_body = w->rp_body.p; c.rp_rope = w->rp_rope.p;
+    c.LAT = w->LAT.p; c.n_particles = w->n_particles;
+    c.dt = dt; c.inv_dt = float(1.0 / double(dt)); c.inv_dt_sq = c.inv_dt * c.inv_dt;
+    c.ff.n = 0;
+    if (ff)
+        for (uint32_t i = 0; i < ff->n_terms && i < 4; ++i) {
+            c.ff.kind[c.ff.n] = ff->terms[i].kind; c.ff.a[c.ff.n] = ff->terms[i].a; c.ff.b[c.ff.n] = ff->terms[i].b;
+            c.ff.c[c.ff.n] = ff->terms[i].c; c.ff.d[c.ff.n] = ff->terms[i].d; c.ff.n++;
+        }
+}
+
+void build_stage_table(SfgWorld* w) {
+    auto& s = w->h_stages;
+    s.clear();
+    auto add = [&](uint32_t kind, uint32_t b, uint32_t e) { if (e > b) s.push_back(Stage{kind, b, e, 0}); };
+    add(ST_INTEGRATE, 0, w->n_bodies);
+    if (w->n_ropes) for (int c = 0; c < 3; ++c) add(ST_ROPE_STEP, w->rope_colour_start[c], w->rope_colour_start[c + 1]);
+    for (uint32_t c = 0; c < w->n_k_colours; ++c) add(ST_CONSTRAINTS, w->k_colour_start[c], w->k_colour_start[c + 1]);
+    if (w->n_ropes && w->n_units) add(ST_PRECONTACT, 0, w->n_particles);
+    for (uint32_t c = 0; c < w->n_unit_colours; ++c) add(ST_CONTACTS, w->unit_colour_start[c], w->unit_colour_start[c + 1]);
+    add(ST_DERIVE, 0, w->n_bodies);
+    for (uint32_t c = 0; c < w->n_unit_colours; ++c) add(ST_CONTACT_VEL, w->unit_colour_start[c], w->unit_colour_start[c + 1]);
+    for (uint32_t c = 0; c < w->n_k_colours; ++c) add(ST_CONSTRAINT_DAMP, w->k_colour_start[c], w->k_colour_start[c + 1]);
+    if (w->n_ropes) {
+        for (int c = 0; c < 2; ++c) add(ST_ROPE_DAMP, w->damp_colour_start[c], w->damp_colour_start[c + 1]);
+        add(ST_ROPE_LATERAL, 0, w->n_particles);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff) {
+    if (!w) return SFG_E_INVALID;
+    if (!(frame_dt > 0.0)) return fail(w, SFG_E_INVALID, "frame_dt must be > 0");
+    if (ff && ff->n_terms > 4) return fail(w, SFG_E_INVALID, "force field: at most 4 terms");
+    int rc = ensure_device(w->device);
+    if (rc != SFG_OK) return fail(w, rc, "no CUDA device (there is no CPU fallback)");
+    cudaStream_t st = w->stream;
+    // physics.rs:404-418
+    uint32_t substeps;
+    double dt;
+    if (!has_time_scale) { substeps = w->tuning.substeps; dt = frame_dt / double(substeps); }
+    else {
+        substeps = uint32_t(std::ceil(time_scale * double(w->tuning.substeps)));
+        dt = time_scale * frame_dt / double(substeps);
+    }
+    w->launches = 0;
+    CK(cudaEventRecord(w->ev[0], st));
+    if (w->n_bodies) CK(cudaMemsetAsync(w->EA.p, 0, size_t(w->n_bodies) * sizeof(float2), st));
+    if (w->n_ropes) CK(cudaMemsetAsync(w->LAT.p, 0xFF, size_t(w->n_bodies) * sizeof(float2), st));
+    rc = broadphase(w, float(frame_dt));
+    if (rc != SFG_OK) return rc;
+    CK(cudaEventRecord(w->ev[1], st));
+    rc = build_graph(w);
+    if (rc != SFG_OK) return rc;
+    CK(cudaEventRecord(w->ev[2], st));
+
+    if (substeps > 0 && w->n_bodies) {
+        SolverCtx ctx;
+        fill_ctx(w, ctx, float(dt), ff);
+        build_stage_table(w);
+        if (w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES) {
+            for (uint32_t s = 0; s < substeps; ++s)
+                for (const Stage& sg : w->h_stages) { rc = launch_stage_dyn(w, ctx, sg, s + 1 == substeps); if (rc != SFG_OK) return rc; }
+        } else {
+            const uint32_t ns = uint32_t(w->h_stages.size());
+            CK(w->d_stages.ensure(ns));
+            CK(cudaMemcpyAsync(w->d_stages.p, w->h_stages.data(), ns * sizeof(Stage), cudaMemcpyHostToDevice, st));
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, 256, 0));
+            if (per_sm < 1) return fail(w, SFG_E_CUDA, "persistent solver kernel does not fit on an SM");
+            uint32_t max_range = 0;
+            for (const Stage& sg : w->h_stages) max_range = std::max(max_range, sg.end - sg.begin);
+            const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range)));
+            const Stage* dst = w->d_stages.p;
+            uint32_t n_stages = ns, n_sub = substeps;
+            void* args[] = {&ctx, (void*)&dst, &n_stages, &n_sub};
+            CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(256), args, 0, st));
+            w->launches++;
+        }
+    }
+    CK(cudaEventRecord(w->ev[3], st));
+    CK(cudaStreamSynchronize(st));
+    w->ticked = true;
+    // stats
+    SfgStats& s = w->stats;
+    memset(&s, 0, sizeof(s));
+    s.n_bodies = w->n_bodies; s.n_colliders = w->n_live; s.n_pairs = w->n_units;
+    s.n_constraint_entries = 0;
+    s.n_contact_colours = w->n_unit_colours; s.n_constraint_colours = w->n_k_colours;
+    s.n_rope_particles = w->n_particles; s.n_ropes = w->n_ropes; s.substeps = substeps;
+    s.grid_levels = uint32_t(w->grid.n_levels); s.grid_cells = w->grid.n_cells; s.cell_size = w->grid.cell[0];
+    s.kernel_launches = w->launches;
+    cudaEventElapsedTime(&s.ms_broadphase, w->ev[0], w->ev[1]);
+    cudaEventElapsedTime(&s.ms_graph, w->ev[1], w->ev[2]);
+    cudaEventElapsedTime(&s.ms_solver, w->ev[2], w->ev[3]);
+    cudaEventElapsedTime(&s.ms_total, w->ev[0], w->ev[3]);
+    s.reserved[0] = uint32_t(w->h_stages.size());
+    return SFG_OK;
+}
+
+int sfg_get_stats(SfgWorld* w, SfgStats* out) {
+    if (!w || !out) return SFG_E_INVALID;
+    *out = w->stats;
+    return SFG_OK;
+}
+
+int sfg_get_bodies(SfgWorld* w, uint32_t first, uint32_t count, SfgBody* out) {
+    if (!w || (count && !out)) return SFG_E_INVALID;
+    if (uint64_t(first) + count > w->n_bodies) return fail(w, SFG_E_INVALID, "body slot range out of bounds");
+    if (count == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(count) * sizeof(SfgBody)));
+    k_pack_bodies<<<nblk(count), 256, 0, st>>>((SfgBody*)w->stage.p, count, first, w->P.p, w->Q.p, w->V.p, w->MI.p);
+    CKL(w);
+    CK(cudaMemcpyAsync(out, w->stage.p, size_t(count) * sizeof(SfgBody), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+int sfg_get_contacts(SfgWorld* w, SfgContactInfo* out, size_t capacity, size_t* n_out) {
+    if (!w || !n_out) return SFG_E_INVALID;
+    *n_out = 0;
+    if (!w->ticked || w->n_units == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    const uint32_t n_entries = w->n_units * 2;
+    const uint32_t cap = uint32_t(std::min<size_t>(capacity, n_entries));
+    CK(w->stage.ensure(size_t(cap) * sizeof(SfgContactInfo) + 16));
+    uint32_t* cnt = (uint32_t*)w->stage.p;
+    SfgContactInfo* buf = (SfgContactInfo*)(w->stage.p + 16);
+    CK(cudaMemsetAsync(cnt, 0, 4, st));
+    k_collect_contacts<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->LN.p, w->S.p, buf, cap, cnt);
+    CKL(w);
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, cnt, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t got = std::min(total, cap);
+    if (got && out) { CK(cudaMemcpyAsync(out, buf, size_t(got) * sizeof(SfgContactInfo), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st)); }
+    *n_out = total;   // total found; only min(total, capacity) were written
+    return SFG_OK;
+}
+
+static int fill_cast_ctx(SfgWorld* w, CastCtx& c) {
+    if (!w->ticked) return fail(w, SFG_E_STATE, "queries use the spatial index of the last tick: call sfg_tick first");
+    c.g = w->grid; c.SA = w->SA.p; c.SI = w->SI.p; c.start = w->cell_start.p;
+    c.CS = w->CS.p; c.CL = w->CL.p; c.CI = w->CI.p; c.P = w->P.p; c.Q = w->Q.p;
+    return SFG_OK;
+}
+
+int sfg_cast_batch(SfgWorld* w, uint32_t n, const SfgRay* rays, SfgCastHit* out) {
+    if (!w || (n && (!rays || !out))) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    CastCtx c;
+    int rc = fill_cast_ctx(w, c);
+    if (rc != SFG_OK) return rc;
+    cudaStream_t st = w->stream;
+    if (w->n_live == 0) { for (uint32_t i = 0; i < n; ++i) { memset(&out[i], 0, sizeof(SfgCastHit)); out[i].collider = -1; } return SFG_OK; }
+    CK(w->d_rays.ensure(n)); CK(w->d_hits.ensure(n));
+    CK(cudaMemcpyAsync(w->d_rays.p, rays, size_t(n) * sizeof(SfgRay), cudaMemcpyHostToDevice, st));
+    k_cast_batch<<<nblk(n, 128), 128, 0, st>>>(c, n, w->d_rays.p, w->d_hits.p);
+    CKL(w);
+    CK(cudaMemcpyAsync(out, w->d_hits.p, size_t(n) * sizeof(SfgCastHit), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+int sfg_query_point_batch(SfgWorld* w, uint32_t n, const float* points_xy, const uint32_t* domains, uint32_t max_hits, int32_t* out_colliders,
+                          uint32_t* out_counts) {
+    if (!w || (n && (!points_xy || !out_colliders || !out_counts)) || max_hits == 0) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    CastCtx c;
+    int rc = fill_cast_ctx(w, c);
+    if (rc != SFG_OK) return rc;
+    cudaStream_t st = w->stream;
+    if (w->n_live == 0) { for (uint32_t i = 0; i < n; ++i) out_counts[i] = 0; for (size_t i = 0; i < size_t(n) * max_hits; ++i) out_colliders[i] = -1; return SFG_OK; }
+    const size_t b_pts = size_t(n) * 8, b_dom = size_t(n) * 4, b_out = size_t(n) * max_hits * 4, b_cnt = size_t(n) * 4;
+    CK(w->stage.ensure(b_pts + b_dom + b_out + b_cnt + 64));
+    unsigned char* p = w->stage.p;
+    float2* d_pts = (float2*)p; uint32_t* d_dom = (uint32_t*)(p + b_pts); int* d_out = (int*)(p + b_pts + b_dom); uint32_t* d_cnt = (uint32_t*)(p + b_pts + b_dom + b_out);
+    CK(cudaMemcpyAsync(d_pts, points_xy, b_pts, cudaMemcpyHostToDevice, st));
+    if (domains) CK(cudaMemcpyAsync(d_dom, domains, b_dom, cudaMemcpyHostToDevice, st));
+    k_query_point<<<nblk(n, 128), 128, 0, st>>>(c, n, d_pts, domains ? d_dom : nullptr, max_hits, d_out, d_cnt);
+    CKL(w);
+    CK(cudaMemcpyAsync(out_colliders, d_out, b_out, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_counts, d_cnt, b_cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+// ---------------------------------------------------------------- parity hooks
+int sfg_debug_get_pairs(SfgWorld* w, uint32_t* out_pairs, size_t capacity_pairs, size_t* n_out) {
+    if (!w || !n_out) return SFG_E_INVALID;
+    *n_out = w->n_units;
+    if (!out_pairs || w->n_units == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    const size_t n = std::min<size_t>(capacity_pairs, w->n_units);
+    CK(cudaMemcpyAsync(out_pairs, w->U_ids.p, n * sizeof(uint2), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return SFG_OK;
+}
+// pair units in the solver's colour-major order: hi, lo | mult2 << 31, colour
+int sfg_debug_get_contact_entries(SfgWorld* w, uint32_t* out_hi, uint32_t* out_lo_copy, uint32_t* out_colour, size_t capacity, size_t* n_out) {
+    if (!w || !n_out) return SFG_E_INVALID;
+    *n_out = w->n_units;
+    if (w->n_units == 0 || !out_hi || !out_lo_copy || !out_colour) return SFG_OK;
+    if (capacity < w->n_units) return fail(w, SFG_E_CAPACITY, "capacity < number of pair units");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    const uint32_t n = w->n_units;
+    CK(w->stage.ensure(size_t(n) * 8));
+    uint32_t* d_hi = (uint32_t*)w->stage.p; uint32_t* d_lo = d_hi + n;
+    k_export_units<<<nblk(n), 256, 0, st>>>(n, w->H.p, w->S.p, d_hi, d_lo);
+    CKL(w);
+    CK(cudaMemcpyAsync(out_hi, d_hi, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_lo_copy, d_lo, size_t(n) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t c = 0; c < w->n_unit_colours; ++c)
+        for (uint32_t u = w->unit_colour_start[c]; u < w->unit_colour_start[c + 1]; ++u) out_colour[u] = c;
+    return SFG_OK;
+}
+// constraint units in colour-major order: index | mult2 << 31, colour
+int sfg_debug_get_constraint_entries(SfgWorld* w, uint32_t* out_index_copy, uint32_t* out_colour, size_t capacity, size_t* n_out) {
+    if (!w || !n_out) return SFG_E_INVALID;
+    *n_out = w->n_kunits;
+    if (w->n_kunits == 0 || !out_index_copy || !out_colour) return SFG_OK;
+    if (capacity < w->n_kunits) return fail(w, SFG_E_CAPACITY, "capacity < number of constraint units");
+    cudaSetDevice(w->device);
+    std::vector<float4> k0(w->n_kunits);
+    CK(cudaMemcpyAsync(k0.data(), w->K0.p, size_t(w->n_kunits) * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    for (uint32_t u = 0; u < w->n_kunits; ++u) {
+        uint32_t idx; int32_t target;
+        memcpy(&idx, &k0[u].w, 4); memcpy(&target, &k0[u].y, 4);
+        out_index_copy[u] = idx | (target >= 0 ? 0x80000000u : 0u);
+    }
+    for (uint32_t c = 0; c < w->n_k_colours; ++c)
+        for (uint32_t u = w->k_colour_start[c]; u < w->k_colour_start[c + 1]; ++u) out_colour[u] = c;
+    return SFG_OK;
+}
+// per contact entry (entry = copy * n_units + unit): hi, lo, count, lambda_n, normal.xy, 2 x (offsets[0].xy, offsets[1].xy) = 14 floats
+int sfg_debug_get_manifolds(SfgWorld* w, float* out, size_t capacity_entries, size_t* n_out) {
+    if (!w || !n_out) return SFG_E_INVALID;
+    const uint32_t n_entries = w->n_units * 2;
+    *n_out = n_entries;
+    if (n_entries == 0 || !out) return SFG_OK;
+    if (capacity_entries < n_entries) return fail(w, SFG_E_CAPACITY, "capacity < number of contact entries");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(n_entries) * 14 * 4));
+    k_export_manifolds<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->S.p, w->M0.p, w->M1.p, w->M2.p, (float*)w->stage.p);
+    CKL(w);
+    CK(cudaMemcpyAsync(out, w->stage.p, size_t(n_entries) * 14 * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+int sfg_debug_get_aabbs(SfgWorld* w, float* out, size_t capacity_colliders) {
+    if (!w || !out) return SFG_E_INVALID;
+    const size_t n = std::min<size_t>(capacity_colliders, w->n_colls);
+    if (n == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    CK(cudaMemcpyAsync(out, w->AABB.p, n * sizeof(float4), cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    return SFG_OK;
+}
+
+static int dbg_run(int device, size_t in_a_bytes, const void* in_a, size_t in_b_bytes, const void* in_b, size_t in_c_bytes, const void* in_c,
+                   size_t out_bytes, void* out, void (*launch)(void*, void*, void*, void*, void*), void* user) {
+    int rc = ensure_device(device);
+    if (rc != SFG_OK) return rc;
+    void *a = nullptr, *b = nullptr, *c = nullptr, *o = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (in_a_bytes) e = cudaMalloc(&a, in_a_bytes);
+    if (e == cudaSuccess && in_b_bytes) e = cudaMalloc(&b, in_b_bytes);
+    if (e == cudaSuccess && in_c_bytes) e = cudaMalloc(&c, in_c_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&o, out_bytes);
+    if (e == cudaSuccess && in_a_bytes) e = cudaMemcpy(a, in_a, in_a_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && in_b_bytes) e = cudaMemcpy(b, in_b, in_b_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && in_c_bytes) e = cudaMemcpy(c, in_c, in_c_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) { launch(a, b, c, o, user); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(out, o, out_bytes, cudaMemcpyDeviceToHost);
+    cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(o);
+    return e == cudaSuccess ? SFG_OK : SFG_E_CUDA;
+}
+// out rows of 14: count, 0, normal.xy, 2 x (offsets[0].xy, offsets[1].xy), pad
+int sfg_debug_intersection_check(int device, uint32_t n, const float* poses, const float* shapes, float* out) {
+    if (!poses || !shapes || !out) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    uint32_t nn = n;
+    return dbg_run(device, size_t(n) * 32, poses, size_t(n) * 32, shapes, 0, nullptr, size_t(n) * 56, out,
+                   [](void* a, void* b, void*, void* o, void* u) { uint32_t n = *(uint32_t*)u; k_dbg_isect<<<nblk(n), 256>>>(n, (const float*)a, (const float*)b, (float*)o); }, &nn);
+}
+int sfg_debug_spherecast_collider(int device, uint32_t n, const SfgRay* rays, const float* poses, const float* shapes, float* out) {
+    if (!rays || !poses || !shapes || !out) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    uint32_t nn = n;
+    return dbg_run(device, size_t(n) * sizeof(SfgRay), rays, size_t(n) * 16, poses, size_t(n) * 16, shapes, size_t(n) * 24, out,
+                   [](void* a, void* b, void* c, void* o, void* u) { uint32_t n = *(uint32_t*)u; k_dbg_cast<<<nblk(n), 256>>>(n, (const SfgRay*)a, (const float*)b, (const float*)c, (float*)o); }, &nn);
+}
+int sfg_debug_geometry(int device, uint32_t op, uint32_t n, const float* args, const float* shapes, float* out) {
+    if (!args || !shapes || !out || op > 3) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    uint32_t u[2] = {n, op};
+    return dbg_run(device, size_t(n) * 8, args, size_t(n) * 16, shapes, 0, nullptr, size_t(n) * 28, out,
+                   [](void* a, void* b, void*, void* o, void* uu) { uint32_t* u = (uint32_t*)uu; k_dbg_geometry<<<nblk(u[0]), 256>>>(u[1], u[0], (const float*)a, (const float*)b, (float*)o); }, u);
+}
+
+}  // extern "C"

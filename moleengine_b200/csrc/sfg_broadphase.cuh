@@ -1,0 +1,358 @@
+// Spatial-hash broadphase and constraint-graph build (once per tick).
+//   k_aabb            tick-time AABB per collider (bit-exact f32 restatement of physics.rs:447-459) + world bounds
+//   k_cell_keys       hierarchical uniform grid: level by AABB extent, key = cell of the AABB centre
+//   radix sort        sfg_sort.cuh
+//   k_gather_sorted / k_cell_starts
+//   k_pairs<EMIT>     one lane per collider, 3x3 cells on its own and every coarser level; candidate
+//                     tests = strict AABB overlap + layer mask + same domain + ">=1 body, distinct
+//                     bodies" (physics.rs:461-474, 551-555, 579); hits compacted with warp ballots
+//   k_unit_setup / k_adj_fill / k_jp_colour / k_build_units   graph colouring (include/sfg_hash.h)
+// The emitted SET equals the reference's BVH result; the order does not.
+#pragma once
+#include <cooperative_groups.h>
+#include "../../include/sfg_hash.h"
+#include "sfg_geom.cuh"
+#include "sfg_state.cuh"
+
+namespace sfg {
+namespace cg = cooperative_groups;
+
+SFG_DI int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+inline float ord2f_host(int i) { int j = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy(&f, &j, 4); return f; }
+
+__global__ void __launch_bounds__(256) k_aabb(uint32_t n_colls, const float4* __restrict__ CS, const float4* __restrict__ CL,
+                                              const int4* __restrict__ CI, const float4* __restrict__ P, const float4* __restrict__ Q,
+                                              const float4* __restrict__ V, float frame_dt, float pad, float4* __restrict__ AABB,
+                                              Bounds* __restrict__ bounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = false;
+    float4 box = make_float4(0, 0, 0, 0);
+    uint32_t domain = 0;
+    if (i < n_colls) {
+        const int4 ci = CI[i];
+        if (ci.w & CF_ALIVE) {
+            live = true;
+            domain = uint32_t(ci.z);
+            const Shape s = mkshape(CS[i]);
+            const float4 l = CL[i];
+            if (ci.x >= 0) {
+                const float4 p = P[ci.x], q = Q[ci.x], v = V[ci.x];
+                const V2 bt = mk(__fadd_rn(p.x, p.z), __fadd_rn(p.y, p.w));
+                const Rot br = mkrot(q.x, q.y);
+                // body.pose * coll.pose
+                V2 rt = rot_apply_exact(br, mk(l.x, l.y));
+                V2 t = mk(__fadd_rn(rt.x, bt.x), __fadd_rn(rt.y, bt.y));
+                Rot r = rot_mul_exact(br, mkrot(l.z, l.w));
+                box = shape_aabb_exact(s, t, r);
+                const float ex = __fmul_rn(v.x, frame_dt), ey = __fmul_rn(v.y, frame_dt);   // collision.rs:49-63
+                if (ex < 0.f) box.x = __fadd_rn(box.x, ex); else box.z = __fadd_rn(box.z, ex);
+                if (ey < 0.f) box.y = __fadd_rn(box.y, ey); else box.w = __fadd_rn(box.w, ey);
+                box.x = __fsub_rn(box.x, pad); box.y = __fsub_rn(box.y, pad);                // collision.rs:39-46
+                box.z = __fadd_rn(box.z, pad); box.w = __fadd_rn(box.w, pad);
+            } else {
+                box = shape_aabb_exact(s, mk(l.x, l.y), mkrot(l.z, l.w));
+            }
+            AABB[i] = box;
+        }
+    }
+    // bounds: warp reduce, one atomic per warp
+    const bool fin = live && isfinite(box.x) && isfinite(box.y) && isfinite(box.z) && isfinite(box.w);
+    float mnx = fin ? box.x : 3.0e38f, mny = fin ? box.y : 3.0e38f, mxx = fin ? box.z : -3.0e38f, mxy = fin ? box.w : -3.0e38f;
+    float ext = fin ? fmaxf(box.z - box.x, box.w - box.y) : 0.f;
+    float sum = ext;
+    uint32_t cnt = fin ? 1u : 0u, dom = live ? domain : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fminf(mnx, __shfl_xor_sync(0xFFFFFFFFu, mnx, o)); mny = fminf(mny, __shfl_xor_sync(0xFFFFFFFFu, mny, o));
+        mxx = fmaxf(mxx, __shfl_xor_sync(0xFFFFFFFFu, mxx, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o));
+        ext = fmaxf(ext, __shfl_xor_sync(0xFFFFFFFFu, ext, o)); sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); dom = max(dom, __shfl_xor_sync(0xFFFFFFFFu, dom, o));
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMin(&bounds->min_x, f2ord(mnx)); atomicMin(&bounds->min_y, f2ord(mny));
+        atomicMax(&bounds->max_x, f2ord(mxx)); atomicMax(&bounds->max_y, f2ord(mxy));
+        atomicMax(&bounds->max_extent, f2ord(ext));
+        atomicMax(&bounds->max_domain, dom);
+        atomicAdd(&bounds->n_live, cnt);
+        atomicAdd(&bounds->sum_extent, double(sum));
+    }
+}
+
+SFG_DI int level_of(const GridParams& g, float ext) {
+    int l = 0;
+    while (l < g.n_levels && !(ext <= g.cell[l])) ++l;
+    return l;   // == n_levels -> huge list
+}
+SFG_DI void cell_of(const GridParams& g, int l, float cx, float cy, int* ix, int* iy) {
+    int x = int(floorf((cx - g.ox) * g.inv_cell[l])), y = int(floorf((cy - g.oy) * g.inv_cell[l]));
+    *ix = min(max(x, 0), g.nx[l] - 1);
+    *iy = min(max(y, 0), g.ny[l] - 1);
+}
+
+__global__ void __launch_bounds__(256) k_cell_keys(const __grid_constant__ GridParams g, uint32_t n_colls, const float4* __restrict__ AABB,
+                                                   const int4* __restrict__ CI, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_colls) return;
+    const int4 ci = CI[i];
+    uint32_t key = 0xFFFFFFFFu;
+    if (ci.w & CF_ALIVE) {
+        const float4 b = AABB[i];
+        const float ext = fmaxf(b.z - b.x, b.w - b.y);
+        if (isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w)) {
+            const int l = level_of(g, ext);
+            if (l >= g.n_levels) key = g.n_cells;
+            else {
+                int ix, iy;
+                cell_of(g, l, 0.5f * (b.x + b.z), 0.5f * (b.y + b.w), &ix, &iy);
+                key = g.base[l] + (uint32_t(ci.z) * uint32_t(g.ny[l]) + uint32_t(iy)) * uint32_t(g.nx[l]) + uint32_t(ix);
+            }
+        }
+    }
+    keys[i] = key;
+    vals[i] = i;
+}
+
+// sorted copies so the pair search streams instead of gathering: SA = box, SI = (slot, body, layer | level << 8, domain)
+__global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ GridParams g, uint32_t n, const uint32_t* __restrict__ keys,
+                                                       const uint32_t* __restrict__ vals, const float4* __restrict__ AABB,
+                                                       const int4* __restrict__ CI, float4* __restrict__ SA, int4* __restrict__ SI) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t slot = vals[j];
+    const uint32_t key = keys[j];
+    const int4 ci = CI[slot];
+    int level = g.n_levels;
+    for (int l = 0; l < g.n_levels; ++l) if (key >= g.base[l]) level = l;
+    if (key >= g.n_cells) level = g.n_levels;
+    SA[j] = AABB[slot];
+    SI[j] = make_int4(int(slot), ci.x, ci.y | (level << 8), ci.z);
+}
+
+// start[c] = first sorted index whose key >= c, for c in [0, n_cells + 1]; start[n_cells + 1] = number of live entries
+__global__ void __launch_bounds__(256) k_cell_starts(const uint32_t* __restrict__ keys, uint32_t n, uint32_t n_cells, uint32_t* __restrict__ start) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > n) return;
+    // virtual key n_cells + 1 after the last live entry
+    uint32_t k = j < n ? min(keys[j], n_cells + 1) : n_cells + 1;
+    uint32_t kp = j == 0 ? 0u : min(keys[j - 1], n_cells + 1) + 1u;
+    if (j == 0) kp = 0u;
+    for (uint32_t cidx = kp; cidx <= k; ++cidx) start[cidx] = j;
+}
+// empty world: every start is 0
+__global__ void k_fill_u32(uint32_t* p, uint32_t n, uint32_t v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParams g, uint32_t n_live, const float4* __restrict__ SA,
+                                               const int4* __restrict__ SI, const uint32_t* __restrict__ start,
+                                               const unsigned long long* __restrict__ mask, uint32_t* __restrict__ warp_counts,
+                                               const uint32_t* __restrict__ warp_offsets, uint2* __restrict__ pairs, uint32_t capacity) {
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t j = gw * 32 + lane;
+    const bool active = j < n_live;
+    float4 A = make_float4(0, 0, 0, 0);
+    int4 I = make_int4(0, -1, 0, 0);
+    if (active) { A = SA[j]; I = SI[j]; }
+    const int my_level = (I.z >> 8) & 0xFF, my_layer = I.z & 0xFF;
+    const float cx = 0.5f * (A.x + A.z), cy = 0.5f * (A.y + A.w);
+    const unsigned long long my_mask = active ? mask[my_layer] : 0ull;
+    // segments: for level l in [my_level, n_levels): rows -1, 0, +1; then the huge list
+    const int n_seg = active ? (max(g.n_levels - my_level, 0) * 3 + 1) : 0;
+    int seg = 0;
+    uint32_t cur = 0, end = 0;
+    uint32_t total = 0;
+    const uint32_t base = EMIT ? warp_offsets[gw] : 0u;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (;;) {
+        while (cur >= end && seg < n_seg) {
+            if (seg == n_seg - 1) { cur = start[g.n_cells]; end = start[g.n_cells + 1]; }
+            else {
+                const int l = min(my_level, g.n_levels) + seg / 3, dy = seg % 3 - 1;
+                int ix, iy;
+                cell_of(g, l, cx, cy, &ix, &iy);
+                const int y = iy + dy;
+                if (y >= 0 && y < g.ny[l]) {
+                    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, g.nx[l] - 1);
+                    const uint32_t row = g.base[l] + (uint32_t(I.w) * uint32_t(g.ny[l]) + uint32_t(y)) * uint32_t(g.nx[l]);
+                    cur = start[row + x0]; end = start[row + x1 + 1];
+                } else { cur = 0; end = 0; }
+            }
+            ++seg;
+        }
+        const bool more = cur < end;
+        if (!__any_sync(0xFFFFFFFFu, more)) break;
+        bool hit = false;
+        uint32_t hi = 0, lo = 0;
+        if (more) {
+            const uint32_t cj = cur++;
+            if (cj != j) {
+                const int4 J = SI[cj];
+                const int o_level = (J.z >> 8) & 0xFF;
+                // same level: the later slot emits; coarser level: we emit (the other never searches down)
+                const bool mine = o_level > my_level || (o_level == my_level && uint32_t(I.x) > uint32_t(J.x));
+                if (mine && J.w == I.w && aabb_overlap(A, SA[cj])) {
+                    hi = max(uint32_t(I.x), uint32_t(J.x)); lo = min(uint32_t(I.x), uint32_t(J.x));
+                    const int l_hi = uint32_t(I.x) > uint32_t(J.x) ? my_layer : (J.z & 0xFF);
+                    const int l_lo = uint32_t(I.x) > uint32_t(J.x) ? (J.z & 0xFF) : my_layer;
+                    const unsigned long long mrow = uint32_t(I.x) > uint32_t(J.x) ? my_mask : mask[l_hi];
+                    const bool bodies_ok = (I.y >= 0 || J.y >= 0) && !(I.y >= 0 && I.y == J.y);
+                    hit = ((mrow >> l_lo) & 1ull) && bodies_ok;
+                }
+            }
+        }
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
+        if (EMIT && hit) {
+            const uint32_t pos = base + total + __popc(ballot & lt);
+            if (pos < capacity) pairs[pos] = make_uint2(hi, lo);
+        }
+        total += __popc(ballot);
+    }
+    if (!EMIT && lane == 0) warp_counts[gw] = total;
+}
+
+// ---------------------------------------------------------------- graph colouring
+// unit = one candidate pair (or one user constraint); ub = its dynamic bodies (or -1); prio = sfg_hash3
+__global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const uint2* __restrict__ ids, const int4* __restrict__ CI,
+                                                         const float4* __restrict__ MI, int2* __restrict__ ub, uint32_t* __restrict__ prio,
+                                                         uint32_t* __restrict__ deg) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const uint2 id = ids[u];
+    int b0 = CI[id.x].x, b1 = CI[id.y].x;
+    if (b0 >= 0 && !(__float_as_uint(MI[b0].z) & (BF_MASS | BF_INERTIA))) b0 = -1;
+    if (b1 >= 0 && !(__float_as_uint(MI[b1].z) & (BF_MASS | BF_INERTIA))) b1 = -1;
+    ub[u] = make_int2(b0, b1);
+    prio[u] = sfg_hash3(id.x, id.y, 0u);
+    if (b0 >= 0) atomicAdd(deg + b0, 1u);
+    if (b1 >= 0) atomicAdd(deg + b1, 1u);
+}
+__global__ void __launch_bounds__(256) k_constraint_unit_setup(uint32_t n_units, const int4* __restrict__ KI /* owner, target, flags, - */,
+                                                               const float4* __restrict__ MI, uint2* __restrict__ ids, int2* __restrict__ ub,
+                                                               uint32_t* __restrict__ prio, uint32_t* __restrict__ deg) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    int b0 = KI[u].x, b1 = KI[u].y;
+    if (b0 >= 0 && !(__float_as_uint(MI[b0].z) & (BF_MASS | BF_INERTIA))) b0 = -1;
+    if (b1 >= 0 && !(__float_as_uint(MI[b1].z) & (BF_MASS | BF_INERTIA))) b1 = -1;
+    ids[u] = make_uint2(u, 0u);
+    ub[u] = make_int2(b0, b1);
+    prio[u] = sfg_hash3(u, SFG_CONSTRAINT_TAG, 0u);
+    if (b0 >= 0) atomicAdd(deg + b0, 1u);
+    if (b1 >= 0) atomicAdd(deg + b1, 1u);
+}
+__global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ adj_start,
+                                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ adj) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const int2 b = ub[u];
+    if (b.x >= 0) adj[adj_start[b.x] + atomicAdd(cursor + b.x, 1u)] = u;
+    if (b.y >= 0) adj[adj_start[b.y] + atomicAdd(cursor + b.y, 1u)] = u;
+}
+
+constexpr uint32_t UNCOLOURED = 0xFFFFFFFFu;
+constexpr uint32_t JP_MAX_ROUNDS = 8192;
+
+// Jones-Plassmann: a unit takes the smallest colour unused by its higher-priority neighbours once all of
+// them are coloured; the fixed point equals greedy colouring in descending priority (what the oracle runs).
+// counters[0 .. JP_MAX_ROUNDS) = units left per round, counters[JP_MAX_ROUNDS] = max colour + 1,
+// hist = units per colour.
+__global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
+                                                   const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
+                                                   const uint32_t* __restrict__ adj, uint32_t* colour, uint32_t* counters,
+                                                   uint32_t* hist, uint32_t hist_cap) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t round = 0; round < JP_MAX_ROUNDS; ++round) {
+        uint32_t pending = 0;
+        for (uint32_t u = tid; u < n_units; u += nth) {
+            if (__ldcg(colour + u) != UNCOLOURED) continue;
+            const int2 b = ub[u];
+            const uint32_t pu = prio[u];
+            const uint2 iu = ids[u];
+            bool ready = true;
+            uint32_t result = 0;
+            // window of 64 colours at a time
+            for (uint32_t win = 0; ready; win += 64) {
+                unsigned long long used = 0ull;
+                bool beyond = false;
+                for (int side = 0; side < 2 && ready; ++side) {
+                    const int body = side ? b.y : b.x;
+                    if (body < 0) continue;
+                    const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
+                    for (uint32_t a = a0; a < a1; ++a) {
+                        const uint32_t v = adj[a];
+                        if (v == u) continue;
+                        const uint32_t pv = prio[v];
+                        bool higher = pv > pu;
+                        if (pv == pu) { const uint2 iv = ids[v]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
+                        if (!higher) continue;
+                        const uint32_t cv = __ldcg(colour + v);
+                        if (cv == UNCOLOURED) { ready = false; break; }
+                        if (cv >= win && cv < win + 64) used |= 1ull << (cv - win);
+                        else if (cv >= win + 64) beyond = true;
+                    }
+                }
+                if (!ready) break;
+                if (used != ~0ull) { result = win + uint32_t(__ffsll((long long)~used) - 1); break; }
+                if (!beyond) { result = win + 64; break; }
+            }
+            if (ready) {
+                __stcg(colour + u, result);
+                atomicMax(counters + JP_MAX_ROUNDS, result + 1u);
+                if (result < hist_cap) atomicAdd(hist + result, 1u);
+            } else ++pending;
+        }
+        if (pending) atomicAdd(counters + round, pending);
+        grid.sync();
+        if (__ldcg(counters + round) == 0u) break;
+    }
+}
+
+// after the stable sort by colour: write the streaming columns of each pair unit
+__global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, const uint32_t* __restrict__ perm, const uint2* __restrict__ ids,
+                                                          const float4* __restrict__ CS, const float4* __restrict__ CL,
+                                                          const float4* __restrict__ CM, const int4* __restrict__ CI,
+                                                          const float4* __restrict__ MI, const int* __restrict__ rope_next,
+                                                          const int* __restrict__ rope_prev, float4* __restrict__ H, float4* __restrict__ S,
+                                                          float4* __restrict__ G0, float4* __restrict__ G1, float4* __restrict__ L0,
+                                                          float4* __restrict__ L1) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_units) return;
+    const uint2 id = ids[perm[s]];
+    const int4 c0 = CI[id.x], c1 = CI[id.y];
+    const float4 m0 = CM[id.x], m1 = CM[id.y];
+    const uint32_t f0 = uint32_t(c0.w), f1 = uint32_t(c1.w);
+    uint32_t fl = 0;
+    if (c0.x >= 0 && c1.x >= 0) fl |= UF_MULT2;
+    if ((f0 | f1) & CF_SENSOR) fl |= UF_SENSOR;
+    if ((f0 & f1) & CF_HAS_SF) fl |= UF_HAS_SF;
+    if ((f0 & f1) & CF_HAS_DF) fl |= UF_HAS_DF;
+    if (c0.x >= 0) {
+        if (__float_as_uint(MI[c0.x].z) & (BF_MASS | BF_INERTIA)) fl |= UF_SEES0;
+        if (rope_next && rope_next[c0.x] >= 0 && rope_prev[c0.x] >= 0) fl |= UF_ROPE0;
+    }
+    if (c1.x >= 0) {
+        if (__float_as_uint(MI[c1.x].z) & (BF_MASS | BF_INERTIA)) fl |= UF_SEES1;
+        if (rope_next && rope_next[c1.x] >= 0 && rope_prev[c1.x] >= 0) fl |= UF_ROPE1;
+    }
+    H[s] = make_float4(__int_as_float(c0.x), __int_as_float(c1.x), __uint_as_float(fl), (m0.x + m1.x) / 2.0f);
+    S[s] = make_float4(__uint_as_float(id.x), __uint_as_float(id.y), (m0.y + m1.y) / 2.0f, fmaxf(m0.z, m1.z));
+    G0[s] = CS[id.x]; G1[s] = CS[id.y];
+    L0[s] = CL[id.x]; L1[s] = CL[id.y];
+}
+__global__ void __launch_bounds__(256) k_build_constraint_units(uint32_t n_units, const uint32_t* __restrict__ perm, const int4* __restrict__ KI,
+                                                                const float4* __restrict__ KA, const float4* __restrict__ KB,
+                                                                float4* __restrict__ K0, float4* __restrict__ K1, float4* __restrict__ K2) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_units) return;
+    const uint32_t u = perm[s];
+    const int4 ki = KI[u];
+    K0[s] = make_float4(__int_as_float(ki.x), __int_as_float(ki.y), __int_as_float(ki.z), __uint_as_float(u));
+    K1[s] = KA[u];
+    K2[s] = KB[u];
+}
+
+}  // namespace sfg

@@ -1,0 +1,435 @@
+// XPBD substep stages (one thread per body / per constraint unit of a colour) and the two ways of
+// driving them: one launch per stage, or a single persistent cooperative kernel with grid-wide
+// barriers between stages. Restates /root/reference/src/physics/solver.rs stage by stage; the
+// Gauss-Seidel order is colour-major (include/sfg_hash.h) instead of the reference's DFS order.
+#pragma once
+#include <cooperative_groups.h>
+#include "sfg_geom.cuh"
+#include "sfg_state.cuh"
+
+namespace sfg {
+namespace cg = cooperative_groups;
+
+// Body state is rewritten by other SMs between stages of the persistent kernel, so it always goes
+// through L2 (ld.cg / st.cg); per-tick constant streams use the read-only path.
+SFG_DI float4 ldb(const float4* p) { return __ldcg(p); }
+SFG_DI float2 ldb(const float2* p) { return __ldcg(p); }
+SFG_DI void stb(float4* p, float4 v) { __stcg(p, v); }
+SFG_DI void stb(float2* p, float2 v) { __stcg(p, v); }
+SFG_DI float4 ldc(const float4* p) { return __ldg(p); }
+
+// forcefield.rs
+SFG_DI V2 force_at(const ForceParams& ff, V2 pos) {
+    V2 acc = mk(0.f, 0.f);
+    for (uint32_t i = 0; i < ff.n; ++i) {
+        if (ff.kind[i] == 1u) acc = acc + mk(ff.a[i], ff.b[i]);
+        else if (ff.kind[i] == 2u) {
+            V2 dist = mk(ff.a[i], ff.b[i]) - pos;
+            float strength = ff.c[i] / ((mag_sq(dist) + 1.0f) * ff.d[i]);
+            acc = acc + strength * normalized(dist);
+        }
+    }
+    return acc;
+}
+
+// solver.rs:57-74 + physics.rs:78-83
+SFG_DI void stage_integrate(const SolverCtx& c, uint32_t i) {
+    float4 mi = ldb(c.MI + i);
+    const uint32_t fl = __float_as_uint(mi.z);
+    if (!(fl & BF_ALIVE)) return;
+    float4 p = ldb(c.P + i), q = ldb(c.Q + i), v = ldb(c.V + i);
+    V2 pos = mk(p.x + p.z, p.y + p.w);
+    if (!(fl & BF_NOGRAV) && (fl & BF_MASS)) {
+        V2 a = force_at(c.ff, pos);
+        v.x += a.x * c.dt; v.y += a.y * c.dt;
+        stb(c.EA + i, make_float2(a.x, a.y));
+    }
+    stb(c.OV + i, v);
+    stb(c.V + i, v);
+    Rot r = rot_from_angle(v.z * c.dt) * mkrot(q.x, q.y);
+    stb(c.P + i, make_float4(pos.x, pos.y, v.x * c.dt, v.y * c.dt));
+    stb(c.Q + i, make_float4(r.s, r.b, q.x, q.y));
+}
+
+// solver.rs:91-97 (+ fold of the displacement into the position after the last substep)
+SFG_DI void stage_derive(const SolverCtx& c, uint32_t i, bool fold) {
+    float4 mi = ldb(c.MI + i);
+    if (!(__float_as_uint(mi.z) & BF_ALIVE)) return;
+    float4 p = ldb(c.P + i), q = ldb(c.Q + i), v = ldb(c.V + i);
+    v.x = p.z * c.inv_dt; v.y = p.w * c.inv_dt;
+    Rot d = mkrot(q.x, q.y) * mkrot(q.z, -q.w);
+    v.z = (-atan2f(d.b, d.s) * 2.0f) * c.inv_dt;
+    stb(c.V + i, v);
+    if (fold) stb(c.P + i, make_float4(p.x + p.z, p.y + p.w, 0.f, 0.f));
+}
+SFG_DI void stage_fold(const SolverCtx& c, uint32_t i) {
+    float4 p = ldb(c.P + i);
+    stb(c.P + i, make_float4(p.x + p.z, p.y + p.w, 0.f, 0.f));
+}
+
+// ---------------------------------------------------------------- ropes (solver.rs:114-181)
+SFG_DI void stage_rope_step(const SolverCtx& c, uint32_t u) {
+    const int4 ru = c.RU[u];
+    const float4 pa = ldc(c.RPA + ru.w);
+    float4 pc = ldb(c.P + ru.x), pn = ldb(c.P + ru.y);
+    const float imc = ldb(c.MI + ru.x).x, imn = ldb(c.MI + ru.y).x;
+    V2 dist = mk((pn.x - pc.x) + (pn.z - pc.z), (pn.y - pc.y) + (pn.w - pc.w));
+    float dm = mag(dist);
+    V2 dir = mk(dist.x / dm, dist.y / dm);
+    float error = pa.x - dm;
+    float lambda = -error / (imc + imn + pa.y * c.inv_dt_sq);
+    pc.z += imc * lambda * dir.x; pc.w += imc * lambda * dir.y;
+    pn.z += -imn * lambda * dir.x; pn.w += -imn * lambda * dir.y;
+    stb(c.P + ru.x, pc);
+    stb(c.P + ru.y, pn);
+    if (ru.z < 0) return;
+    float4 pf = ldb(c.P + ru.z);
+    const float ima = ldb(c.MI + ru.z).x;
+    V2 c2n = mk((pn.x - pc.x) + (pn.z - pc.z), (pn.y - pc.y) + (pn.w - pc.w));
+    V2 n2a = mk((pf.x - pn.x) + (pf.z - pn.z), (pf.y - pn.y) + (pf.w - pn.w));
+    float angle = acosf(dot(normalized(n2a), normalized(c2n)));
+    float err = angle - pa.z;
+    if (err > 0.f) {
+        float lam = -err / (ima + pa.w * c.inv_dt_sq);
+        float lo = dot(left_normal(c2n), n2a) > 0.f ? lam : -lam;
+        Rot corr = rot_from_angle(lo * ima);
+        V2 na = corr * n2a;
+        // new position of `after`, expressed as a displacement from its own substep-start position
+        float ndx = (pn.x - pf.x) + pn.z + na.x, ndy = (pn.y - pf.y) + pn.w + na.y;
+        stb(c.LAT + ru.z, make_float2(ndx - pf.z, ndy - pf.w));
+        pf.z = ndx; pf.w = ndy;
+        stb(c.P + ru.z, pf);
+    }
+}
+// solver.rs:722-740
+SFG_DI void stage_rope_damp(const SolverCtx& c, uint32_t u) {
+    const int4 rd = c.RD[u];
+    const float damping = ldc(c.RPB + rd.z).x;
+    float4 vc = ldb(c.V + rd.x), vn = ldb(c.V + rd.y);
+    const float imc = ldb(c.MI + rd.x).x, imn = ldb(c.MI + rd.y).x;
+    V2 rel = mk(vc.x - vn.x, vc.y - vn.y);
+    float m = mag(rel);
+    if (m != 0.f) {
+        V2 dir = mk(rel.x / m, rel.y / m);
+        float upd = -m * fminf(damping * c.dt, 1.0f);
+        float imp = upd / (imc + imn);
+        vc.x += imc * imp * dir.x; vc.y += imc * imp * dir.y;
+        vn.x -= imn * imp * dir.x; vn.y -= imn * imp * dir.y;
+        stb(c.V + rd.x, vc);
+        stb(c.V + rd.y, vn);
+    }
+}
+// solver.rs:750-765, one thread per rope particle
+SFG_DI void stage_rope_lateral(const SolverCtx& c, uint32_t p) {
+    const int b = c.rp_body[p];
+    float2 corr = ldb(c.LAT + b);
+    if (isnan(corr.x)) return;
+    const float bend_c = ldc(c.RPA + c.rp_rope[p]).w;
+    float4 v = ldb(c.V + b);
+    const float im = ldb(c.MI + b).x;
+    float cm = sqrtf(corr.x * corr.x + corr.y * corr.y);
+    float vfc = cm * c.inv_dt;
+    V2 dir = mk(corr.x / cm, corr.y / cm);
+    float vid = v.x * dir.x + v.y * dir.y;
+    float vc = fmaxf(fminf(vid, vfc), -vfc);
+    float imp = -vc / (im + bend_c * c.inv_dt);
+    v.x += im * imp * dir.x; v.y += im * imp * dir.y;
+    stb(c.V + b, v);
+}
+// pre_contact_poses (solver.rs:83-85), only rope particles ever read them (solver.rs:337-362)
+SFG_DI void stage_precontact(const SolverCtx& c, uint32_t p) {
+    const int b = c.rp_body[p];
+    float4 pp = ldb(c.P + b);
+    stb(c.PCD + b, make_float2(pp.z, pp.w));
+}
+
+// ---------------------------------------------------------------- helpers
+SFG_DI void apply_correction(float4& P, Rot& r, float im, float ii, float sgn, float lambda, V2 dir, float wdg) {
+    const float k = sgn * im * lambda;
+    P.z += k * dir.x; P.w += k * dir.y;
+    if (ii != 0.f) r = rot_from_angle(sgn * ii * lambda * wdg) * r;
+}
+
+// ---------------------------------------------------------------- distance constraints (solver.rs:187-269)
+SFG_DI void stage_constraints(const SolverCtx& c, uint32_t u) {
+    const float4 k0 = ldc(c.K0 + u), k1 = ldc(c.K1 + u), k2 = ldc(c.K2 + u);
+    const int owner = __float_as_int(k0.x), target = __float_as_int(k0.y);
+    const uint32_t fl = __float_as_uint(k0.z);
+    const uint32_t limit = fl & 3u;
+    const int mult = target >= 0 ? 2 : 1;
+    float4 P0 = ldb(c.P + owner), Q0 = ldb(c.Q + owner);
+    float4 mi0 = ldb(c.MI + owner);
+    float4 P1 = make_float4(0, 0, 0, 0), Q1 = make_float4(1, 0, 1, 0), mi1 = make_float4(0, 0, 0, 0);
+    if (target >= 0) { P1 = ldb(c.P + target); Q1 = ldb(c.Q + target); mi1 = ldb(c.MI + target); }
+    Rot r0 = mkrot(Q0.x, Q0.y), r1 = mkrot(Q1.x, Q1.y);
+    const V2 o0 = mk(k2.x, k2.y), o1 = mk(k2.z, k2.w);
+    for (int m = 0; m < mult; ++m) {
+        // world offsets relative to the owner's substep-start position
+        V2 w0 = r0 * o0 + mk(P0.z, P0.w);
+        V2 w1 = target >= 0 ? r1 * o1 + mk((P1.x - P0.x) + P1.z, (P1.y - P0.y) + P1.w) : mk(o1.x - P0.x, o1.y - P0.y);
+        V2 actual = w1 - w0;
+        float am = mag(actual);
+        float error = k1.w - am;
+        bool act = limit == 0u || (limit == 1u && error < 0.f) || (limit == 2u && error > 0.f);
+        if (!act) continue;
+        V2 dir = am != 0.f ? mk(actual.x / am, actual.y / am) : mk(0.f, 1.f);
+        float wd0 = wedge(r0 * o0, dir);
+        float wd1 = target >= 0 ? wedge(r1 * o1, dir) : 0.f;
+        float e0 = mi0.x + (wd0 * wd0 * mi0.y), e1 = target >= 0 ? mi1.x + (wd1 * wd1 * mi1.y) : 0.f;
+        float lambda = -error / (e0 + e1 + k1.x * c.inv_dt_sq);
+        apply_correction(P0, r0, mi0.x, mi0.y, 1.f, lambda, dir, wd0);
+        if (target >= 0) apply_correction(P1, r1, mi1.x, mi1.y, -1.f, lambda, dir, wd1);
+    }
+    if (mi0.x != 0.f || mi0.y != 0.f) { stb(c.P + owner, P0); Q0.x = r0.s; Q0.y = r0.b; stb(c.Q + owner, Q0); }
+    if (target >= 0 && (mi1.x != 0.f || mi1.y != 0.f)) { stb(c.P + target, P1); Q1.x = r1.s; Q1.y = r1.b; stb(c.Q + target, Q1); }
+}
+
+// solver.rs:624-709
+SFG_DI void stage_constraint_damp(const SolverCtx& c, uint32_t u) {
+    const float4 k0 = ldc(c.K0 + u), k1 = ldc(c.K1 + u), k2 = ldc(c.K2 + u);
+    const int owner = __float_as_int(k0.x), target = __float_as_int(k0.y);
+    const int mult = target >= 0 ? 2 : 1;
+    float4 Q0 = ldb(c.Q + owner), V0 = ldb(c.V + owner), mi0 = ldb(c.MI + owner);
+    float4 Q1 = make_float4(1, 0, 1, 0), V1 = make_float4(0, 0, 0, 0), mi1 = make_float4(0, 0, 0, 0);
+    if (target >= 0) { Q1 = ldb(c.Q + target); V1 = ldb(c.V + target); mi1 = ldb(c.MI + target); }
+    const V2 or0 = mkrot(Q0.x, Q0.y) * mk(k2.x, k2.y);
+    const V2 or1 = target >= 0 ? mkrot(Q1.x, Q1.y) * mk(k2.z, k2.w) : mk(0.f, 0.f);
+    const float lin = fminf(k1.y * c.dt, 1.0f), ang = fminf(k1.z * c.dt, 1.0f);
+    for (int m = 0; m < mult; ++m) {
+        V2 pv0 = mk(V0.x - or0.y * V0.z, V0.y + or0.x * V0.z);
+        if (target >= 0) {
+            V2 pv1 = mk(V1.x - or1.y * V1.z, V1.y + or1.x * V1.z);
+            V2 rel = pv0 - pv1;
+            float rm = mag(rel);
+            if (rm == 0.f) continue;
+            V2 dir = mk(rel.x / rm, rel.y / rm);
+            float wd0 = wedge(or0, dir), wd1 = wedge(or1, dir);
+            float e0 = mi0.x + (wd0 * wd0 * mi0.y), e1 = mi1.x + (wd1 * wd1 * mi1.y);
+            float imp = (-rm * lin) / (e0 + e1);
+            V0.x += mi0.x * imp * dir.x; V0.y += mi0.x * imp * dir.y; V0.z += mi0.y * imp * wd0;
+            V1.x -= mi1.x * imp * dir.x; V1.y -= mi1.x * imp * dir.y; V1.z -= mi1.y * imp * wd1;
+            if (k1.z > 0.f) {
+                float relw = V0.z - V1.z;
+                float ai = (-relw * ang) / (e0 + e1);
+                V1.z -= mi1.y * ai;
+                V0.z += mi0.y * ai;
+            }
+        } else {
+            float pm = mag(pv0);
+            if (pm == 0.f) continue;
+            V2 dir = mk(pv0.x / pm, pv0.y / pm);
+            float wd = wedge(or0, dir);
+            float e = mi0.x + wd * wd * mi0.y;
+            float imp = (-pm * lin) / e;
+            V0.x += mi0.x * imp * dir.x; V0.y += mi0.x * imp * dir.y; V0.z += mi0.y * imp * wd;
+            if (k1.z > 0.f) {
+                float au = V0.z * ang;
+                float ai = -au / e;
+                V0.z += mi0.y * ai;
+            }
+        }
+    }
+    if (mi0.x != 0.f || mi0.y != 0.f) stb(c.V + owner, V0);
+    if (target >= 0 && (mi1.x != 0.f || mi1.y != 0.f)) stb(c.V + target, V1);
+}
+
+// ---------------------------------------------------------------- contacts (solver.rs:275-490, narrowphase inline)
+SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
+    const float4 h = ldc(c.H + u);
+    const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
+    const uint32_t fl = __float_as_uint(h.z);
+    const float mu_s = h.w;
+    Shape sh[2] = {mkshape(ldc(c.G0 + u)), mkshape(ldc(c.G1 + u))};
+    const float4 l0 = ldc(c.L0 + u), l1 = ldc(c.L1 + u);
+    const Iso loc0 = mkiso(mk(l0.x, l0.y), mkrot(l0.z, l0.w)), loc1 = mkiso(mk(l1.x, l1.y), mkrot(l1.z, l1.w));
+
+    float4 P0 = make_float4(0, 0, 0, 0), Q0 = make_float4(1, 0, 1, 0), P1 = P0, Q1 = Q0;
+    float im0 = 0.f, ii0 = 0.f, im1 = 0.f, ii1 = 0.f;
+    if (b0 >= 0) { P0 = ldb(c.P + b0); Q0 = ldb(c.Q + b0); float4 m = ldb(c.MI + b0); im0 = m.x; ii0 = m.y; }
+    if (b1 >= 0) { P1 = ldb(c.P + b1); Q1 = ldb(c.Q + b1); float4 m = ldb(c.MI + b1); im1 = m.x; ii1 = m.y; }
+    // pair-local frame: origin at object 0's substep-start position (or its static translation)
+    const V2 org = b0 >= 0 ? mk(P0.x, P0.y) : loc0.t;
+    const V2 told0 = mk(0.f, 0.f);
+    const V2 told1 = b1 >= 0 ? mk(P1.x - org.x, P1.y - org.y) : mk(0.f, 0.f);
+    const Iso st0 = mkiso(mk(0.f, 0.f), loc0.r);                       // static collider 0 in the local frame
+    const Iso st1 = mkiso(loc1.t - org, loc1.r);
+    Rot r0 = mkrot(Q0.x, Q0.y), r1 = mkrot(Q1.x, Q1.y);
+    const Rot ro0 = mkrot(Q0.z, Q0.w), ro1 = mkrot(Q1.z, Q1.w);
+    const int mult = (fl & UF_MULT2) ? 2 : 1;
+    const bool sees = (fl & (UF_SEES0 | UF_SEES1)) != 0;
+
+    for (int m = 0; m < mult; ++m) {
+        const uint32_t e = u + uint32_t(m) * c.n_units;
+        Iso pw[2];
+        pw[0] = b0 >= 0 ? mkiso(mk(P0.z, P0.w), r0) * loc0 : st0;
+        pw[1] = b1 >= 0 ? mkiso(mk(told1.x + P1.z, told1.y + P1.w), r1) * loc1 : st1;
+        Manifold mf;
+        intersection_check(pw, sh, mf);
+        if (mf.count == 0) { c.M0[e] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+        for (int k = 0; k < mf.count; ++k) {                            // solver.rs:308-315
+            if (b0 >= 0) mf.off[k][0] = loc0 * mf.off[k][0];
+            if (b1 >= 0) mf.off[k][1] = loc1 * mf.off[k][1];
+        }
+        c.LN[e] = make_float2(mf.n.x, mf.n.y);                          // solver.rs:318-320 (latch)
+        float lambda_n = 0.f;
+        if (sees) {
+            if (mf.count == 1 && (fl & (UF_ROPE0 | UF_ROPE1))) {        // solver.rs:337-362
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    if (!(fl & (i ? UF_ROPE1 : UF_ROPE0))) continue;
+                    const int bi = i ? b1 : b0;
+                    const int prev = c.rope_prev[bi], next = c.rope_next[bi];
+                    const float4 ps = i ? P1 : P0;
+                    const float2 ds = ldb(c.PCD + bi);
+                    const float4 pp = ldb(c.P + prev), pn = ldb(c.P + next);
+                    const float2 dp = ldb(c.PCD + prev), dn = ldb(c.PCD + next);
+                    V2 no = i ? -mf.n : mf.n;
+                    V2 to_prev = mk((pp.x - ps.x) + (dp.x - ds.x), (pp.y - ps.y) + (dp.y - ds.y));
+                    V2 to_next = mk((pn.x - ps.x) + (dn.x - ds.x), (pn.y - ps.y) + (dn.y - ds.y));
+                    V2 nn = dot(no, to_prev) > dot(no, to_next) ? normalized(left_normal(to_prev)) : normalized(left_normal(to_next));
+                    mf.n = dot(mf.n, nn) > 0.f ? nn : -nn;
+                }
+            }
+            if (!(fl & UF_SENSOR)) {
+                const V2 n = mf.n, tan = left_normal(mf.n);
+                for (int k = 0; k < mf.count; ++k) {
+                    V2 ow0, ow1, owo0, owo1;
+                    float wn0 = 0.f, wn1 = 0.f, wt0 = 0.f, wt1 = 0.f, en0 = 0.f, en1 = 0.f, et0 = 0.f, et1 = 0.f;
+                    if (b0 >= 0) {
+                        V2 orot = r0 * mf.off[k][0];
+                        wn0 = wedge(orot, n); wt0 = wedge(orot, tan);
+                        ow0 = orot + mk(P0.z, P0.w);
+                        en0 = im0 + (wn0 * wn0 * ii0); et0 = im0 + (wt0 * wt0 * ii0);
+                        owo0 = ro0 * mf.off[k][0] + told0;
+                    } else { ow0 = st0 * mf.off[k][0]; owo0 = ow0; }
+                    if (b1 >= 0) {
+                        V2 orot = r1 * mf.off[k][1];
+                        wn1 = wedge(orot, n); wt1 = wedge(orot, tan);
+                        ow1 = orot + mk(told1.x + P1.z, told1.y + P1.w);
+                        en1 = im1 + (wn1 * wn1 * ii1); et1 = im1 + (wt1 * wt1 * ii1);
+                        owo1 = ro1 * mf.off[k][1] + told1;
+                    } else { ow1 = st1 * mf.off[k][1]; owo1 = ow1; }
+                    float depth = dot(ow0 - ow1, n);
+                    if (depth <= 0.f) { lambda_n = 0.f; continue; }
+                    lambda_n = -depth / (en0 + en1);
+                    apply_correction(P0, r0, im0, ii0, 1.f, lambda_n, n, wn0);
+                    apply_correction(P1, r1, im1, ii1, -1.f, lambda_n, n, wn1);
+                    if (fl & UF_HAS_SF) {                               // solver.rs:456-487
+                        V2 odm = (ow0 - owo0) - (ow1 - owo1);
+                        float mat = dot(odm, tan);
+                        float lambda_t = -mat / (et0 + et1);
+                        if (lambda_t < lambda_n * mu_s) {
+                            apply_correction(P0, r0, im0, ii0, 1.f, lambda_t, tan, wt0);
+                            apply_correction(P1, r1, im1, ii1, -1.f, lambda_t, tan, wt1);
+                        }
+                    }
+                }
+            }
+        }
+        c.M0[e] = make_float4(__int_as_float(mf.count), lambda_n, mf.n.x, mf.n.y);
+        c.M1[e] = make_float4(mf.off[0][0].x, mf.off[0][0].y, mf.off[0][1].x, mf.off[0][1].y);
+        if (mf.count == 2) c.M2[e] = make_float4(mf.off[1][0].x, mf.off[1][0].y, mf.off[1][1].x, mf.off[1][1].y);
+    }
+    if (fl & UF_SEES0) { stb(c.P + b0, P0); Q0.x = r0.s; Q0.y = r0.b; stb(c.Q + b0, Q0); }
+    if (fl & UF_SEES1) { stb(c.P + b1, P1); Q1.x = r1.s; Q1.y = r1.b; stb(c.Q + b1, Q1); }
+}
+
+// solver.rs:496-618
+SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u) {
+    const float4 h = ldc(c.H + u);
+    const uint32_t fl = __float_as_uint(h.z);
+    if ((fl & UF_SENSOR) || !(fl & (UF_SEES0 | UF_SEES1))) return;
+    const int mult = (fl & UF_MULT2) ? 2 : 1;
+    float4 m0[2];
+    m0[0] = c.M0[u];
+    m0[1] = mult == 2 ? c.M0[u + c.n_units] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (__float_as_int(m0[0].x) == 0 && __float_as_int(m0[1].x) == 0) return;
+    const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
+    const float4 s = ldc(c.S + u);
+    const float mu_d = s.z, rest_mat = s.w;
+    float4 V0 = make_float4(0, 0, 0, 0), V1 = V0, OV0 = V0, OV1 = V0;
+    Rot r0 = mkrot(1.f, 0.f), r1 = r0;
+    float im0 = 0.f, ii0 = 0.f, im1 = 0.f, ii1 = 0.f;
+    V2 ea = mk(0.f, 0.f);
+    if (b0 >= 0) { float4 q = ldb(c.Q + b0); r0 = mkrot(q.x, q.y); V0 = ldb(c.V + b0); OV0 = ldb(c.OV + b0); float4 mi = ldb(c.MI + b0); im0 = mi.x; ii0 = mi.y; float2 a = ldb(c.EA + b0); ea = ea + mk(a.x, a.y); }
+    if (b1 >= 0) { float4 q = ldb(c.Q + b1); r1 = mkrot(q.x, q.y); V1 = ldb(c.V + b1); OV1 = ldb(c.OV + b1); float4 mi = ldb(c.MI + b1); im1 = mi.x; ii1 = mi.y; float2 a = ldb(c.EA + b1); ea = ea + mk(a.x, a.y); }
+    const float rest_gate = c.dt * c.dt * mag_sq(ea);
+    for (int m = 0; m < mult; ++m) {
+        const int count = __float_as_int(m0[m].x);
+        if (count == 0) continue;
+        const uint32_t e = u + uint32_t(m) * c.n_units;
+        const float lambda_n = m0[m].y;
+        const V2 n = mk(m0[m].z, m0[m].w), tan = left_normal(n);
+        for (int k = 0; k < count; ++k) {
+            const float4 pt = k == 0 ? c.M1[e] : c.M2[e];
+            const V2 or0 = b0 >= 0 ? r0 * mk(pt.x, pt.y) : mk(0.f, 0.f);
+            const V2 or1 = b1 >= 0 ? r1 * mk(pt.z, pt.w) : mk(0.f, 0.f);
+            V2 pv0 = mk(V0.x - or0.y * V0.z, V0.y + or0.x * V0.z), pv1 = mk(V1.x - or1.y * V1.z, V1.y + or1.x * V1.z);
+            V2 opv0 = mk(OV0.x - or0.y * OV0.z, OV0.y + or0.x * OV0.z), opv1 = mk(OV1.x - or1.y * OV1.z, OV1.y + or1.x * OV1.z);
+            V2 rel = pv0 - pv1;
+            float nv = dot(rel, n);
+            float onv = dot(opv0 - opv1, n);
+            float rest = (onv * onv < rest_gate) ? 0.f : rest_mat;
+            float dnv = -nv - rest * fmaxf(onv, 0.f);
+            float dtv = 0.f;
+            if (fl & UF_HAS_DF) {
+                float tv = dot(rel, tan);
+                float max_dv = c.inv_dt * lambda_n * mu_d;
+                dtv = fminf(fabsf(tv), fabsf(max_dv)) * -signum_rs(tv);
+            }
+            V2 upd = dnv * n + dtv * tan;
+            float um = mag(upd);
+            if (um < 0.0001f) continue;
+            V2 dir = mk(upd.x / um, upd.y / um);
+            float wd0 = wedge(or0, dir), wd1 = wedge(or1, dir);
+            float e0 = im0 + (wd0 * wd0 * ii0), e1 = im1 + (wd1 * wd1 * ii1);
+            float imp = um / (e0 + e1);
+            V0.x += im0 * imp * dir.x; V0.y += im0 * imp * dir.y; V0.z += ii0 * imp * wd0;
+            V1.x -= im1 * imp * dir.x; V1.y -= im1 * imp * dir.y; V1.z -= ii1 * imp * wd1;
+        }
+    }
+    if (fl & UF_SEES0) stb(c.V + b0, V0);
+    if (fl & UF_SEES1) stb(c.V + b1, V1);
+}
+
+// ---------------------------------------------------------------- drivers
+SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_substep) {
+    switch (kind) {
+    case ST_INTEGRATE: stage_integrate(c, i); break;
+    case ST_ROPE_STEP: stage_rope_step(c, i); break;
+    case ST_CONSTRAINTS: stage_constraints(c, i); break;
+    case ST_PRECONTACT: stage_precontact(c, i); break;
+    case ST_CONTACTS: stage_contacts(c, i); break;
+    case ST_DERIVE: stage_derive(c, i, last_substep); break;
+    case ST_CONTACT_VEL: stage_contact_vel(c, i); break;
+    case ST_CONSTRAINT_DAMP: stage_constraint_damp(c, i); break;
+    case ST_ROPE_DAMP: stage_rope_damp(c, i); break;
+    case ST_ROPE_LATERAL: stage_rope_lateral(c, i); break;
+    case ST_FOLD: stage_fold(c, i); break;
+    default: break;
+    }
+}
+
+template <uint32_t KIND>
+__global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx c, uint32_t begin, uint32_t end, int last_substep) {
+    const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < end) run_stage(c, KIND, i, last_substep != 0);
+}
+
+// The whole substep loop of one tick in ONE launch: every CTA walks the stage table, grid-strides over
+// the stage's range, and meets the others at a grid-wide barrier before the next stage (colour).
+__global__ void __launch_bounds__(256) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
+                                                          uint32_t n_stages, uint32_t substeps) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (uint32_t s = 0; s < substeps; ++s) {
+        const bool last = s + 1 == substeps;
+        for (uint32_t k = 0; k < n_stages; ++k) {
+            const Stage st = stages[k];
+            for (uint32_t i = st.begin + tid; i < st.end; i += nth) run_stage(c, st.kind, i, last);
+            grid.sync();
+        }
+    }
+}
+
+}  // namespace sfg

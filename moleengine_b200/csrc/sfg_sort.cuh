@@ -1,0 +1,177 @@
+// CUB-free device primitives for the broadphase / graph build: an LSD radix sort whose ranking runs
+// in shared memory (8-bit digits, warp match-any multisplit, stable) and a three-phase exclusive
+// scan. Written for sm_100a: 256-thread CTAs, 2048-key tiles, grids sized by the tile count.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sfg {
+
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // keys per CTA
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+// ---- histogram: hist[digit * n_tiles + tile] ----
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift,
+                                                            uint32_t* __restrict__ hist, uint32_t n_tiles) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * SORT_TILE;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        uint32_t i = base + r * SORT_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+// ---- scatter: stable rank inside the tile in shared memory, then a direct write ----
+// Order inside a tile is (warp, round, lane): warp w owns keys [w*256, (w+1)*256) of the tile.
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                                                               int shift, const uint32_t* __restrict__ hist_scanned, uint32_t n_tiles) {
+    __shared__ uint32_t warp_hist[SORT_WARPS][256];
+    __shared__ uint32_t digit_base[256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+    uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : 0xFFFFFFFFu;
+        val[r] = ok ? vals_in[i] : 0u;
+        const uint32_t d = ok ? ((key[r] >> shift) & 255u) : 256u;   // 256 = out of range, ranked nowhere
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t b = 0;
+        if (ok && lane == leader) { b = warp_hist[warp][d]; warp_hist[warp][d] = b + __popc(peers); }
+        b = __shfl_sync(0xFFFFFFFFu, b, leader);
+        rank[r] = b + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive scan of each digit over the warps + global base of this tile
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) { uint32_t c = warp_hist[w][d]; warp_hist[w][d] = run; run += c; }
+        digit_base[d] = hist_scanned[d * n_tiles + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[r] >> shift) & 255u;
+            const uint32_t pos = digit_base[d] + warp_hist[warp][d] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+// ---- exclusive scan (u32), three phases; block sums scanned by one CTA ----
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < nw ? wsum[lane] : 0, wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (lane >= o) wi += t; }
+        wsum[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    uint32_t res = wsum[warp] + inc - v;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t tot;
+    uint32_t s = 0;
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) s += in[base + k];
+    block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+// one CTA scans `sums` in place (exclusive) and writes the grand total to *total_out
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ sums, uint32_t n, uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t tot;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < n; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? sums[i] : 0;
+        uint32_t e = block_exclusive_scan(v, &tot);
+        if (i < n) sums[i] = carry + e;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ sums,
+                                                             uint32_t* __restrict__ out) {
+    __shared__ uint32_t tot;
+    uint32_t v[SCAN_ITEMS], s = 0;
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
+    uint32_t e = block_exclusive_scan(s, &tot) + sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = e; e += v[k]; }
+}
+
+// Host-side drivers. `tmp` must hold at least scan_tmp_words(n) uint32.
+inline size_t scan_tmp_words(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+// exclusive scan of in[0..n) into out[0..n) (in == out allowed); the grand total goes to *total_dev if not null
+inline int scan_exclusive(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, uint32_t* total_dev, cudaStream_t st) {
+    if (n == 0) { if (total_dev) cudaMemsetAsync(total_dev, 0, 4, st); return 0; }
+    const uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
+    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nb, total_dev);
+    k_scan_apply<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp, out);
+    return 3;
+}
+
+inline size_t sort_tmp_words(size_t n) {
+    size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    return 256 * tiles + scan_tmp_words(256 * tiles);
+}
+// Sorts (keys, vals) by the low `bits` bits of the key, stable. Ping-pongs between (k0, v0) and (k1, v1);
+// returns 0 if the result is in (k0, v0), 1 if in (k1, v1); *launches is incremented by the kernels launched.
+inline int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, int bits, uint32_t* tmp,
+                            cudaStream_t st, int* launches) {
+    if (n == 0) return 0;
+    const uint32_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    uint32_t* hist = tmp;
+    uint32_t* scan_tmp = tmp + 256 * size_t(tiles);
+    int cur = 0;
+    for (int shift = 0; shift < bits; shift += 8) {
+        uint32_t *ki = cur ? k1 : k0, *vi = cur ? v1 : v0, *ko = cur ? k0 : k1, *vo = cur ? v0 : v1;
+        k_sort_hist<<<tiles, SORT_THREADS, 0, st>>>(ki, n, shift, hist, tiles);
+        int l = scan_exclusive(hist, hist, 256 * tiles, scan_tmp, nullptr, st);
+        k_sort_scatter<<<tiles, SORT_THREADS, 0, st>>>(ki, vi, ko, vo, n, shift, hist, tiles);
+        if (launches) *launches += 2 + l;
+        cur ^= 1;
+    }
+    return cur;
+}
+
+}  // namespace sfg

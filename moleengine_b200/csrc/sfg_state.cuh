@@ -1,0 +1,92 @@
+// Device-resident state of one physics world and the parameter blocks handed to kernels.
+// Layout (all structure-of-arrays, 16-byte columns, indexed by ARENA SLOT unless noted):
+//
+//  bodies     P  float4 (x_old, y_old, dx, dy)  position at substep start + displacement so far
+//             Q  float4 (s, b, s_old, b_old)    rotor now / at substep start
+//             V  float4 (vx, vy, w, -)          OV float4 velocity after forces, before the solve
+//             MI float4 (1/m, 1/I, flags, -)    EA float2 external acceleration (restitution gate)
+//  colliders  CS float4 (p0, p1, circle_r, kind) CL float4 local pose (x, y, s, b)
+//             CM float4 (mu_s, mu_d, e, flags)   CI int4 (body, layer, domain, flags)   AABB float4
+//  pair units (sorted colour-major, rebuilt every tick)
+//             H  (body0, body1, flags, mu_s)   S (hi, lo, mu_d, e)   G0 G1 shapes   L0 L1 local poses
+//             M0 (count, lambda_n, n.x, n.y)  M1 / M2 point 0 / 1 (off0.xy, off1.xy); entry = copy * n_units + unit
+//
+// Keeping (x_old, dx) instead of x lets every kernel form differences of nearby points without the
+// cancellation that absolute f32 coordinates suffer far from the origin, and makes the velocity
+// update v = dx / dt exact to f32 rounding (SURVEY.md "hard parts" 1).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sfg {
+
+constexpr int MAX_LEVELS = 8;
+
+struct GridParams {
+    float ox, oy;
+    int n_levels;                 // grid levels; colliders larger than the top cell go to the "huge" list
+    uint32_t n_domains;
+    float inv_cell[MAX_LEVELS];
+    float cell[MAX_LEVELS];
+    int nx[MAX_LEVELS], ny[MAX_LEVELS];
+    uint32_t base[MAX_LEVELS];    // first key of each level
+    uint32_t n_cells;             // key n_cells = huge list; 0xFFFFFFFF = dead
+};
+
+struct Bounds {                   // filled by k_aabb with ordered-int atomics
+    int min_x, min_y, max_x, max_y;   // float bits mapped to ordered ints
+    int max_extent;
+    uint32_t max_domain;
+    uint32_t n_live;
+    uint32_t pad;
+    double sum_extent;
+};
+
+// unit flags
+enum : uint32_t {
+    UF_MULT2 = 1u, UF_SENSOR = 2u, UF_HAS_SF = 4u, UF_HAS_DF = 8u, UF_SEES0 = 16u, UF_SEES1 = 32u,
+    UF_ROPE0 = 64u, UF_ROPE1 = 128u,
+};
+// body flag bits kept in MI.z (same values as SFG_BODY_*)
+enum : uint32_t { BF_ALIVE = 1u, BF_NOGRAV = 2u, BF_MASS = 4u, BF_INERTIA = 8u };
+// collider flag bits kept in CM.w / CI.w (same values as SFG_COLL_*)
+enum : uint32_t { CF_ALIVE = 1u, CF_SENSOR = 2u, CF_HAS_SF = 4u, CF_HAS_DF = 8u };
+
+struct ForceParams { uint32_t n; uint32_t kind[4]; float a[4], b[4], c[4], d[4]; };
+
+// Everything a solver stage needs. Passed by value (kernel parameter space).
+struct SolverCtx {
+    // bodies
+    float4 *P, *Q, *V, *OV, *MI;
+    float2 *EA, *PCD;
+    const int *rope_next, *rope_prev;
+    uint32_t n_bodies;
+    // pair units
+    const float4 *H, *S, *G0, *G1, *L0, *L1;
+    float4 *M0, *M1, *M2;
+    float2* LN;
+    uint32_t n_units;
+    // constraint units (sorted colour-major)
+    const float4 *K0, *K1, *K2;   // (owner, target, flags, -) (compliance, lin damp, ang damp, distance) (off0.xy, off1.xy)
+    uint32_t n_kunits;
+    // rope units
+    const int4* RU;               // (curr, next, after, rope) body slots, sorted by colour i mod 3
+    const int4* RD;               // (curr, next, rope, -) damping pairs sorted by colour i mod 2
+    const float4 *RPA, *RPB;      // per rope (spacing, compliance, max_angle, bend_compliance) (damping, -, -, -)
+    const int* rp_body;           // particle -> body slot
+    const int* rp_rope;           // particle -> rope
+    float2* LAT;                  // per body slot: lateral correction; x = NaN means unset
+    uint32_t n_particles;
+    // step
+    float dt, inv_dt, inv_dt_sq;
+    ForceParams ff;
+};
+
+// stage table of the persistent solver kernel
+enum StageKind : uint32_t {
+    ST_INTEGRATE = 0, ST_ROPE_STEP, ST_CONSTRAINTS, ST_PRECONTACT, ST_CONTACTS, ST_DERIVE, ST_CONTACT_VEL,
+    ST_CONSTRAINT_DAMP, ST_ROPE_DAMP, ST_ROPE_LATERAL, ST_FOLD,
+};
+struct Stage { uint32_t kind, begin, end, pad; };
+
+}  // namespace sfg

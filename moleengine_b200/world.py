@@ -1,0 +1,162 @@
+"""Thin Python handle over the C ABI (one SfgWorld = one device + one stream).
+
+This is the harness-level wrapper used by tests and bench.py; it moves structured numpy arrays
+(abi.*_dtype) across the boundary unchanged. It never computes physics itself.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class SfgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sfg error {code}: {msg}")
+        self.code = code
+
+
+class GpuWorld:
+    def __init__(self, tuning=None, mask_matrix=None, device=0):
+        self.lib = abi.load()
+        self.h = C.c_void_p()
+        t = abi.default_tuning() if tuning is None else tuning
+        m = abi.default_mask_matrix() if mask_matrix is None else np.ascontiguousarray(mask_matrix, dtype=np.uint64)
+        rc = self.lib.sfg_world_create(abi.ptr(t), abi.ptr(m), device, C.byref(self.h))
+        if rc != abi.SFG_OK:
+            raise SfgError(rc, "sfg_world_create failed (no CUDA device? there is no CPU fallback)")
+        self.n_bodies = 0
+
+    def close(self):
+        if self.h:
+            self.lib.sfg_world_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != abi.SFG_OK:
+            raise SfgError(rc, self.lib.sfg_last_error(self.h).decode())
+
+    # ---- uploads -------------------------------------------------------------------------------
+    def set_tuning(self, tuning):
+        self._ck(self.lib.sfg_set_tuning(self.h, abi.ptr(tuning)))
+
+    def set_mask_matrix(self, m):
+        self._ck(self.lib.sfg_set_mask_matrix(self.h, abi.ptr(np.ascontiguousarray(m, dtype=np.uint64))))
+
+    def set_bodies(self, bodies):
+        assert bodies.dtype == abi.body_dtype
+        self._ck(self.lib.sfg_set_bodies(self.h, len(bodies), abi.ptr(bodies)))
+        self.n_bodies = len(bodies)
+
+    def update_bodies(self, first, bodies):
+        self._ck(self.lib.sfg_update_bodies(self.h, first, len(bodies), abi.ptr(bodies)))
+
+    def set_colliders(self, colliders):
+        assert colliders.dtype == abi.collider_dtype
+        self._ck(self.lib.sfg_set_colliders(self.h, len(colliders), abi.ptr(colliders)))
+
+    def update_colliders(self, first, colliders):
+        self._ck(self.lib.sfg_update_colliders(self.h, first, len(colliders), abi.ptr(colliders)))
+
+    def set_constraints(self, constraints):
+        assert constraints.dtype == abi.constraint_dtype
+        self._ck(self.lib.sfg_set_constraints(self.h, len(constraints), abi.ptr(constraints) if len(constraints) else None))
+
+    def set_ropes(self, ropes, particle_bodies):
+        assert ropes.dtype == abi.rope_dtype
+        pb = np.ascontiguousarray(particle_bodies, dtype=np.int32)
+        self._ck(self.lib.sfg_set_ropes(self.h, len(ropes), abi.ptr(ropes) if len(ropes) else None, len(pb),
+                                        abi.ptr(pb) if len(pb) else None))
+
+    def load_scene(self, scene):
+        """scene: dict with bodies / colliders / constraints / ropes / rope_particles (see scenes.py)."""
+        self.set_bodies(scene["bodies"])
+        self.set_colliders(scene["colliders"])
+        self.set_constraints(scene.get("constraints", np.zeros(0, abi.constraint_dtype)))
+        self.set_ropes(scene.get("ropes", np.zeros(0, abi.rope_dtype)), scene.get("rope_particles", np.zeros(0, np.int32)))
+
+    # ---- step + readback -----------------------------------------------------------------------
+    def tick(self, frame_dt=1.0 / 60.0, time_scale=None, forcefield=None):
+        ff = abi.gravity_field() if forcefield is None else forcefield
+        self._ck(self.lib.sfg_tick(self.h, frame_dt, 0 if time_scale is None else 1,
+                                   0.0 if time_scale is None else time_scale, abi.ptr(ff)))
+
+    def get_bodies(self, first=0, count=None):
+        count = self.n_bodies - first if count is None else count
+        out = np.zeros(count, abi.body_dtype)
+        self._ck(self.lib.sfg_get_bodies(self.h, first, count, abi.ptr(out)))
+        return out
+
+    def get_contacts(self, capacity=1 << 20):
+        out = np.zeros(capacity, abi.contact_dtype)
+        n = C.c_size_t()
+        self._ck(self.lib.sfg_get_contacts(self.h, abi.ptr(out), capacity, C.byref(n)))
+        if n.value > capacity:
+            return self.get_contacts(n.value)
+        return out[: n.value]
+
+    def stats(self):
+        s = np.zeros(1, abi.stats_dtype)
+        self._ck(self.lib.sfg_get_stats(self.h, abi.ptr(s)))
+        return s[0]
+
+    def cast_batch(self, rays):
+        assert rays.dtype == abi.ray_dtype
+        out = np.zeros(len(rays), abi.hit_dtype)
+        self._ck(self.lib.sfg_cast_batch(self.h, len(rays), abi.ptr(rays), abi.ptr(out)))
+        return out
+
+    def query_point_batch(self, points, domains=None, max_hits=8):
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
+        dom = None if domains is None else np.ascontiguousarray(domains, dtype=np.uint32)
+        out = np.zeros((len(pts), max_hits), np.int32)
+        cnt = np.zeros(len(pts), np.uint32)
+        self._ck(self.lib.sfg_query_point_batch(self.h, len(pts), abi.ptr(pts), abi.ptr(dom), max_hits, abi.ptr(out), abi.ptr(cnt)))
+        return out, cnt
+
+    # ---- parity hooks ----------------------------------------------------------------------------
+    def debug_pairs(self):
+        n = C.c_size_t()
+        self._ck(self.lib.sfg_debug_get_pairs(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 2), np.uint32)
+        if n.value:
+            self._ck(self.lib.sfg_debug_get_pairs(self.h, abi.ptr(out), n.value, C.byref(n)))
+        return out
+
+    def debug_contact_units(self):
+        n = C.c_size_t()
+        self._ck(self.lib.sfg_debug_get_contact_entries(self.h, None, None, None, 0, C.byref(n)))
+        hi = np.zeros(n.value, np.uint32)
+        lo = np.zeros(n.value, np.uint32)
+        col = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.lib.sfg_debug_get_contact_entries(self.h, abi.ptr(hi), abi.ptr(lo), abi.ptr(col), n.value, C.byref(n)))
+        return hi, lo & 0x7FFFFFFF, (lo >> 31) + 1, col
+
+    def debug_constraint_units(self):
+        n = C.c_size_t()
+        self._ck(self.lib.sfg_debug_get_constraint_entries(self.h, None, None, 0, C.byref(n)))
+        idx = np.zeros(n.value, np.uint32)
+        col = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.lib.sfg_debug_get_constraint_entries(self.h, abi.ptr(idx), abi.ptr(col), n.value, C.byref(n)))
+        return idx & 0x7FFFFFFF, (idx >> 31) + 1, col
+
+    def debug_manifolds(self):
+        n = C.c_size_t()
+        self._ck(self.lib.sfg_debug_get_manifolds(self.h, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 14), np.float32)
+        if n.value:
+            self._ck(self.lib.sfg_debug_get_manifolds(self.h, abi.ptr(out), n.value, C.byref(n)))
+        return out
+
+    def debug_aabbs(self, n_colliders):
+        out = np.zeros((n_colliders, 4), np.float32)
+        self._ck(self.lib.sfg_debug_get_aabbs(self.h, abi.ptr(out), n_colliders))
+        return out
