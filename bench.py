@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py — body-substeps/s of the Starframe physics tick on B200 (BASELINE.json metric).
+
+A "step" is one physics tick (frame_dt = 1/60, 4 XPBD substeps) of the C3 workload: 1 M mixed-collider bodies
+in one large world. With --gpus N > 1 every rank steps its own independent 1 M-body world
+(different seed, no data-path collective): weak scaling over independent worlds, the partition north_star
+names first. `value` is device-resident throughput (state already in HBM); `e2e` goes through the C ABI with
+pinned HOST buffers: poses in (sfg_update_bodies) -> sfg_tick -> poses out (sfg_get_bodies) every step, which is
+what the reference's Game::physics_tick does around PhysicsWorld::tick (game.rs:297-303).
+
+--impl reference times the CPU restatement of the reference tick (oracle/, MODE_REFERENCE, all host threads) on a
+bounded sample of the same workload (the reference itself is Rust and cannot be built in this image).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SUBSTEPS = 4
+FRAME_DT = 1.0 / 60.0
+
+
+def workload(scale, seed):
+    from moleengine_b200 import scenes
+    nx, ny = {"full": (1250, 800), "tenth": (400, 250), "tiny": (100, 50)}[scale]
+    return scenes.c3_mixed(nx, ny, seed=seed)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, device):
+        self.rows, self.proc, self.device = [], None, device
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes_per_tick(st, n_bodies, substeps):
+    """Compulsory HBM bytes of the solver kernel for one tick, from the data layout in DESIGN.md §3:
+    per substep, 384 B per body (integrate 136, contact position gather/scatter 80, derive 80, contact velocity 88),
+    112 B per pair unit (H, G0, G1, L0, L1 once + H, S once) and 72 B per contact entry (manifold + latch written,
+    manifold read back); constraints 96 B per unit, rope particles 64 B."""
+    n_units = int(st["n_pairs"])
+    n_entries = 2 * n_units   # upper bound is exact for body-body pairs; static pairs have one entry
+    per_sub = 384 * n_bodies + 112 * n_units + 72 * n_entries + 96 * int(st["n_constraint_colours"] > 0) * 0 + 64 * int(st["n_rope_particles"])
+    return per_sub * substeps
+
+
+def run_reference(args, rank, world_size):
+    """CPU arm: the oracle port of the reference tick (DFS islands, BVH broadphase, sequential Gauss-Seidel, island-group threads)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    from moleengine_b200 import abi
+    sc = workload("tenth", 0xC3)
+    tun = abi.default_tuning(substeps=SUBSTEPS)
+    cores = os.cpu_count() or 1
+    w = O.OracleWorld(tuning=tun)
+    w.load_scene(sc)
+    nb = len(sc["bodies"])
+    for _ in range(args.warmup):
+        w.tick(FRAME_DT, mode=O.MODE_REFERENCE, threads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        w.tick(FRAME_DT, mode=O.MODE_REFERENCE, threads=cores)
+    dt = time.perf_counter() - t0
+    val = nb * SUBSTEPS * args.steps / dt
+    sample = f"c3_mixed at 1/10 scale ({nb} bodies), {args.steps} ticks of {SUBSTEPS} substeps, f64 oracle port of the reference tick"
+    print(json.dumps({
+        "impl": "reference", "metric": "body-substeps/sec", "value": val, "unit": "body-substeps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": "c3_mixed 1M bodies (reference arm: bounded 1/10-scale sample per step)", "substeps": SUBSTEPS},
+        "cpu_baseline": {"value": val, "unit": "body-substeps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "body-substeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", default="full", choices=["full", "tenth", "tiny"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    from moleengine_b200 import GpuWorld, abi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: moleengine_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sc = workload(args.scale, 0xC3 + rank)
+    nb = len(sc["bodies"])
+    tun = abi.default_tuning(substeps=SUBSTEPS)
+    g = GpuWorld(tuning=tun, device=local_rank)
+    g.load_scene(sc)
+    ff = abi.gravity_field()
+
+    # ---------------- device-resident arm: `value`
+    for _ in range(args.warmup):
+        g.tick(FRAME_DT, None, ff)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    solver_ms, total_ms, broad_ms, graph_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        g.tick(FRAME_DT, None, ff)      # synchronous: returns after the tick's stream has drained
+        st = g.stats()
+        solver_ms += float(st["ms_solver"]); total_ms += float(st["ms_total"]); broad_ms += float(st["ms_broadphase"]); graph_ms += float(st["ms_graph"])
+        launches += int(st["kernel_launches"])
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    step_s = max_over_ranks(wall) / args.steps
+    value = world_size * nb * SUBSTEPS / step_s
+    st = g.stats()
+
+    # ---------------- end-to-end arm: pinned host poses in -> tick -> poses out, through the C ABI
+    host = torch.empty(nb * abi.body_dtype.itemsize, dtype=torch.uint8).pin_memory()
+    host_np = host.numpy().view(abi.body_dtype)
+    host_np[:] = g.get_bodies()
+    lib, h = g.lib, g.h
+    for _ in range(3):
+        lib.sfg_update_bodies(h, 0, nb, abi.ptr(host_np)); g.tick(FRAME_DT, None, ff); lib.sfg_get_bodies(h, 0, nb, abi.ptr(host_np))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        rc = lib.sfg_update_bodies(h, 0, nb, abi.ptr(host_np))
+        assert rc == 0
+        g.tick(FRAME_DT, None, ff)
+        rc = lib.sfg_get_bodies(h, 0, nb, abi.ptr(host_np))
+        assert rc == 0
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e_value = world_size * nb * SUBSTEPS / e2e_s
+    checksum = float(np.abs(host_np["y"][:1000]).sum())   # the step's result is read on the host
+
+    if rank != 0:
+        g.close()
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (persistent solver)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = algorithmic_bytes_per_tick(st, nb, SUBSTEPS)
+    solver_s = solver_ms / args.steps / 1e3
+    achieved = alg_bytes / solver_s / 1e9 if solver_s > 0 else 0.0
+
+    # ---------------- CPU baseline: the oracle port of the reference tick on a bounded sample
+    cpu = None
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py as O
+        from moleengine_b200 import scenes  # noqa: F401
+        scs = workload("tenth", 0xC3)
+        cores = os.cpu_count() or 1
+        ow = O.OracleWorld(tuning=tun)
+        ow.load_scene(scs)
+        ow.tick(FRAME_DT, mode=O.MODE_REFERENCE, threads=cores)
+        t0 = time.perf_counter()
+        n_t = 4
+        for _ in range(n_t):
+            ow.tick(FRAME_DT, mode=O.MODE_REFERENCE, threads=cores)
+        cdt = time.perf_counter() - t0
+        cpu = {"value": len(scs["bodies"]) * SUBSTEPS * n_t / cdt, "unit": "body-substeps/s", "cores": cores, "kind": "port",
+               "sample": f"c3_mixed at 1/10 scale ({len(scs['bodies'])} bodies), {n_t} ticks x {SUBSTEPS} substeps, f64 oracle restatement of the reference tick "
+                         f"(BVH broadphase + DFS islands + sequential GS, island groups on {cores} threads)"}
+
+    out = {
+        "metric": "body-substeps/sec", "value": value, "unit": "body-substeps/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"c3_mixed: {nb} mixed-collider bodies per GPU in one large world ({sc['name']})", "substeps": SUBSTEPS, "frame_hz": 60,
+                   "pairs": int(st["n_pairs"]), "contact_colours": int(st["n_contact_colours"]), "l2": "working set (>1 GB of body + pair columns) exceeds the 126 MB L2",
+                   "parallelism": f"independent worlds x{world_size}", "ticks_hz": 1.0 / step_s},
+        "e2e": {"value": e2e_value, "unit": "body-substeps/s", "h2d_bytes_per_step": nb * abi.body_dtype.itemsize, "d2h_bytes_per_step": nb * abi.body_dtype.itemsize,
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "checksum": checksum},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_solve_persistent", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": solver_s * 1e3},
+        "phases_ms": {"broadphase": broad_ms / args.steps, "graph": graph_ms / args.steps, "solver": solver_ms / args.steps, "device_total": total_ms / args.steps},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    g.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
