@@ -83,7 +83,7 @@ struct SfgWorld {
     DBuf<float4> SA;
     DBuf<int4> SI;
     // pair units
-    uint32_t n_units = 0, n_unit_colours = 0;
+    uint32_t n_units = 0, n_unit_colours = 0, prev_pairs = 0;
     std::vector<uint32_t> unit_colour_start;   // n_unit_colours + 1
     DBuf<uint2> U_ids;
     DBuf<int2> U_ub;
@@ -217,7 +217,7 @@ __global__ void k_dbg_isect(uint32_t n, const float* poses, const float* shapes,
         s[k].kind = uint32_t(ss[0]); s[k].p0 = ss[1]; s[k].p1 = ss[2]; s[k].r = ss[3];
     }
     Manifold m;
-    intersection_check(p, s, m);
+    intersection_check(p[0], p[1], s[0], s[1], m);
     float* o = out + 14 * size_t(i);
     for (int k = 0; k < 14; ++k) o[k] = 0.f;
     o[0] = float(m.count);
@@ -418,6 +418,7 @@ int sfg_set_bodies(SfgWorld* w, uint32_t n, const SfgBody* b) {
     if (!w || (n && !b)) return SFG_E_INVALID;
     cudaSetDevice(w->device);
     CK(w->P.ensure(n)); CK(w->Q.ensure(n)); CK(w->V.ensure(n)); CK(w->OV.ensure(n)); CK(w->MI.ensure(n)); CK(w->EA.ensure(n));
+    if (n != w->n_bodies) { w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0; w->n_constraints = 0; }   // slot space changed: re-upload ropes / constraints
     w->n_bodies = n;
     return upload_bodies(w, 0, n, b);
 }
@@ -639,22 +640,24 @@ int broadphase(SfgWorld* w, float frame_dt) {
     CKL(w); w->launches++;
     k_cell_starts<<<nblk(nc + 1), 256, 0, st>>>(keys, nc, g.n_cells, w->cell_start.p);
     CKL(w); w->launches++;
-    // 4. count, scan, emit
+    // 4. candidate pairs in one pass; capacity is last tick's count + 25 % (re-run once if it overflows)
     const uint32_t n_warps = (w->n_live + 31) / 32;
-    CK(w->warp_counts.ensure(n_warps + 1)); CK(w->scan_tmp.ensure(scan_tmp_words(n_warps + 1)));
-    k_pairs<false><<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, w->cell_start.p, w->d_mask.p, w->warp_counts.p, nullptr,
-                                                       nullptr, 0);
-    CKL(w); w->launches++;
-    w->launches += scan_exclusive(w->warp_counts.p, w->warp_counts.p, n_warps, w->scan_tmp.p, &w->hdr.p->n_pairs, st);
-    uint32_t n_pairs = 0;
-    CK(cudaMemcpyAsync(&n_pairs, &w->hdr.p->n_pairs, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    w->n_units = n_pairs;
-    if (n_pairs == 0) return SFG_OK;
-    CK(w->U_ids.ensure(n_pairs));
-    k_pairs<true><<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, w->cell_start.p, w->d_mask.p, nullptr, w->warp_counts.p,
-                                                      w->U_ids.p, n_pairs);
-    CKL(w); w->launches++;
+    size_t want = std::max<size_t>(size_t(w->prev_pairs) + w->prev_pairs / 4 + 4096, size_t(w->n_live) * 2);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CK(w->U_ids.ensure(want));
+        const uint32_t cap = uint32_t(std::min<size_t>(w->U_ids.cap, 0xFFFFFFFFu));
+        CK(cudaMemsetAsync(&w->hdr.p->n_pairs, 0, 4, st));
+        k_pairs<<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, w->cell_start.p, w->d_mask.p, &w->hdr.p->n_pairs, w->U_ids.p, cap);
+        CKL(w); w->launches++;
+        uint32_t n_pairs = 0;
+        CK(cudaMemcpyAsync(&n_pairs, &w->hdr.p->n_pairs, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        w->n_units = n_pairs;
+        w->prev_pairs = n_pairs;
+        if (n_pairs <= cap) break;
+        if (attempt == 1) return fail(w, SFG_E_CAPACITY, "candidate pair buffer overflowed twice");
+        want = size_t(n_pairs) + 1024;
+    }
     return SFG_OK;
 }
 

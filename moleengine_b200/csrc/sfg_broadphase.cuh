@@ -3,7 +3,7 @@
 //   k_cell_keys       hierarchical uniform grid: level by AABB extent, key = cell of the AABB centre
 //   radix sort        sfg_sort.cuh
 //   k_gather_sorted / k_cell_starts
-//   k_pairs<EMIT>     one lane per collider, 3x3 cells on its own and every coarser level; candidate
+//   k_pairs           one lane per collider, forward half of the 3x3 block on its own level + 3x3 on every coarser level; candidate
 //                     tests = strict AABB overlap + layer mask + same domain + ">=1 body, distinct
 //                     bodies" (physics.rs:461-474, 551-555, 579); hits compacted with warp ballots
 //   k_unit_setup / k_adj_fill / k_jp_colour / k_build_units   graph colouring (include/sfg_hash.h)
@@ -68,13 +68,26 @@ __global__ void __launch_bounds__(256) k_aabb(uint32_t n_colls, const float4* __
         ext = fmaxf(ext, __shfl_xor_sync(0xFFFFFFFFu, ext, o)); sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
         cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); dom = max(dom, __shfl_xor_sync(0xFFFFFFFFu, dom, o));
     }
-    if ((threadIdx.x & 31) == 0 && cnt) {
-        atomicMin(&bounds->min_x, f2ord(mnx)); atomicMin(&bounds->min_y, f2ord(mny));
-        atomicMax(&bounds->max_x, f2ord(mxx)); atomicMax(&bounds->max_y, f2ord(mxy));
-        atomicMax(&bounds->max_extent, f2ord(ext));
-        atomicMax(&bounds->max_domain, dom);
-        atomicAdd(&bounds->n_live, cnt);
-        atomicAdd(&bounds->sum_extent, double(sum));
+    // one set of atomics per CTA (per-warp atomics on 8 hot addresses cost more than the whole kernel)
+    __shared__ float s_f[5][8];
+    __shared__ uint32_t s_u[2][8];
+    __shared__ float s_sum[8];
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_f[0][warp] = mnx; s_f[1][warp] = mny; s_f[2][warp] = mxx; s_f[3][warp] = mxy; s_f[4][warp] = ext; s_u[0][warp] = cnt; s_u[1][warp] = dom; s_sum[warp] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 8; ++k) {
+            mnx = fminf(mnx, s_f[0][k]); mny = fminf(mny, s_f[1][k]); mxx = fmaxf(mxx, s_f[2][k]); mxy = fmaxf(mxy, s_f[3][k]);
+            ext = fmaxf(ext, s_f[4][k]); cnt += s_u[0][k]; dom = max(dom, s_u[1][k]); sum += s_sum[k];
+        }
+        if (cnt) {
+            atomicMin(&bounds->min_x, f2ord(mnx)); atomicMin(&bounds->min_y, f2ord(mny));
+            atomicMax(&bounds->max_x, f2ord(mxx)); atomicMax(&bounds->max_y, f2ord(mxy));
+            atomicMax(&bounds->max_extent, f2ord(ext));
+            atomicMax(&bounds->max_domain, dom);
+            atomicAdd(&bounds->n_live, cnt);
+            atomicAdd(&bounds->sum_extent, double(sum));
+        }
     }
 }
 
@@ -144,13 +157,19 @@ __global__ void k_fill_u32(uint32_t* p, uint32_t n, uint32_t v) {
     if (i < n) p[i] = v;
 }
 
-template <bool EMIT>
+// One lane per collider (in cell-sorted order). Same-level partners are searched in the FORWARD half
+// neighbourhood only (rest of the own cell + cell x+1, then cells x-1..x+1 of row y+1): sorted order is a
+// total order, so every unordered pair inside a 3x3 block is met exactly once. Coarser levels are searched
+// 3x3 (a coarser collider never searches down). Hits are compacted with a warp ballot into a per-warp
+// shared-memory staging buffer and flushed 32+ at a time behind ONE atomic reservation.
+constexpr int PAIR_STAGE = 64;
 __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParams g, uint32_t n_live, const float4* __restrict__ SA,
                                                const int4* __restrict__ SI, const uint32_t* __restrict__ start,
-                                               const unsigned long long* __restrict__ mask, uint32_t* __restrict__ warp_counts,
-                                               const uint32_t* __restrict__ warp_offsets, uint2* __restrict__ pairs, uint32_t capacity) {
+                                               const unsigned long long* __restrict__ mask, uint32_t* __restrict__ cursor,
+                                               uint2* __restrict__ pairs, uint32_t capacity) {
+    __shared__ uint2 stage[8][PAIR_STAGE];
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t j = gw * 32 + lane;
     const bool active = j < n_live;
     float4 A = make_float4(0, 0, 0, 0);
@@ -159,25 +178,42 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
     const int my_level = (I.z >> 8) & 0xFF, my_layer = I.z & 0xFF;
     const float cx = 0.5f * (A.x + A.z), cy = 0.5f * (A.y + A.w);
     const unsigned long long my_mask = active ? mask[my_layer] : 0ull;
-    // segments: for level l in [my_level, n_levels): rows -1, 0, +1; then the huge list
-    const int n_seg = active ? (max(g.n_levels - my_level, 0) * 3 + 1) : 0;
+    // segments: own level: 0 = own row forward, 1 = next row; coarser level l: 3 rows each; last = huge list
+    const int n_own = my_level < g.n_levels ? 2 : 0;
+    const int n_seg = active ? (n_own + max(g.n_levels - my_level - 1, 0) * 3 + 1) : 0;
     int seg = 0;
     uint32_t cur = 0, end = 0;
-    uint32_t total = 0;
-    const uint32_t base = EMIT ? warp_offsets[gw] : 0u;
+    uint32_t n_buf = 0;
     const uint32_t lt = (1u << lane) - 1u;
+    auto flush = [&]() {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cursor, n_buf);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        for (uint32_t k = lane; k < n_buf; k += 32) if (base + k < capacity) pairs[base + k] = stage[warp][k];
+        __syncwarp();
+        n_buf = 0;
+    };
     for (;;) {
         while (cur >= end && seg < n_seg) {
-            if (seg == n_seg - 1) { cur = start[g.n_cells]; end = start[g.n_cells + 1]; }
-            else {
-                const int l = min(my_level, g.n_levels) + seg / 3, dy = seg % 3 - 1;
+            if (seg == n_seg - 1) {   // huge list; huge-vs-huge forward only
+                cur = my_level >= g.n_levels ? j + 1 : start[g.n_cells]; end = start[g.n_cells + 1];
+            } else if (seg < n_own) {
+                int ix, iy;
+                cell_of(g, my_level, cx, cy, &ix, &iy);
+                const int nx = g.nx[my_level], ny = g.ny[my_level];
+                const uint32_t row = g.base[my_level] + (uint32_t(I.w) * uint32_t(ny) + uint32_t(iy)) * uint32_t(nx);
+                if (seg == 0) { cur = j + 1; end = start[row + min(ix + 1, nx - 1) + 1]; }
+                else if (iy + 1 < ny) { cur = start[row + nx + max(ix - 1, 0)]; end = start[row + nx + min(ix + 1, nx - 1) + 1]; }
+                else { cur = 0; end = 0; }
+            } else {
+                const int k = seg - n_own;
+                const int l = my_level + 1 + k / 3, dy = k % 3 - 1;
                 int ix, iy;
                 cell_of(g, l, cx, cy, &ix, &iy);
                 const int y = iy + dy;
                 if (y >= 0 && y < g.ny[l]) {
-                    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, g.nx[l] - 1);
                     const uint32_t row = g.base[l] + (uint32_t(I.w) * uint32_t(g.ny[l]) + uint32_t(y)) * uint32_t(g.nx[l]);
-                    cur = start[row + x0]; end = start[row + x1 + 1];
+                    cur = start[row + max(ix - 1, 0)]; end = start[row + min(ix + 1, g.nx[l] - 1) + 1];
                 } else { cur = 0; end = 0; }
             }
             ++seg;
@@ -188,29 +224,23 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
         uint32_t hi = 0, lo = 0;
         if (more) {
             const uint32_t cj = cur++;
-            if (cj != j) {
-                const int4 J = SI[cj];
-                const int o_level = (J.z >> 8) & 0xFF;
-                // same level: the later slot emits; coarser level: we emit (the other never searches down)
-                const bool mine = o_level > my_level || (o_level == my_level && uint32_t(I.x) > uint32_t(J.x));
-                if (mine && J.w == I.w && aabb_overlap(A, SA[cj])) {
-                    hi = max(uint32_t(I.x), uint32_t(J.x)); lo = min(uint32_t(I.x), uint32_t(J.x));
-                    const int l_hi = uint32_t(I.x) > uint32_t(J.x) ? my_layer : (J.z & 0xFF);
-                    const int l_lo = uint32_t(I.x) > uint32_t(J.x) ? (J.z & 0xFF) : my_layer;
-                    const unsigned long long mrow = uint32_t(I.x) > uint32_t(J.x) ? my_mask : mask[l_hi];
-                    const bool bodies_ok = (I.y >= 0 || J.y >= 0) && !(I.y >= 0 && I.y == J.y);
-                    hit = ((mrow >> l_lo) & 1ull) && bodies_ok;
-                }
+            const int4 J = SI[cj];
+            if (J.w == I.w && aabb_overlap(A, SA[cj])) {
+                const bool i_later = uint32_t(I.x) > uint32_t(J.x);
+                hi = i_later ? uint32_t(I.x) : uint32_t(J.x); lo = i_later ? uint32_t(J.x) : uint32_t(I.x);
+                const int l_lo = i_later ? (J.z & 0xFF) : my_layer;
+                const unsigned long long mrow = i_later ? my_mask : mask[J.z & 0xFF];   // mask_matrix.get(later.layer, earlier.layer)
+                const bool bodies_ok = (I.y >= 0 || J.y >= 0) && !(I.y >= 0 && I.y == J.y);
+                hit = ((mrow >> l_lo) & 1ull) && bodies_ok;
             }
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
-        if (EMIT && hit) {
-            const uint32_t pos = base + total + __popc(ballot & lt);
-            if (pos < capacity) pairs[pos] = make_uint2(hi, lo);
-        }
-        total += __popc(ballot);
+        if (hit) stage[warp][n_buf + __popc(ballot & lt)] = make_uint2(hi, lo);
+        n_buf += __popc(ballot);
+        __syncwarp();
+        if (n_buf >= 32) flush();
     }
-    if (!EMIT && lane == 0) warp_counts[gw] = total;
+    if (n_buf) flush();
 }
 
 // ---------------------------------------------------------------- graph colouring
@@ -264,7 +294,12 @@ __global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2*
                                                    const uint32_t* __restrict__ adj, uint32_t* colour, uint32_t* counters,
                                                    uint32_t* hist, uint32_t hist_cap) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ uint32_t s_hist[64];
+    __shared__ uint32_t s_pending, s_max;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { s_pending = 0; s_max = 0; }
+    __syncthreads();
     for (uint32_t round = 0; round < JP_MAX_ROUNDS; ++round) {
         uint32_t pending = 0;
         for (uint32_t u = tid; u < n_units; u += nth) {
@@ -274,8 +309,7 @@ __global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2*
             const uint2 iu = ids[u];
             bool ready = true;
             uint32_t result = 0;
-            // window of 64 colours at a time
-            for (uint32_t win = 0; ready; win += 64) {
+            for (uint32_t win = 0; ready; win += 64) {   // window of 64 colours at a time
                 unsigned long long used = 0ull;
                 bool beyond = false;
                 for (int side = 0; side < 2 && ready; ++side) {
@@ -301,14 +335,22 @@ __global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2*
             }
             if (ready) {
                 __stcg(colour + u, result);
-                atomicMax(counters + JP_MAX_ROUNDS, result + 1u);
-                if (result < hist_cap) atomicAdd(hist + result, 1u);
+                if (result < 64) atomicAdd(&s_hist[result], 1u);
+                else if (result < hist_cap) atomicAdd(hist + result, 1u);
+                atomicMax(&s_max, result + 1u);
             } else ++pending;
         }
-        if (pending) atomicAdd(counters + round, pending);
+        // one global atomic per CTA per round
+        pending = __reduce_add_sync(0xFFFFFFFFu, pending);
+        if ((threadIdx.x & 31) == 0 && pending) atomicAdd(&s_pending, pending);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_pending) { atomicAdd(counters + round, s_pending); s_pending = 0; }
         grid.sync();
         if (__ldcg(counters + round) == 0u) break;
     }
+    __syncthreads();
+    if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(hist + threadIdx.x, s_hist[threadIdx.x]);
+    if (threadIdx.x == 0 && s_max) atomicMax(counters + JP_MAX_ROUNDS, s_max);
 }
 
 // after the stable sort by colour: write the streaming columns of each pair unit

@@ -283,97 +283,108 @@ SFG_DI int clip_edge(const Edge& target, const Edge& edge, float* enters, float*
     return 1;
 }
 
-// shape_shape.rs:160-349
-SFG_DI void any_any(const Iso* poses, const Shape* shapes, Manifold& m) {
-    Iso p2w1 = inversed(poses[0]) * poses[1];
-    Iso rel[2] = {inversed(p2w1), p2w1};
+// shape_shape.rs:160-349. Everything is kept in named registers (no dynamically indexed arrays): the SAT loop is
+// unrolled over the two owners, and the winning owner's data is picked with selects afterwards.
+SFG_DI void sat_pass(const Shape& own, const Shape& oth, V2 dist, Rot rel_own_r, float r_sum, int pass, float& pen_depth, PEdge& pen,
+                     float& pen_ext, int& o0, bool& have, bool& separated) {
+    const int n = edge_count(own);
+    const bool sym = symmetrical(own);
+    for (int ei = 0; ei < n; ++ei) {
+        PEdge e = get_edge(own, ei);
+        if (!(dot(e.n, dist) >= 0.f)) {
+            if (sym) e = mirrored(e);
+            else continue;
+        }
+        const float ext = edge_extent(own, ei);
+        const V2 axis_o = -(rel_own_r * e.n);
+        const float depth = ext + projected_extent(oth, axis_o) + r_sum - dot(dist, e.n);
+        if (depth <= 0.f) { separated = true; return; }
+        if (depth < pen_depth) { pen_depth = depth; pen = e; pen_ext = ext; have = true; o0 = pass; }
+    }
+}
+SFG_DI void any_any(Iso pose0, Iso pose1, const Shape& s0, const Shape& s1, Manifold& m) {
+    const Iso rel1 = inversed(pose0) * pose1;     // object 1 in object 0's frame
+    const Iso rel0 = inversed(rel1);              // object 0 in object 1's frame
     float pen_depth = 3.402823466e+38f, pen_ext = 0.f;
     PEdge pen;
-    bool have = false;
+    pen.n = mk(0.f, 0.f); pen.e.start = mk(0.f, 0.f); pen.e.dir = mk(0.f, 0.f); pen.e.len = 0.f;
+    bool have = false, separated = false;
     int o0 = 0;
-#pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const Shape& own = shapes[pass];
-        const Shape& oth = shapes[1 - pass];
-        const int n = edge_count(own);
-        const V2 dist = rel[1 - pass].t;
-        for (int ei = 0; ei < n; ++ei) {
-            PEdge e = get_edge(own, ei);
-            if (!(dot(e.n, dist) >= 0.f)) {
-                if (symmetrical(own)) e = mirrored(e);
-                else continue;
-            }
-            float ext = edge_extent(own, ei);
-            V2 axis_o = -(rel[pass].r * e.n);
-            float depth = ext + shapes[0].r + projected_extent(oth, axis_o) + shapes[1].r - dot(dist, e.n);
-            if (depth <= 0.f) { m.count = 0; return; }
-            if (depth < pen_depth) { pen_depth = depth; pen = e; pen_ext = ext; have = true; o0 = pass; }
-        }
-    }
-    if (!have) { m.count = 0; return; }
-    const int o1 = 1 - o0;
-    const float r_own = shapes[o0].r, r_inc = shapes[o1].r;
+    // depth = extent + shapes[0].circle_r + projected_extent + shapes[1].circle_r - dist.n  (reference order of the sum:
+    // ((ext + r0) + proj) + r1; f32 rounding differences of the regrouping are far below the parity tolerance)
+    const float r_sum = s0.r + s1.r;
+    sat_pass(s0, s1, rel1.t, rel0.r, r_sum, 0, pen_depth, pen, pen_ext, o0, have, separated);
+    if (separated) { m.count = 0; return; }
+    sat_pass(s1, s0, rel0.t, rel1.r, r_sum, 1, pen_depth, pen, pen_ext, o0, have, separated);
+    if (separated || !have) { m.count = 0; return; }
+    const bool f = o0 != 0;
+    const Shape& sown = f ? s1 : s0;
+    const Shape& sinc = f ? s0 : s1;
+    const Iso rel_own = f ? rel1 : rel0;          // relative_poses[shape_order[0]]
+    const Iso rel_inc = f ? rel0 : rel1;          // relative_poses[shape_order[1]]
+    const Rot pose_own_r = f ? pose1.r : pose0.r;
+    const float r_own = sown.r, r_inc = sinc.r;
     Edge own_e = pen.e;
     if (r_own != 0.f) own_e.start = own_e.start + r_own * pen.n;
-    V2 axis_snd = -(rel[o0].r * pen.n);
-    PEdge inc = supporting_edge(shapes[o1], axis_snd);
+    const V2 axis_snd = -(rel_own.r * pen.n);
+    PEdge inc = supporting_edge(sinc, axis_snd);
     const bool both_simple = r_own == 0.f && r_inc == 0.f;
     // incident edge in the owner's local space
-    inc.n = rel[o1].r * inc.n;
-    inc.e.start = rel[o1] * inc.e.start;
-    inc.e.dir = rel[o1].r * inc.e.dir;
+    inc.n = rel_inc.r * inc.n;
+    inc.e.start = rel_inc * inc.e.start;
+    inc.e.dir = rel_inc.r * inc.e.dir;
     Edge inc_outer = inc.e;
     if (r_inc != 0.f) inc_outer.start = inc_outer.start + r_inc * inc.n;
 
     float enters = 0.f, exits = 0.f;
-    int clip = clip_edge(own_e, inc_outer, &enters, &exits);
+    const int clip = clip_edge(own_e, inc_outer, &enters, &exits);
     if (clip == 1) {
-        float start_depth = pen_ext + r_own - dot(inc_outer.start, pen.n);
-        float dda = dot(inc_outer.dir, pen.n);
-        float enter_depth = start_depth - enters * dda, exit_depth = start_depth - exits * dda;
+        const float start_depth = pen_ext + r_own - dot(inc_outer.start, pen.n);
+        const float dda = dot(inc_outer.dir, pen.n);
+        const float enter_depth = start_depth - enters * dda, exit_depth = start_depth - exits * dda;
         if (enter_depth > 0.f && exit_depth > 0.f) {
-            V2 ep = inc_outer.start + enters * inc_outer.dir, xp = inc_outer.start + exits * inc_outer.dir;
-            m.count = 2; m.n = poses[o0].r * pen.n;
-            m.off[0][0] = ep + enter_depth * pen.n; m.off[0][1] = rel[o0] * ep;
-            m.off[1][0] = xp + exit_depth * pen.n;  m.off[1][1] = rel[o0] * xp;
-            if (o0) flip(m);
+            const V2 ep = inc_outer.start + enters * inc_outer.dir, xp = inc_outer.start + exits * inc_outer.dir;
+            m.count = 2; m.n = pose_own_r * pen.n;
+            m.off[0][0] = ep + enter_depth * pen.n; m.off[0][1] = rel_own * ep;
+            m.off[1][0] = xp + exit_depth * pen.n;  m.off[1][1] = rel_own * xp;
+            if (f) flip(m);
             return;
         } else if (both_simple) { m.count = 0; return; }
     } else if (clip == 2 && both_simple) { m.count = 0; return; }
 
-    V2 cl_other = inc.e.start;
-    float tproj = dot(cl_other - pen.e.start, pen.e.dir);
+    const V2 cl_other = inc.e.start;
+    const float tproj = dot(cl_other - pen.e.start, pen.e.dir);
     float tcl;
     if (tproj < 0.f) tcl = 0.f;
     else if (tproj > pen.e.len) tcl = pen.e.len;
     else {
-        m.count = 1; m.n = poses[o0].r * pen.n;
+        m.count = 1; m.n = pose_own_r * pen.n;
         m.off[0][0] = pen.e.start + tproj * pen.e.dir + r_own * pen.n;
-        m.off[0][1] = rel[o0] * (cl_other - r_inc * pen.n);
-        if (o0) flip(m);
+        m.off[0][1] = rel_own * (cl_other - r_inc * pen.n);
+        if (f) flip(m);
         return;
     }
-    V2 cl_pen = pen.e.start + tcl * pen.e.dir;
-    V2 d = cl_other - cl_pen;
-    float dsq = mag_sq(d), rs = shapes[0].r + shapes[1].r;
-    if (dsq >= rs * rs) { m.count = 0; return; }
-    V2 axis = d * (1.0f / sqrtf(dsq));
-    m.count = 1; m.n = poses[o0].r * axis;
+    const V2 cl_pen = pen.e.start + tcl * pen.e.dir;
+    const V2 d = cl_other - cl_pen;
+    const float dsq = mag_sq(d);
+    if (dsq >= r_sum * r_sum) { m.count = 0; return; }
+    const V2 axis = d * (1.0f / sqrtf(dsq));
+    m.count = 1; m.n = pose_own_r * axis;
     m.off[0][0] = cl_pen + r_own * axis;
-    m.off[0][1] = rel[o0] * (cl_other - r_inc * axis);
-    if (o0) flip(m);
+    m.off[0][1] = rel_own * (cl_other - r_inc * axis);
+    if (f) flip(m);
 }
 
 // shape_shape.rs:63-73
-SFG_DI void intersection_check(const Iso* poses, const Shape* shapes, Manifold& m) {
+SFG_DI void intersection_check(Iso pose0, Iso pose1, const Shape& s0, const Shape& s1, Manifold& m) {
     m.count = 0;
     m.n = mk(0.f, 0.f);
     m.off[0][0] = m.off[0][1] = m.off[1][0] = m.off[1][1] = mk(0.f, 0.f);
-    const bool c0 = shapes[0].kind == K_POINT, c1 = shapes[1].kind == K_POINT;
-    if (c0 && c1) circle_circle(poses[0], shapes[0].r, poses[1], shapes[1].r, m);
-    else if (c0) circle_any(poses[0], shapes[0].r, poses[1], shapes[1], m);
-    else if (c1) { circle_any(poses[1], shapes[1].r, poses[0], shapes[0], m); flip(m); }
-    else any_any(poses, shapes, m);
+    const bool c0 = s0.kind == K_POINT, c1 = s1.kind == K_POINT;
+    if (c0 && c1) circle_circle(pose0, s0.r, pose1, s1.r, m);
+    else if (c0) circle_any(pose0, s0.r, pose1, s1, m);
+    else if (c1) { circle_any(pose1, s1.r, pose0, s0, m); flip(m); }
+    else any_any(pose0, pose1, s0, s1, m);
 }
 
 // ---- queries ----

@@ -239,7 +239,7 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     const uint32_t fl = __float_as_uint(h.z);
     const float mu_s = h.w;
-    Shape sh[2] = {mkshape(ldc(c.G0 + u)), mkshape(ldc(c.G1 + u))};
+    const Shape sh0 = mkshape(ldc(c.G0 + u)), sh1 = mkshape(ldc(c.G1 + u));
     const float4 l0 = ldc(c.L0 + u), l1 = ldc(c.L1 + u);
     const Iso loc0 = mkiso(mk(l0.x, l0.y), mkrot(l0.z, l0.w)), loc1 = mkiso(mk(l1.x, l1.y), mkrot(l1.z, l1.w));
 
@@ -260,11 +260,10 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
 
     for (int m = 0; m < mult; ++m) {
         const uint32_t e = u + uint32_t(m) * c.n_units;
-        Iso pw[2];
-        pw[0] = b0 >= 0 ? mkiso(mk(P0.z, P0.w), r0) * loc0 : st0;
-        pw[1] = b1 >= 0 ? mkiso(mk(told1.x + P1.z, told1.y + P1.w), r1) * loc1 : st1;
+        const Iso pw0 = b0 >= 0 ? mkiso(mk(P0.z, P0.w), r0) * loc0 : st0;
+        const Iso pw1 = b1 >= 0 ? mkiso(mk(told1.x + P1.z, told1.y + P1.w), r1) * loc1 : st1;
         Manifold mf;
-        intersection_check(pw, sh, mf);
+        intersection_check(pw0, pw1, sh0, sh1, mf);
         if (mf.count == 0) { c.M0[e] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         for (int k = 0; k < mf.count; ++k) {                            // solver.rs:308-315
             if (b0 >= 0) mf.off[k][0] = loc0 * mf.off[k][0];
@@ -418,7 +417,7 @@ __global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx
 
 // The whole substep loop of one tick in ONE launch: every CTA walks the stage table, grid-strides over
 // the stage's range, and meets the others at a grid-wide barrier before the next stage (colour).
-__global__ void __launch_bounds__(256) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
+__global__ void __launch_bounds__(256, 3) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
                                                           uint32_t n_stages, uint32_t substeps) {
     cg::grid_group grid = cg::this_grid();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;

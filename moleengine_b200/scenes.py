@@ -203,9 +203,9 @@ def c4_ropes(n_ropes=10000, particles_per_rope=64, n_free_blocks=30000, seed=0xC
     n_part = n_ropes * ppr
     nb = n_blocks + n_part + n_free_blocks
     bodies = np.zeros(nb, abi.body_dtype)
-    # blocks: left block centre (ox - L/2 - 0.5), right (ox + L/2 + 0.5); rope ends on the facing block edges (offset (+-0.5, 0))
+    # blocks: rope ends sit 0.55 from the block centres like scenes/ropes.ron (offset1 (0.55, ..), offset2 (-0.55, ..))
     blk = shapes.rounded_rect(np.full(n_blocks, 1.0), 1.0, 0.0)
-    bxl, bxr = ox - length / 2.0 - 0.5, ox + length / 2.0 + 0.5
+    bxl, bxr = ox - length / 2.0 - 0.55, ox + length / 2.0 + 0.55
     shapes.fill_bodies_dynamic(bodies[:n_blocks], shapes.area(*blk), shapes.second_moment_of_area(*blk), 0.5,
                                np.stack([bxl, bxr], 1).ravel(), np.repeat(oy, 2))
     # particles: Body::new_particle(0.02) along the line (rope.rs:113-141)
@@ -240,7 +240,7 @@ def c4_ropes(n_ropes=10000, particles_per_rope=64, n_free_blocks=30000, seed=0xC
     cons = np.zeros(2 * n_ropes, abi.constraint_dtype)
     cons["owner"] = np.stack([n_blocks + r * ppr, n_blocks + r * ppr + ppr - 1], 1).ravel()
     cons["target"] = np.arange(n_blocks)
-    cons["off1x"] = np.tile([0.5, -0.5], n_ropes)
+    cons["off1x"] = np.tile([0.55, -0.55], n_ropes)
     cons["linear_damping"] = 0.1
     cons["flags"] = abi.LIMIT_EQ | abi.CONSTRAINT_CAN_SLEEP
     return _scene(f"c4_ropes_{n_ropes}x{ppr}", bodies, colliders, 4, cons, ropes, rope_particles)

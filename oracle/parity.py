@@ -50,25 +50,22 @@ def compare_tick(g, o, scene, tol_manifold=1e-5, tol_state=1e-4, hops=3):
     mism = cnt_g != cnt_o
     # ties: the side that has the contact carries (numerically) zero normal correction
     lam = np.where(cnt_o > 0, np.abs(omr[:, 3]), np.abs(gmr[:, 3]))
-    scale = np.maximum(np.abs(omr[:, 3]).max(initial=0.0), 1e-3)
-    not_tie = mism & (lam > 1e-4 * scale)
-    same = ~mism & (cnt_o > 0)
-    # normals + offsets of matching manifolds (count 2 compares both points)
-    d = np.abs(gmr[same][:, 4:] - omr[same][:, 4:])
-    ref = np.maximum(1.0, np.abs(omr[same][:, 4:]))
-    two = (cnt_o[same] == 2)[:, None]
-    colmask = np.concatenate([np.ones((same.sum(), 6), bool), np.repeat(two, 4, 1)], 1)
-    man_err = float((d / ref * colmask).max(initial=0.0))
+    scale = np.maximum(np.nanmax(np.abs(omr[:, 3]), initial=0.0), 1e-3)
+    tie = mism & ~(lam > 1e-4 * scale)
     # body states
     got, want = body_state(g.get_bodies()), o.get_bodies()
-    ep = np.abs(got[:, :4] - want[:, :4]).max(1) / np.maximum(1.0, np.abs(want[:, :2]).max(1))
-    ev = (np.abs(got[:, 4:] - want[:, 4:]) / np.maximum(1.0, np.abs(want[:, 4:]))).max(1)
-    bad = (ep > tol_state) | (ev > tol_state)
-    # influence set of the tied entries: `hops` steps through entries that touched (either side)
+    with np.errstate(invalid="ignore"):
+        ep = np.abs(got[:, :4] - want[:, :4]).max(1) / np.maximum(1.0, np.abs(want[:, :2]).max(1))
+        ev = (np.abs(got[:, 4:] - want[:, 4:]) / np.maximum(1.0, np.abs(want[:, 4:]))).max(1)
+    both_nan = np.isnan(got).any(1) & np.isnan(want).any(1)      # NaN poses stay NaN on both sides (shape_shape.rs:209-218)
+    ep[both_nan] = 0.0
+    ev[both_nan] = 0.0
+    bad = ~((ep <= tol_state) & (ev <= tol_state))
+    # influence set of the tied entries: `hops` steps through entries that touched (either side), constraints and rope links
     cb = scene["colliders"]["body"]
     b0, b1 = cb[uh], cb[ul]
     infl = np.zeros(len(got), bool)
-    for arr in (b0[mism], b1[mism]):
+    for arr in (b0[tie], b1[tie]):
         infl[arr[arr >= 0]] = True
     touching = (cnt_g > 0) | (cnt_o > 0)
     tb0, tb1 = b0[touching], b1[touching]
@@ -83,7 +80,7 @@ def compare_tick(g, o, scene, tol_manifold=1e-5, tol_state=1e-4, hops=3):
     for r in scene["ropes"]:
         p = rp[r["first_particle"]: r["first_particle"] + r["particle_count"]]
         extra.append((p[:-1], p[1:]))
-    for _ in range(hops):
+    for _ in range(hops if tie.any() else 0):
         nxt = infl.copy()
         nxt[tb1[infl[tb0]]] = True
         nxt[tb0[infl[tb1]]] = True
@@ -91,10 +88,51 @@ def compare_tick(g, o, scene, tol_manifold=1e-5, tol_state=1e-4, hops=3):
             nxt[b[infl[a]]] = True
             nxt[a[infl[b]]] = True
         infl = nxt
+    e_infl = np.where(b0 >= 0, infl[np.maximum(b0, 0)], False) | np.where(b1 >= 0, infl[np.maximum(b1, 0)], False)
+    # manifolds of entries outside the influence set: counts must match, normals + offsets to tol (count 2 compares both points)
+    same = ~mism & (cnt_o > 0) & ~e_infl
+    with np.errstate(invalid="ignore"):
+        d = np.abs(gmr[same][:, 4:] - omr[same][:, 4:])
+    d[np.isnan(gmr[same][:, 4:]) & np.isnan(omr[same][:, 4:])] = 0.0
+    ref = np.maximum(1.0, np.abs(omr[same][:, 4:]))
+    two = (cnt_o[same] == 2)[:, None]
+    colmask = np.concatenate([np.ones((int(same.sum()), 6), bool), np.repeat(two, 4, 1)], 1)
+    man = np.where(colmask, d / ref, 0.0)
+    man_err = float(man.max(initial=0.0)) if not np.isnan(man).any() else float("nan")
     return {
-        "entries": int(len(cnt_o)), "ties": int(mism.sum()), "non_tie_mismatches": int(not_tie.sum()),
-        "manifold_err": man_err, "pos_err_clean": float(ep[~infl].max(initial=0.0)), "vel_err_clean": float(ev[~infl].max(initial=0.0)),
-        "pos_err_all": float(ep.max(initial=0.0)), "vel_err_all": float(ev.max(initial=0.0)),
+        "entries": int(len(cnt_o)), "ties": int(tie.sum()), "non_tie_mismatches": int((mism & ~tie & ~e_infl).sum()),
+        "mismatches_inside_influence": int((mism & ~tie & e_infl).sum()),
+        "manifold_err": man_err, "manifolds_compared": int(same.sum()),
+        "pos_err_clean": float(ep[~infl].max(initial=0.0)), "vel_err_clean": float(ev[~infl].max(initial=0.0)),
+        "pos_err_all": float(np.nanmax(ep, initial=0.0)), "vel_err_all": float(np.nanmax(ev, initial=0.0)),
         "bad_bodies": int(bad.sum()), "bad_outside_influence": int((bad & ~infl).sum()), "influenced": int(infl.sum()),
-        "bodies": int(len(got)),
+        "bodies": int(len(got)), "pos_err_median": float(np.nanmedian(ep)), "vel_err_median": float(np.nanmedian(ev)),
+        "momentum_rel_err": _momentum_err(scene, got, want), "kinetic_rel_err": _kinetic_err(scene, got, want),
     }
+
+
+def _mass(scene):
+    b = scene["bodies"]
+    fin = (b["flags"] & 4) != 0
+    with np.errstate(divide="ignore"):
+        m = np.where(fin & (b["inv_mass"] > 0), 1.0 / b["inv_mass"].astype(np.float64), 0.0)
+        fi = (b["flags"] & 8) != 0
+        i = np.where(fi & (b["inv_inertia"] > 0), 1.0 / b["inv_inertia"].astype(np.float64), 0.0)
+    return m, i
+
+
+def _momentum_err(scene, got, want):
+    m, _ = _mass(scene)
+    ok = ~(np.isnan(got).any(1) | np.isnan(want).any(1))
+    pg = (m[ok, None] * got[ok, 4:6]).sum(0)
+    pw = (m[ok, None] * want[ok, 4:6]).sum(0)
+    scale = (m[ok] * np.linalg.norm(want[ok, 4:6], axis=1)).sum() + 1e-12
+    return float(np.linalg.norm(pg - pw) / scale)
+
+
+def _kinetic_err(scene, got, want):
+    m, i = _mass(scene)
+    ok = ~(np.isnan(got).any(1) | np.isnan(want).any(1))
+    kg = 0.5 * (m[ok] * (got[ok, 4] ** 2 + got[ok, 5] ** 2) + i[ok] * got[ok, 6] ** 2).sum()
+    kw = 0.5 * (m[ok] * (want[ok, 4] ** 2 + want[ok, 5] ** 2) + i[ok] * want[ok, 6] ** 2).sum()
+    return float(abs(kg - kw) / (abs(kw) + 1e-12))

@@ -1,0 +1,196 @@
+"""GPU parity on the other BASELINE configs (scaled down so the oracle finishes in seconds): ropes + attachment
+constraints (C4), batched independent worlds with casts (C5), the circle pile (C2), plus edge cases."""
+import numpy as np
+import pytest
+
+import parity
+from moleengine_b200 import GpuWorld, SfgError, abi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _replay(oracle, sc, substeps=1, ff=None, f32=False):
+    tun = abi.default_tuning(substeps=substeps)
+    g = GpuWorld(tuning=tun)
+    g.load_scene(sc)
+    g.tick(forcefield=ff)
+    o = oracle.OracleWorld(tuning=tun, use_f32=f32)
+    o.load_scene(sc)
+    o.set_external_pairs(g.debug_pairs())
+    o.tick(mode=oracle.MODE_COLOURED, forcefield=ff)
+    return g, o
+
+
+def _check(r, ties_frac=0.02):
+    print(r)
+    assert r["non_tie_mismatches"] == 0
+    assert r["ties"] <= ties_frac * max(r["entries"], 50)
+    assert r["manifold_err"] < 1e-5 and r["manifolds_compared"] > 0
+    assert r["bad_outside_influence"] == 0
+    assert r["influenced"] < r["bodies"]
+
+
+def test_c4_ropes_and_attachments(oracle):
+    sc = scenes.c4_ropes(n_ropes=24, particles_per_rope=32, n_free_blocks=60)
+    # let the free blocks start right on the ropes so rope-body contacts (normal fix-up) are exercised
+    g, o = _replay(oracle, sc)
+    r = parity.compare_tick(g, o, sc)
+    _check(r)
+    # constraint colouring bit-exact
+    idx, mult, col = g.debug_constraint_units()
+    oi, om, oc = o.constraint_units()
+    assert dict(zip(idx.tolist(), zip(mult.tolist(), col.tolist()))) == dict(zip(oi.tolist(), zip(om.tolist(), oc.tolist())))
+    g.close()
+
+
+def test_c4_ropes_settled_contacts(oracle):
+    """Run the GPU for a while so blocks are lying on the ropes, then compare ONE tick from that state."""
+    sc = scenes.c4_ropes(n_ropes=12, particles_per_rope=32, n_free_blocks=48)
+    tun = abi.default_tuning(substeps=4)
+    g = GpuWorld(tuning=tun)
+    g.load_scene(sc)
+    for _ in range(45):
+        g.tick()
+    sc2 = dict(sc)
+    sc2["bodies"] = g.get_bodies()
+    g.close()
+    g, o = _replay(oracle, sc2)
+    r = parity.compare_tick(g, o, sc2)
+    _check(r, ties_frac=0.05)
+    m = g.debug_manifolds()
+    assert (m[:, 2] > 0).sum() > 10      # there really are contacts
+    g.close()
+
+
+def test_c5_worlds_and_casts(oracle):
+    nw, bps = 6, 6
+    sc = scenes.c5_worlds(n_worlds=nw, bodies_per_side=bps)
+    g, o = _replay(oracle, sc)
+    # no pair may cross worlds
+    p = g.debug_pairs()
+    dom = sc["colliders"]["domain"]
+    assert len(p) > 0 and np.all(dom[p[:, 0]] == dom[p[:, 1]])
+    _check(parity.compare_tick(g, o, sc))
+    # batched raycasts + spherecasts over the tick-time grid vs the oracle's closed form (f32 oracle: same arithmetic)
+    rays = scenes.c5_rays(sc["bodies"], nw, bps * bps, rays_per_world=64)
+    hits = g.cast_batch(rays)
+    o32 = oracle.OracleWorld(use_f32=True, tuning=abi.default_tuning(substeps=1))
+    sc_after = dict(sc)
+    sc_after["bodies"] = g.get_bodies()
+    # oracle needs the same tick-time boxes: tick it from the same start, then give it the GPU's post-tick bodies
+    o32.load_scene(sc)
+    o32.set_external_pairs(g.debug_pairs())
+    o32.tick(mode=oracle.MODE_COLOURED)
+    o32.set_bodies(sc_after["bodies"])
+    want = o32.cast_batch(rays, use_bvh=False)
+    assert (hits["collider"] >= 0).sum() > len(rays) // 2
+    same = hits["collider"] == want[:, 0].astype(np.int32)
+    # a different collider is acceptable only on an exact-distance tie
+    assert np.all(same | (np.abs(hits["t"] - want[:, 1]) <= 1e-4 * np.maximum(1.0, want[:, 1])))
+    ok = same & (hits["collider"] >= 0)
+    assert np.allclose(hits["t"][ok], want[ok, 1], rtol=1e-4, atol=1e-5)
+    assert np.allclose(hits["px"][ok], want[ok, 2], rtol=1e-4, atol=1e-4) and np.allclose(hits["py"][ok], want[ok, 3], rtol=1e-4, atol=1e-4)
+    assert np.allclose(hits["nx"][ok], want[ok, 4], atol=1e-3) and np.allclose(hits["ny"][ok], want[ok, 5], atol=1e-3)
+    # point queries
+    pts = np.stack([sc_after["bodies"]["x"][:200], sc_after["bodies"]["y"][:200]], 1).astype(np.float32)
+    doms = (np.arange(200) // (bps * bps)).astype(np.uint32)
+    out, cnt = g.query_point_batch(pts, doms, max_hits=8)
+    for i in range(0, 200, 7):
+        want_c = sorted(o32.query_point(float(pts[i, 0]), float(pts[i, 1]), int(doms[i])).tolist())
+        got_c = sorted(out[i, : cnt[i]].tolist())
+        assert got_c == want_c
+    g.close()
+
+
+def test_c2_pile_after_settling(oracle):
+    sc = scenes.c2_circles(40, 25)
+    tun = abi.default_tuning(substeps=4)
+    g = GpuWorld(tuning=tun)
+    g.load_scene(sc)
+    for _ in range(90):
+        g.tick()
+    sc2 = dict(sc)
+    sc2["bodies"] = g.get_bodies()
+    st = g.stats()
+    assert st["n_pairs"] > len(sc["bodies"])        # a real pile: more candidate pairs than bodies
+    g.close()
+    g, o = _replay(oracle, sc2)
+    # A resting pile of circles is the worst case for zero-depth ties (circle corrections are exact, so every second
+    # visit of a pair is decided by the last rounding bit) and Gauss-Seidel carries each tie through the pile within
+    # the substep; so besides the per-entry checks this scene is judged on aggregate statistics.
+    r = parity.compare_tick(g, o, sc2, hops=16)
+    print(r)
+    assert r["ties"] <= 0.02 * r["entries"]
+    assert r["non_tie_mismatches"] + r["mismatches_inside_influence"] <= r["ties"]
+    assert r["bad_outside_influence"] == 0
+    assert r["pos_err_median"] < 1e-6 and r["vel_err_median"] < 1e-3
+    assert r["momentum_rel_err"] < 2e-2 and r["kinetic_rel_err"] < 5e-2
+    g.close()
+
+
+def test_point_gravity_and_time_scale(oracle):
+    sc = scenes.parity_mix(150, 3, n_ropes=1)
+    ff = np.zeros(1, abi.forcefield_dtype)
+    ff["n_terms"] = 2
+    ff["terms"][0, 0] = (abi.FF_POINT_GRAVITY, 0.0, 3.0, 40.0, 0.5)
+    ff["terms"][0, 1] = (abi.FF_GRAVITY, 0.5, -1.0, 0.0, 0.0)
+    tun = abi.default_tuning(substeps=3)
+    g = GpuWorld(tuning=tun)
+    g.load_scene(sc)
+    g.tick(1.0 / 60.0, 0.5, ff)           # physics.rs:411-415: ceil(0.5 * 3) = 2 substeps of dt = 0.5 / 60 / 2
+    assert g.stats()["substeps"] == 2
+    o = oracle.OracleWorld(tuning=tun)
+    o.load_scene(sc)
+    o.set_external_pairs(g.debug_pairs())
+    o.tick(1.0 / 60.0, 0.5, ff, mode=oracle.MODE_COLOURED)
+    r = parity.compare_tick(g, o, sc, tol_state=5e-4, hops=6)
+    print(r)
+    assert r["non_tie_mismatches"] == 0 and r["bad_outside_influence"] == 0
+    g.close()
+
+
+def test_edge_cases():
+    g = GpuWorld()
+    # empty world ticks and answers queries
+    g.set_bodies(np.zeros(0, abi.body_dtype))
+    g.set_colliders(np.zeros(0, abi.collider_dtype))
+    g.tick()
+    rays = np.zeros(3, abi.ray_dtype)
+    rays["dx"], rays["max_distance"] = 1.0, 10.0
+    assert np.all(g.cast_batch(rays)["collider"] == -1)
+    # a single static collider, a dead slot and a NaN pose: no pairs, no crash
+    sc = scenes.parity_mix(20, 1, n_ropes=0, with_constraints=False)
+    sc["bodies"]["x"][3] = np.nan
+    sc["colliders"]["flags"][6] = 0
+    g.load_scene(sc)
+    g.tick()
+    b = g.get_bodies()
+    finite = np.isfinite(b["x"])
+    assert finite.sum() == len(b) - 1 and not finite[3]
+    # invalid input is rejected with an error code, never a crash
+    bad = sc["colliders"].copy()
+    bad["kind"][0] = 9
+    with pytest.raises(SfgError):
+        g.set_colliders(bad)
+    bad = sc["colliders"].copy()
+    bad["body"][5] = 10_000
+    with pytest.raises(SfgError):
+        g.set_colliders(bad)
+    one = np.zeros(1, abi.rope_dtype)
+    one["particle_count"] = 1
+    with pytest.raises(SfgError):       # reference: expect("Rope only had one particle") (solver.rs:120)
+        g.set_ropes(one, np.zeros(1, np.int32))
+    g.close()
+
+
+def test_contacts_published(oracle):
+    sc = scenes.parity_mix(200, 5)
+    g, o = _replay(oracle, sc, substeps=2)
+    gc = g.get_contacts()
+    oc, on = o.contacts()
+    gk = np.sort(gc["collider0"].astype(np.uint64) << np.uint64(32) | gc["collider1"].astype(np.uint64))
+    ok = np.sort(oc[:, 0].astype(np.uint64) << np.uint64(32) | oc[:, 1].astype(np.uint64))
+    # ContactInfo multiset (pairs appear once per entry, physics.rs:1097-1122); allow the zero-depth ties
+    common = len(np.intersect1d(gk, ok))
+    assert common >= 0.97 * max(len(np.unique(gk)), len(np.unique(ok)))
+    g.close()
