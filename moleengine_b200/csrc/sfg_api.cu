@@ -262,7 +262,7 @@ int ensure_device(int device) {
 
 // Colour a unit graph and return the sorted permutation + colour starts. Shared by pairs and constraints.
 int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub, const uint32_t* prio, DBuf<uint32_t>& colour,
-                 uint32_t** perm_out, std::vector<uint32_t>& colour_start, uint32_t* n_colours_out) {
+                 uint32_t** perm_out, std::vector<uint32_t>& colour_start, uint32_t* n_colours_out, bool pair_units) {
     cudaStream_t st = w->stream;
     colour_start.clear();
     *n_colours_out = 0;
@@ -307,10 +307,10 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     // stable sort by colour: perm = unit indices in colour-major order
     CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units)); CK(w->perm0.ensure(n_units)); CK(w->perm1.ensure(n_units));
     CK(w->sort_tmp.ensure(sort_tmp_words(n_units)));
-    CK(cudaMemcpyAsync(w->ckey0.p, colour.p, size_t(n_units) * 4, cudaMemcpyDeviceToDevice, st));
+    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CI.p, w->ckey0.p); CKL(w); w->launches++;
     k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
-    int bits = 1;
-    while ((1u << bits) < n_colours) ++bits;
+    int bits = 5;
+    while ((1u << bits) < n_colours * 16u) ++bits;
     int launches = 0;
     int where = radix_sort_pairs(w->ckey0.p, w->perm0.p, w->ckey1.p, w->perm1.p, n_units, bits, w->sort_tmp.p, st, &launches);
     w->launches += launches;
@@ -675,7 +675,7 @@ int build_graph(SfgWorld* w) {
         k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->U_ub.p, w->U_prio.p, w->deg.p);
         CKL(w); w->launches++;
         uint32_t* perm = nullptr;
-        int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours);
+        int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours, true);
         if (rc != SFG_OK) return rc;
         CK(w->H.ensure(n)); CK(w->S.ensure(n)); CK(w->G0.ensure(n)); CK(w->G1.ensure(n)); CK(w->L0.ensure(n)); CK(w->L1.ensure(n));
         CK(w->M0.ensure(size_t(n) * 2)); CK(w->M1.ensure(size_t(n) * 2)); CK(w->M2.ensure(size_t(n) * 2)); CK(w->LN.ensure(size_t(n) * 2));
@@ -695,7 +695,7 @@ int build_graph(SfgWorld* w) {
         k_constraint_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->KI.p, w->MI.p, w->KU_ids.p, w->KU_ub.p, w->KU_prio.p, w->deg.p);
         CKL(w); w->launches++;
         uint32_t* perm = nullptr;
-        int rc = colour_units(w, n, w->KU_ids.p, w->KU_ub.p, w->KU_prio.p, w->KU_colour, &perm, w->k_colour_start, &w->n_k_colours);
+        int rc = colour_units(w, n, w->KU_ids.p, w->KU_ub.p, w->KU_prio.p, w->KU_colour, &perm, w->k_colour_start, &w->n_k_colours, false);
         if (rc != SFG_OK) return rc;
         CK(w->K0.ensure(n)); CK(w->K1.ensure(n)); CK(w->K2.ensure(n));
         k_build_constraint_units<<<nblk(n), 256, 0, st>>>(n, perm, w->KI.p, w->KA.p, w->KB.p, w->K0.p, w->K1.p, w->K2.p);

@@ -282,6 +282,27 @@ __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* 
     if (b.y >= 0) adj[adj_start[b.y] + atomicAdd(cursor + b.y, 1u)] = u;
 }
 
+// Sort key of a coloured unit: colour-major, and inside a colour grouped by narrowphase path (circle-circle /
+// circle-polygon by polygon kind / polygon-polygon by edge count) and visit count, so the 32 lanes of a warp run the
+// same branches. The order inside a colour cannot change results (no shared dynamic body), only divergence.
+__global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const uint32_t* __restrict__ colour, const uint2* __restrict__ ids,
+                                                        const float4* __restrict__ CS, const int4* __restrict__ CI, uint32_t* __restrict__ keys) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    uint32_t cls = 0;
+    if (CS) {
+        const uint2 id = ids[u];
+        const uint32_t k0 = __float_as_uint(CS[id.x].w), k1 = __float_as_uint(CS[id.y].w);
+        uint32_t path;
+        if (k0 == K_POINT && k1 == K_POINT) path = 0;
+        else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
+        else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
+        const uint32_t mult2 = (CI[id.x].x >= 0 && CI[id.y].x >= 0) ? 1u : 0u;
+        cls = path * 2 + mult2;
+    }
+    keys[u] = colour[u] * 16u + cls;
+}
+
 constexpr uint32_t UNCOLOURED = 0xFFFFFFFFu;
 constexpr uint32_t JP_MAX_ROUNDS = 8192;
 
