@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,7 +39,8 @@ struct DBuf {
 struct TickHeader {            // small device block read back once per tick phase
     Bounds bounds;
     uint32_t n_pairs;
-    uint32_t pad[3];
+    uint32_t barrier;
+    uint32_t pad[2];
 };
 
 }  // namespace
@@ -83,7 +85,7 @@ struct SfgWorld {
     DBuf<float4> SA;
     DBuf<int4> SI;
     // pair units
-    uint32_t n_units = 0, n_unit_colours = 0, prev_pairs = 0;
+    uint32_t n_units = 0, n_unit_colours = 0, prev_pairs = 0, stats_jp_rounds = 0;
     std::vector<uint32_t> unit_colour_start;   // n_unit_colours + 1
     DBuf<uint2> U_ids;
     DBuf<int2> U_ub;
@@ -99,6 +101,7 @@ struct SfgWorld {
     DBuf<float4> K0, K1, K2;
     // persistent solver
     DBuf<Stage> d_stages;
+    DBuf<unsigned long long> trace;
     std::vector<Stage> h_stages;
     // casts
     DBuf<SfgRay> d_rays;
@@ -277,9 +280,10 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, w->adj_start.p, w->cursor.p, w->adj.p); CKL(w); w->launches++;
     // Jones-Plassmann in one cooperative launch
     constexpr uint32_t HIST_CAP = 65536;
-    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(JP_MAX_ROUNDS + 1)); CK(w->jp_hist.ensure(HIST_CAP));
+    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(16)); CK(w->jp_hist.ensure(HIST_CAP));
+    CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units));   // reused as the two worklists before they hold sort keys
     CK(cudaMemsetAsync(colour.p, 0xFF, size_t(n_units) * 4, st));
-    CK(cudaMemsetAsync(w->jp_counters.p, 0, (JP_MAX_ROUNDS + 1) * 4, st));
+    CK(cudaMemsetAsync(w->jp_counters.p, 0, 16 * 4, st));
     CK(cudaMemsetAsync(w->jp_hist.p, 0, HIST_CAP * 4, st));
     {
         int per_sm = 0;
@@ -287,14 +291,17 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         uint32_t grid = std::min<uint32_t>(uint32_t(per_sm * w->n_sms), std::max<uint32_t>(nblk(n_units), 1));
         uint32_t hist_cap = HIST_CAP;
         const uint32_t* adj_start = w->adj_start.p; const uint32_t* adj = w->adj.p;
-        uint32_t* col = colour.p; uint32_t* counters = w->jp_counters.p; uint32_t* hist = w->jp_hist.p;
-        void* args[] = {&n_units, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &counters, &hist, &hist_cap};
+        uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_hist.p;
+        uint32_t* l0 = w->ckey0.p; uint32_t* l1 = w->ckey1.p;
+        void* args[] = {&n_units, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &ctrl, &hist, &hist_cap, &l0, &l1};
         CK(cudaLaunchCooperativeKernel((void*)k_jp_colour, dim3(grid), dim3(256), args, 0, st));
         w->launches++;
     }
-    uint32_t n_colours = 0;
-    CK(cudaMemcpyAsync(&n_colours, w->jp_counters.p + JP_MAX_ROUNDS, 4, cudaMemcpyDeviceToHost, st));
+    uint32_t jp_ctrl[8] = {0};
+    CK(cudaMemcpyAsync(jp_ctrl, w->jp_counters.p, sizeof(jp_ctrl), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const uint32_t n_colours = jp_ctrl[1];
+    w->stats_jp_rounds = jp_ctrl[4];
     if (n_colours == 0 || n_colours > HIST_CAP) return fail(w, SFG_E_CAPACITY, "colouring did not converge or needs > 65536 colours");
     std::vector<uint32_t> hist(n_colours);
     CK(cudaMemcpyAsync(hist.data(), w->jp_hist.p, size_t(n_colours) * 4, cudaMemcpyDeviceToHost, st));
@@ -789,9 +796,28 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
             const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range)));
             const Stage* dst = w->d_stages.p;
             uint32_t n_stages = ns, n_sub = substeps;
-            void* args[] = {&ctx, (void*)&dst, &n_stages, &n_sub};
+            unsigned int* bar = &w->hdr.p->barrier;
+            CK(cudaMemsetAsync(bar, 0, 4, st));
+            // debug: SFG_TRACE=<file> dumps per-stage, per-CTA (arrival, release) %globaltimer stamps of the barrier
+            const char* trace_path = getenv("SFG_TRACE");
+            unsigned long long* trace = nullptr;
+            const size_t trace_n = size_t(2) * n_sub * ns * grid;
+            if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; }
+            void* args[] = {&ctx, (void*)&dst, &n_stages, &n_sub, (void*)&bar, (void*)&trace};
             CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(256), args, 0, st));
             w->launches++;
+            if (trace_path) {
+                std::vector<unsigned long long> h(trace_n);
+                CK(cudaMemcpyAsync(h.data(), trace, trace_n * 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (FILE* f = fopen(trace_path, "wb")) {
+                    uint32_t hdr4[4] = {n_sub, ns, grid, 0};
+                    fwrite(hdr4, 4, 4, f);
+                    for (const Stage& sg : w->h_stages) { uint32_t r[4] = {sg.kind, sg.begin, sg.end, 0}; fwrite(r, 4, 4, f); }
+                    fwrite(h.data(), 8, trace_n, f);
+                    fclose(f);
+                }
+            }
         }
     }
     CK(cudaEventRecord(w->ev[3], st));
@@ -811,6 +837,7 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
     cudaEventElapsedTime(&s.ms_solver, w->ev[2], w->ev[3]);
     cudaEventElapsedTime(&s.ms_total, w->ev[0], w->ev[3]);
     s.reserved[0] = uint32_t(w->h_stages.size());
+    s.reserved[1] = w->stats_jp_rounds;
     return SFG_OK;
 }
 

@@ -224,14 +224,16 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
         uint32_t hi = 0, lo = 0;
         if (more) {
             const uint32_t cj = cur++;
-            const int4 J = SI[cj];
-            if (J.w == I.w && aabb_overlap(A, SA[cj])) {
-                const bool i_later = uint32_t(I.x) > uint32_t(J.x);
-                hi = i_later ? uint32_t(I.x) : uint32_t(J.x); lo = i_later ? uint32_t(J.x) : uint32_t(I.x);
-                const int l_lo = i_later ? (J.z & 0xFF) : my_layer;
-                const unsigned long long mrow = i_later ? my_mask : mask[J.z & 0xFF];   // mask_matrix.get(later.layer, earlier.layer)
-                const bool bodies_ok = (I.y >= 0 || J.y >= 0) && !(I.y >= 0 && I.y == J.y);
-                hit = ((mrow >> l_lo) & 1ull) && bodies_ok;
+            if (aabb_overlap(A, __ldg(SA + cj))) {       // cells of one key share the domain; only the huge list mixes them
+                const int4 J = __ldg(SI + cj);
+                if (J.w == I.w) {
+                    const bool i_later = uint32_t(I.x) > uint32_t(J.x);
+                    hi = i_later ? uint32_t(I.x) : uint32_t(J.x); lo = i_later ? uint32_t(J.x) : uint32_t(I.x);
+                    const int l_lo = i_later ? (J.z & 0xFF) : my_layer;
+                    const unsigned long long mrow = i_later ? my_mask : mask[J.z & 0xFF];   // mask_matrix.get(later.layer, earlier.layer)
+                    const bool bodies_ok = (I.y >= 0 || J.y >= 0) && !(I.y >= 0 && I.y == J.y);
+                    hit = ((mrow >> l_lo) & 1ull) && bodies_ok;
+                }
             }
         }
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, hit);
@@ -308,70 +310,97 @@ constexpr uint32_t JP_MAX_ROUNDS = 8192;
 
 // Jones-Plassmann: a unit takes the smallest colour unused by its higher-priority neighbours once all of
 // them are coloured; the fixed point equals greedy colouring in descending priority (what the oracle runs).
-// counters[0 .. JP_MAX_ROUNDS) = units left per round, counters[JP_MAX_ROUNDS] = max colour + 1,
-// hist = units per colour.
+// One cooperative launch; units that are not ready go to the next round's worklist (warp-aggregated append), so
+// later rounds only touch what is left. ctrl: [0] barrier, [1] max colour + 1, [2], [3] worklist sizes (ping-pong),
+// [4] rounds used. hist = units per colour.
+SFG_DI void jp_barrier(unsigned int* counter, unsigned int& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
 __global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
                                                    const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
-                                                   const uint32_t* __restrict__ adj, uint32_t* colour, uint32_t* counters,
-                                                   uint32_t* hist, uint32_t hist_cap) {
-    cg::grid_group grid = cg::this_grid();
+                                                   const uint32_t* __restrict__ adj, uint32_t* colour, uint32_t* ctrl,
+                                                   uint32_t* hist, uint32_t hist_cap, uint32_t* list0, uint32_t* list1) {
     __shared__ uint32_t s_hist[64];
-    __shared__ uint32_t s_pending, s_max;
+    __shared__ uint32_t s_max;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31;
     if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { s_pending = 0; s_max = 0; }
+    if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
-    for (uint32_t round = 0; round < JP_MAX_ROUNDS; ++round) {
-        uint32_t pending = 0;
-        for (uint32_t u = tid; u < n_units; u += nth) {
-            if (__ldcg(colour + u) != UNCOLOURED) continue;
-            const int2 b = ub[u];
-            const uint32_t pu = prio[u];
-            const uint2 iu = ids[u];
-            bool ready = true;
-            uint32_t result = 0;
-            for (uint32_t win = 0; ready; win += 64) {   // window of 64 colours at a time
-                unsigned long long used = 0ull;
-                bool beyond = false;
-                for (int side = 0; side < 2 && ready; ++side) {
-                    const int body = side ? b.y : b.x;
-                    if (body < 0) continue;
-                    const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
-                    for (uint32_t a = a0; a < a1; ++a) {
-                        const uint32_t v = adj[a];
-                        if (v == u) continue;
-                        const uint32_t pv = prio[v];
-                        bool higher = pv > pu;
-                        if (pv == pu) { const uint2 iv = ids[v]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
-                        if (!higher) continue;
-                        const uint32_t cv = __ldcg(colour + v);
-                        if (cv == UNCOLOURED) { ready = false; break; }
-                        if (cv >= win && cv < win + 64) used |= 1ull << (cv - win);
-                        else if (cv >= win + 64) beyond = true;
+    unsigned int target = 0;
+    uint32_t n_cur = n_units;
+    for (uint32_t round = 0; round < JP_MAX_ROUNDS && n_cur; ++round) {
+        const uint32_t* cur = (round & 1) ? list1 : list0;
+        uint32_t* nxt = (round & 1) ? list0 : list1;
+        uint32_t* nxt_count = ctrl + 2 + ((round + 1) & 1);
+        const uint32_t n_iter = (n_cur + nth - 1) / nth;
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const uint32_t idx = it * nth + tid;
+            bool pending = false;
+            uint32_t u = 0;
+            if (idx < n_cur) {
+                u = round == 0 ? idx : cur[idx];
+                const int2 b = ub[u];
+                const uint32_t pu = prio[u];
+                const uint2 iu = ids[u];
+                bool ready = true;
+                uint32_t result = 0;
+                for (uint32_t win = 0; ready; win += 64) {   // window of 64 colours at a time
+                    unsigned long long used = 0ull;
+                    bool beyond = false;
+                    for (int side = 0; side < 2 && ready; ++side) {
+                        const int body = side ? b.y : b.x;
+                        if (body < 0) continue;
+                        const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
+                        for (uint32_t a = a0; a < a1; ++a) {
+                            const uint32_t v = adj[a];
+                            if (v == u) continue;
+                            const uint32_t pv = prio[v];
+                            bool higher = pv > pu;
+                            if (pv == pu) { const uint2 iv = ids[v]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
+                            if (!higher) continue;
+                            const uint32_t cv = __ldcg(colour + v);
+                            if (cv == UNCOLOURED) { ready = false; break; }
+                            if (cv >= win && cv < win + 64) used |= 1ull << (cv - win);
+                            else if (cv >= win + 64) beyond = true;
+                        }
                     }
+                    if (!ready) break;
+                    if (used != ~0ull) { result = win + uint32_t(__ffsll((long long)~used) - 1); break; }
+                    if (!beyond) { result = win + 64; break; }
                 }
-                if (!ready) break;
-                if (used != ~0ull) { result = win + uint32_t(__ffsll((long long)~used) - 1); break; }
-                if (!beyond) { result = win + 64; break; }
+                if (ready) {
+                    __stcg(colour + u, result);
+                    if (result < 64) atomicAdd(&s_hist[result], 1u);
+                    else if (result < hist_cap) atomicAdd(hist + result, 1u);
+                    atomicMax(&s_max, result + 1u);
+                } else pending = true;
             }
-            if (ready) {
-                __stcg(colour + u, result);
-                if (result < 64) atomicAdd(&s_hist[result], 1u);
-                else if (result < hist_cap) atomicAdd(hist + result, 1u);
-                atomicMax(&s_max, result + 1u);
-            } else ++pending;
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pending);
+            if (ballot) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(nxt_count, __popc(ballot));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (pending) nxt[base + __popc(ballot & ((1u << lane) - 1u))] = u;
+            }
         }
-        // one global atomic per CTA per round
-        pending = __reduce_add_sync(0xFFFFFFFFu, pending);
-        if ((threadIdx.x & 31) == 0 && pending) atomicAdd(&s_pending, pending);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_pending) { atomicAdd(counters + round, s_pending); s_pending = 0; }
-        grid.sync();
-        if (__ldcg(counters + round) == 0u) break;
+        jp_barrier(ctrl, target);
+        n_cur = __ldcg(nxt_count);
+        jp_barrier(ctrl, target);                      // everyone has read the size before it is reset for reuse
+        if (tid == 0) { ctrl[2 + (round & 1)] = 0; ctrl[4] = round + 1; }
     }
     __syncthreads();
     if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(hist + threadIdx.x, s_hist[threadIdx.x]);
-    if (threadIdx.x == 0 && s_max) atomicMax(counters + JP_MAX_ROUNDS, s_max);
+    if (threadIdx.x == 0 && s_max) atomicMax(ctrl + 1, s_max);
 }
 
 // after the stable sort by colour: write the streaming columns of each pair unit

@@ -258,18 +258,21 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
     const int mult = (fl & UF_MULT2) ? 2 : 1;
     const bool sees = (fl & (UF_SEES0 | UF_SEES1)) != 0;
 
+    bool prev_zero = false;
     for (int m = 0; m < mult; ++m) {
         const uint32_t e = u + uint32_t(m) * c.n_units;
+        // second visit of a pair whose first visit found nothing: no pose changed, so the same test gives the same nothing
+        if (prev_zero) { stb(c.M0 + e, make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
         const Iso pw0 = b0 >= 0 ? mkiso(mk(P0.z, P0.w), r0) * loc0 : st0;
         const Iso pw1 = b1 >= 0 ? mkiso(mk(told1.x + P1.z, told1.y + P1.w), r1) * loc1 : st1;
         Manifold mf;
         intersection_check(pw0, pw1, sh0, sh1, mf);
-        if (mf.count == 0) { c.M0[e] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+        if (mf.count == 0) { stb(c.M0 + e, make_float4(0.f, 0.f, 0.f, 0.f)); prev_zero = true; continue; }
         for (int k = 0; k < mf.count; ++k) {                            // solver.rs:308-315
             if (b0 >= 0) mf.off[k][0] = loc0 * mf.off[k][0];
             if (b1 >= 0) mf.off[k][1] = loc1 * mf.off[k][1];
         }
-        c.LN[e] = make_float2(mf.n.x, mf.n.y);                          // solver.rs:318-320 (latch)
+        stb(c.LN + e, make_float2(mf.n.x, mf.n.y));                          // solver.rs:318-320 (latch)
         float lambda_n = 0.f;
         if (sees) {
             if (mf.count == 1 && (fl & (UF_ROPE0 | UF_ROPE1))) {        // solver.rs:337-362
@@ -325,9 +328,9 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
                 }
             }
         }
-        c.M0[e] = make_float4(__int_as_float(mf.count), lambda_n, mf.n.x, mf.n.y);
-        c.M1[e] = make_float4(mf.off[0][0].x, mf.off[0][0].y, mf.off[0][1].x, mf.off[0][1].y);
-        if (mf.count == 2) c.M2[e] = make_float4(mf.off[1][0].x, mf.off[1][0].y, mf.off[1][1].x, mf.off[1][1].y);
+        stb(c.M0 + e, make_float4(__int_as_float(mf.count), lambda_n, mf.n.x, mf.n.y));
+        stb(c.M1 + e, make_float4(mf.off[0][0].x, mf.off[0][0].y, mf.off[0][1].x, mf.off[0][1].y));
+        if (mf.count == 2) stb(c.M2 + e, make_float4(mf.off[1][0].x, mf.off[1][0].y, mf.off[1][1].x, mf.off[1][1].y));
     }
     if (fl & UF_SEES0) { stb(c.P + b0, P0); Q0.x = r0.s; Q0.y = r0.b; stb(c.Q + b0, Q0); }
     if (fl & UF_SEES1) { stb(c.P + b1, P1); Q1.x = r1.s; Q1.y = r1.b; stb(c.Q + b1, Q1); }
@@ -340,8 +343,8 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u) {
     if ((fl & UF_SENSOR) || !(fl & (UF_SEES0 | UF_SEES1))) return;
     const int mult = (fl & UF_MULT2) ? 2 : 1;
     float4 m0[2];
-    m0[0] = c.M0[u];
-    m0[1] = mult == 2 ? c.M0[u + c.n_units] : make_float4(0.f, 0.f, 0.f, 0.f);
+    m0[0] = ldb(c.M0 + u);
+    m0[1] = mult == 2 ? ldb(c.M0 + u + c.n_units) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (__float_as_int(m0[0].x) == 0 && __float_as_int(m0[1].x) == 0) return;
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     const float4 s = ldc(c.S + u);
@@ -360,7 +363,7 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u) {
         const float lambda_n = m0[m].y;
         const V2 n = mk(m0[m].z, m0[m].w), tan = left_normal(n);
         for (int k = 0; k < count; ++k) {
-            const float4 pt = k == 0 ? c.M1[e] : c.M2[e];
+            const float4 pt = k == 0 ? ldb(c.M1 + e) : ldb(c.M2 + e);
             const V2 or0 = b0 >= 0 ? r0 * mk(pt.x, pt.y) : mk(0.f, 0.f);
             const V2 or1 = b1 >= 0 ? r1 * mk(pt.z, pt.w) : mk(0.f, 0.f);
             V2 pv0 = mk(V0.x - or0.y * V0.z, V0.y + or0.x * V0.z), pv1 = mk(V1.x - or1.y * V1.z, V1.y + or1.x * V1.z);
@@ -415,18 +418,43 @@ __global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx
     if (i < end) run_stage(c, KIND, i, last_substep != 0);
 }
 
-// The whole substep loop of one tick in ONE launch: every CTA walks the stage table, grid-strides over
-// the stage's range, and meets the others at a grid-wide barrier before the next stage (colour).
+// Grid-wide barrier of the persistent kernel: one release-atomic per CTA on a monotonically increasing counter, a
+// relaxed polling load (no L1 invalidation per poll, unlike cooperative_groups' grid.sync) and one acquire fence at
+// the end. All data that crosses SMs between stages is accessed with ld.cg / st.cg, so L1 never holds it.
+SFG_DI unsigned long long global_timer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, unsigned long long* trace = nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        if (trace) trace[0] = global_timer();
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int seen;
+        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
+        __threadfence();
+        if (trace) trace[1] = global_timer();
+    }
+    __syncthreads();
+}
+
+// The whole substep loop of one tick in ONE launch: every CTA walks the stage table, and the units of a stage are dealt
+// to warps round-robin ACROSS CTAs (chunk c of 32 units -> CTA c mod gridDim, warp slot c / gridDim), so a run of
+// expensive units (they are grouped by narrowphase path) is spread over all SMs; then all CTAs meet at a barrier.
 __global__ void __launch_bounds__(256, 3) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
-                                                          uint32_t n_stages, uint32_t substeps) {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+                                                             uint32_t n_stages, uint32_t substeps, unsigned int* barrier_counter, unsigned long long* trace) {
+    const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+    const uint32_t first_chunk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, chunk_stride = gridDim.x * warps_per_cta;
+    unsigned int target = 0;
     for (uint32_t s = 0; s < substeps; ++s) {
         const bool last = s + 1 == substeps;
         for (uint32_t k = 0; k < n_stages; ++k) {
             const Stage st = stages[k];
-            for (uint32_t i = st.begin + tid; i < st.end; i += nth) run_stage(c, st.kind, i, last);
-            grid.sync();
+            const uint32_t n = st.end - st.begin;
+            for (uint32_t chunk = first_chunk; chunk * 32u < n; chunk += chunk_stride) {
+                const uint32_t i = chunk * 32u + lane;
+                if (i < n) run_stage(c, st.kind, st.begin + i, last);
+            }
+            grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t(s * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
         }
     }
 }
