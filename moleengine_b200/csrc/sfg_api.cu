@@ -280,21 +280,21 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, w->adj_start.p, w->cursor.p, w->adj.p); CKL(w); w->launches++;
     // Jones-Plassmann in one cooperative launch
     constexpr uint32_t HIST_CAP = 65536;
-    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(16)); CK(w->jp_hist.ensure(HIST_CAP));
+    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(JP_MAX_ROUNDS + 16)); CK(w->jp_hist.ensure(HIST_CAP));
     CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units));   // reused as the two worklists before they hold sort keys
     CK(cudaMemsetAsync(colour.p, 0xFF, size_t(n_units) * 4, st));
-    CK(cudaMemsetAsync(w->jp_counters.p, 0, 16 * 4, st));
+    CK(cudaMemsetAsync(w->jp_counters.p, 0, (JP_MAX_ROUNDS + 16) * 4, st));
     CK(cudaMemsetAsync(w->jp_hist.p, 0, HIST_CAP * 4, st));
     {
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jp_colour, 256, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jp_colour, 1024, 0));
         uint32_t grid = std::min<uint32_t>(uint32_t(per_sm * w->n_sms), std::max<uint32_t>(nblk(n_units), 1));
         uint32_t hist_cap = HIST_CAP;
         const uint32_t* adj_start = w->adj_start.p; const uint32_t* adj = w->adj.p;
         uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_hist.p;
         uint32_t* l0 = w->ckey0.p; uint32_t* l1 = w->ckey1.p;
         void* args[] = {&n_units, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &ctrl, &hist, &hist_cap, &l0, &l1};
-        CK(cudaLaunchCooperativeKernel((void*)k_jp_colour, dim3(grid), dim3(256), args, 0, st));
+        CK(cudaLaunchCooperativeKernel((void*)k_jp_colour, dim3(grid), dim3(1024), args, 0, st));
         w->launches++;
     }
     uint32_t jp_ctrl[8] = {0};
@@ -789,11 +789,11 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
             CK(w->d_stages.ensure(ns));
             CK(cudaMemcpyAsync(w->d_stages.p, w->h_stages.data(), ns * sizeof(Stage), cudaMemcpyHostToDevice, st));
             int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, 256, 0));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, 768, 0));
             if (per_sm < 1) return fail(w, SFG_E_CUDA, "persistent solver kernel does not fit on an SM");
             uint32_t max_range = 0;
             for (const Stage& sg : w->h_stages) max_range = std::max(max_range, sg.end - sg.begin);
-            const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range)));
+            const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range, 768)));
             const Stage* dst = w->d_stages.p;
             uint32_t n_stages = ns, n_sub = substeps;
             unsigned int* bar = &w->hdr.p->barrier;
@@ -804,7 +804,7 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
             const size_t trace_n = size_t(2) * n_sub * ns * grid;
             if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; }
             void* args[] = {&ctx, (void*)&dst, &n_stages, &n_sub, (void*)&bar, (void*)&trace};
-            CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(256), args, 0, st));
+            CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(768), args, 0, st));
             w->launches++;
             if (trace_path) {
                 std::vector<unsigned long long> h(trace_n);

@@ -311,7 +311,7 @@ constexpr uint32_t JP_MAX_ROUNDS = 8192;
 // Jones-Plassmann: a unit takes the smallest colour unused by its higher-priority neighbours once all of
 // them are coloured; the fixed point equals greedy colouring in descending priority (what the oracle runs).
 // One cooperative launch; units that are not ready go to the next round's worklist (warp-aggregated append), so
-// later rounds only touch what is left. ctrl: [0] barrier, [1] max colour + 1, [2], [3] worklist sizes (ping-pong),
+// later rounds only touch what is left. ctrl: [0] barrier, [1] max colour + 1, [4] rounds used, [8 + r] worklist size after round r.
 // [4] rounds used. hist = units per colour.
 SFG_DI void jp_barrier(unsigned int* counter, unsigned int& target) {
     __syncthreads();
@@ -325,7 +325,7 @@ SFG_DI void jp_barrier(unsigned int* counter, unsigned int& target) {
     }
     __syncthreads();
 }
-__global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
+__global__ void __launch_bounds__(1024) k_jp_colour(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
                                                    const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
                                                    const uint32_t* __restrict__ adj, uint32_t* colour, uint32_t* ctrl,
                                                    uint32_t* hist, uint32_t hist_cap, uint32_t* list0, uint32_t* list1) {
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2*
     for (uint32_t round = 0; round < JP_MAX_ROUNDS && n_cur; ++round) {
         const uint32_t* cur = (round & 1) ? list1 : list0;
         uint32_t* nxt = (round & 1) ? list0 : list1;
-        uint32_t* nxt_count = ctrl + 2 + ((round + 1) & 1);
+        uint32_t* nxt_count = ctrl + 8 + round;                 // one size slot per round: never reset, one barrier per round
         const uint32_t n_iter = (n_cur + nth - 1) / nth;
         for (uint32_t it = 0; it < n_iter; ++it) {
             const uint32_t idx = it * nth + tid;
@@ -395,8 +395,7 @@ __global__ void __launch_bounds__(256) k_jp_colour(uint32_t n_units, const int2*
         }
         jp_barrier(ctrl, target);
         n_cur = __ldcg(nxt_count);
-        jp_barrier(ctrl, target);                      // everyone has read the size before it is reset for reuse
-        if (tid == 0) { ctrl[2 + (round & 1)] = 0; ctrl[4] = round + 1; }
+        if (tid == 0) ctrl[4] = round + 1;
     }
     __syncthreads();
     if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(hist + threadIdx.x, s_hist[threadIdx.x]);
