@@ -187,6 +187,12 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
 /* ---- results: bodies written back (physics.rs:1150-1157), contacts (:1097-1122, :1165) ---- */
 int sfg_get_bodies(SfgWorld* w, uint32_t first_slot, uint32_t count, SfgBody* out);
 int sfg_get_contacts(SfgWorld* w, SfgContactInfo* out, size_t capacity, size_t* n_out);
+
+/* ---- pose-only sync, the GPU side of HecsSyncManager (physics/hecs_sync.rs:121-227): the game loop pushes f32
+ *      `Pose`s of both-ways entities in before the tick (Game::physics_tick, game.rs:297-303) and pulls poses out after.
+ *      poses: `count` rows of (x, y, rot_s, rot_b); velocities and masses are untouched. ---- */
+int sfg_set_poses(SfgWorld* w, uint32_t first_slot, uint32_t count, const float* poses_xysb);
+int sfg_get_poses(SfgWorld* w, uint32_t first_slot, uint32_t count, float* poses_xysb);
 int sfg_get_stats(SfgWorld* w, SfgStats* out);
 
 /* ---- PhysicsWorld::raycast / spherecast (physics.rs:1255-1311), batched ---- */

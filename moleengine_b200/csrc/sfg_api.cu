@@ -158,6 +158,19 @@ __global__ void k_pack_bodies(SfgBody* out, uint32_t n, uint32_t first, const fl
     b.reserved[0] = b.reserved[1] = 0;
     out[i] = b;
 }
+__global__ void k_set_poses(const float4* in, uint32_t n, uint32_t first, float4* P, float4* Q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = in[i];
+    P[first + i] = make_float4(v.x, v.y, 0.f, 0.f);
+    Q[first + i] = make_float4(v.z, v.w, v.z, v.w);
+}
+__global__ void k_get_poses(float4* out, uint32_t n, uint32_t first, const float4* P, const float4* Q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = P[first + i], q = Q[first + i];
+    out[i] = make_float4(p.x + p.z, p.y + p.w, q.x, q.y);
+}
 __global__ void k_unpack_colliders(const SfgCollider* in, uint32_t n, uint32_t first, float4* CS, float4* CL, float4* CM, int4* CI) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -857,6 +870,33 @@ int sfg_get_bodies(SfgWorld* w, uint32_t first, uint32_t count, SfgBody* out) {
     k_pack_bodies<<<nblk(count), 256, 0, st>>>((SfgBody*)w->stage.p, count, first, w->P.p, w->Q.p, w->V.p, w->MI.p);
     CKL(w);
     CK(cudaMemcpyAsync(out, w->stage.p, size_t(count) * sizeof(SfgBody), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+int sfg_set_poses(SfgWorld* w, uint32_t first, uint32_t count, const float* poses) {
+    if (!w || (count && !poses)) return SFG_E_INVALID;
+    if (uint64_t(first) + count > w->n_bodies) return fail(w, SFG_E_INVALID, "body slot range out of bounds");
+    if (count == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(count) * 16));
+    CK(cudaMemcpyAsync(w->stage.p, poses, size_t(count) * 16, cudaMemcpyHostToDevice, st));
+    k_set_poses<<<nblk(count), 256, 0, st>>>((const float4*)w->stage.p, count, first, w->P.p, w->Q.p);
+    CKL(w);
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+int sfg_get_poses(SfgWorld* w, uint32_t first, uint32_t count, float* poses) {
+    if (!w || (count && !poses)) return SFG_E_INVALID;
+    if (uint64_t(first) + count > w->n_bodies) return fail(w, SFG_E_INVALID, "body slot range out of bounds");
+    if (count == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(count) * 16));
+    k_get_poses<<<nblk(count), 256, 0, st>>>((float4*)w->stage.p, count, first, w->P.p, w->Q.p);
+    CKL(w);
+    CK(cudaMemcpyAsync(poses, w->stage.p, size_t(count) * 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return SFG_OK;
 }

@@ -93,6 +93,17 @@ class GpuWorld:
         self._ck(self.lib.sfg_get_bodies(self.h, first, count, abi.ptr(out)))
         return out
 
+    def set_poses(self, poses, first=0):
+        """poses: (n, 4) float32 rows of x, y, rot_s, rot_b (hecs_sync.rs sync_hecs_to_physics)."""
+        p = np.ascontiguousarray(poses, np.float32).reshape(-1, 4)
+        self._ck(self.lib.sfg_set_poses(self.h, first, len(p), abi.ptr(p)))
+
+    def get_poses(self, first=0, count=None, out=None):
+        count = self.n_bodies - first if count is None else count
+        out = np.zeros((count, 4), np.float32) if out is None else out
+        self._ck(self.lib.sfg_get_poses(self.h, first, count, abi.ptr(out)))
+        return out
+
     def get_contacts(self, capacity=1 << 20):
         out = np.zeros(capacity, abi.contact_dtype)
         n = C.c_size_t()

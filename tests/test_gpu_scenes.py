@@ -194,3 +194,21 @@ def test_contacts_published(oracle):
     common = len(np.intersect1d(gk, ok))
     assert common >= 0.97 * max(len(np.unique(gk)), len(np.unique(ok)))
     g.close()
+
+
+def test_pose_sync_roundtrip():
+    """sfg_set_poses / sfg_get_poses (the HecsSyncManager path) leave velocities alone and round-trip exactly."""
+    sc = scenes.parity_mix(80, 2, n_ropes=0, with_constraints=False)
+    g = GpuWorld(tuning=abi.default_tuning(substeps=2))
+    g.load_scene(sc)
+    g.tick()
+    b0 = g.get_bodies()
+    p = g.get_poses()
+    assert np.array_equal(p[:, 0], b0["x"]) and np.array_equal(p[:, 3], b0["rot_b"])
+    p2 = p.copy()
+    p2[:10, 0] += 0.25
+    g.set_poses(p2)
+    b1 = g.get_bodies()
+    assert np.array_equal(b1["x"], p2[:, 0]) and np.array_equal(b1["vx"], b0["vx"]) and np.array_equal(b1["w"], b0["w"])
+    g.tick()
+    g.close()
