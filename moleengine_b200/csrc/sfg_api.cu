@@ -54,6 +54,7 @@ struct SfgWorld {
     uint64_t mask[64];
     int n_sms = 148;
     bool ticked = false;
+    float frame_dt = 1.0f / 60.0f;   // of the tick in flight
 
     // bodies
     uint32_t n_bodies = 0;
@@ -92,6 +93,9 @@ struct SfgWorld {
     DBuf<uint32_t> U_prio, U_colour, deg, adj_start, adj, cursor, jp_counters, jp_hist, perm0, perm1, ckey0, ckey1;
     DBuf<float4> H, S, G0, G1, L0, L1, M0, M1, M2;
     DBuf<float2> LN;
+    DBuf<float> RC;
+    DBuf<uint32_t> WL, wl_count;
+    uint32_t last_substeps = 0;   // substeps of the last tick = tag of a manifold entry written in its last substep
     // constraint units
     uint32_t n_kunits = 0, n_k_colours = 0;
     std::vector<uint32_t> k_colour_start;
@@ -202,12 +206,13 @@ __global__ void k_collect_contacts(uint32_t n_entries, uint32_t n_units, const f
     ci.collider0 = __float_as_uint(s.x); ci.collider1 = __float_as_uint(s.y); ci.nx = n.x; ci.ny = n.y;
     out[pos] = ci;
 }
-__global__ void k_export_manifolds(uint32_t n_entries, uint32_t n_units, const float4* S, const float4* M0, const float4* M1, const float4* M2,
-                                   float* out) {
+__global__ void k_export_manifolds(uint32_t n_entries, uint32_t n_units, uint32_t tag, const float4* S, const float4* M0, const float4* M1,
+                                   const float4* M2, float* out) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_entries) return;
     const float4 s = S[e % n_units], m0 = M0[e];
-    const int count = __float_as_int(m0.x);
+    const uint32_t bits = __float_as_uint(m0.x);
+    const int count = (bits >> 8) == tag ? int(bits & M0_COUNT_MASK) : 0;   // entries not written in the last substep hold no contact
     float* o = out + 14 * size_t(e);
     o[0] = float(__float_as_uint(s.x)); o[1] = float(__float_as_uint(s.y));
     o[2] = float(count); o[3] = count ? m0.y : 0.f; o[4] = count ? m0.z : 0.f; o[5] = count ? m0.w : 0.f;
@@ -327,10 +332,11 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     // stable sort by colour: perm = unit indices in colour-major order
     CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units)); CK(w->perm0.ensure(n_units)); CK(w->perm1.ensure(n_units));
     CK(w->sort_tmp.ensure(sort_tmp_words(n_units)));
-    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CI.p, w->ckey0.p); CKL(w); w->launches++;
+    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p,
+                                                    w->frame_dt, w->ckey0.p); CKL(w); w->launches++;
     k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
     int bits = 5;
-    while ((1u << bits) < n_colours * 16u) ++bits;
+    while ((1u << bits) < n_colours * 32u) ++bits;
     int launches = 0;
     int where = radix_sort_pairs(w->ckey0.p, w->perm0.p, w->ckey1.p, w->perm1.p, n_units, bits, w->sort_tmp.p, st, &launches);
     w->launches += launches;
@@ -392,7 +398,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->KU_ids.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -596,27 +602,28 @@ void choose_grid(SfgWorld* w, const Bounds& b) {
 }
 
 template <uint32_t KIND>
-int launch_stage(SfgWorld* w, const SolverCtx& ctx, uint32_t begin, uint32_t end, bool last) {
+int launch_stage(SfgWorld* w, const SolverCtx& ctx, const Stage& s, bool last, uint32_t sub) {
+    const uint32_t begin = s.begin, end = s.end;
     if (end <= begin) return SFG_OK;
-    k_stage<KIND><<<nblk(end - begin), 256, 0, w->stream>>>(ctx, begin, end, last ? 1 : 0);
+    k_stage<KIND><<<nblk(end - begin), 256, 0, w->stream>>>(ctx, begin, end, last ? 1 : 0, sub, s.colour);
     CKL(w);
     w->launches++;
     return SFG_OK;
 }
 
-int launch_stage_dyn(SfgWorld* w, const SolverCtx& ctx, const Stage& s, bool last) {
+int launch_stage_dyn(SfgWorld* w, const SolverCtx& ctx, const Stage& s, bool last, uint32_t sub) {
     switch (s.kind) {
-    case ST_INTEGRATE: return launch_stage<ST_INTEGRATE>(w, ctx, s.begin, s.end, last);
-    case ST_ROPE_STEP: return launch_stage<ST_ROPE_STEP>(w, ctx, s.begin, s.end, last);
-    case ST_CONSTRAINTS: return launch_stage<ST_CONSTRAINTS>(w, ctx, s.begin, s.end, last);
-    case ST_PRECONTACT: return launch_stage<ST_PRECONTACT>(w, ctx, s.begin, s.end, last);
-    case ST_CONTACTS: return launch_stage<ST_CONTACTS>(w, ctx, s.begin, s.end, last);
-    case ST_DERIVE: return launch_stage<ST_DERIVE>(w, ctx, s.begin, s.end, last);
-    case ST_CONTACT_VEL: return launch_stage<ST_CONTACT_VEL>(w, ctx, s.begin, s.end, last);
-    case ST_CONSTRAINT_DAMP: return launch_stage<ST_CONSTRAINT_DAMP>(w, ctx, s.begin, s.end, last);
-    case ST_ROPE_DAMP: return launch_stage<ST_ROPE_DAMP>(w, ctx, s.begin, s.end, last);
-    case ST_ROPE_LATERAL: return launch_stage<ST_ROPE_LATERAL>(w, ctx, s.begin, s.end, last);
-    default: return launch_stage<ST_FOLD>(w, ctx, s.begin, s.end, last);
+    case ST_INTEGRATE: return launch_stage<ST_INTEGRATE>(w, ctx, s, last, sub);
+    case ST_ROPE_STEP: return launch_stage<ST_ROPE_STEP>(w, ctx, s, last, sub);
+    case ST_CONSTRAINTS: return launch_stage<ST_CONSTRAINTS>(w, ctx, s, last, sub);
+    case ST_PRECONTACT: return launch_stage<ST_PRECONTACT>(w, ctx, s, last, sub);
+    case ST_CONTACTS: return launch_stage<ST_CONTACTS>(w, ctx, s, last, sub);
+    case ST_DERIVE: return launch_stage<ST_DERIVE>(w, ctx, s, last, sub);
+    case ST_CONTACT_VEL: return launch_stage<ST_CONTACT_VEL>(w, ctx, s, last, sub);
+    case ST_CONSTRAINT_DAMP: return launch_stage<ST_CONSTRAINT_DAMP>(w, ctx, s, last, sub);
+    case ST_ROPE_DAMP: return launch_stage<ST_ROPE_DAMP>(w, ctx, s, last, sub);
+    case ST_ROPE_LATERAL: return launch_stage<ST_ROPE_LATERAL>(w, ctx, s, last, sub);
+    default: return launch_stage<ST_FOLD>(w, ctx, s, last, sub);
     }
 }
 
@@ -697,11 +704,12 @@ int build_graph(SfgWorld* w) {
         uint32_t* perm = nullptr;
         int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours, true);
         if (rc != SFG_OK) return rc;
+        CK(w->RC.ensure(n)); CK(w->WL.ensure(n));
         CK(w->H.ensure(n)); CK(w->S.ensure(n)); CK(w->G0.ensure(n)); CK(w->G1.ensure(n)); CK(w->L0.ensure(n)); CK(w->L1.ensure(n));
         CK(w->M0.ensure(size_t(n) * 2)); CK(w->M1.ensure(size_t(n) * 2)); CK(w->M2.ensure(size_t(n) * 2)); CK(w->LN.ensure(size_t(n) * 2));
         k_build_pair_units<<<nblk(n), 256, 0, st>>>(n, perm, w->U_ids.p, w->CS.p, w->CL.p, w->CM.p, w->CI.p, w->MI.p,
                                                     w->n_ropes ? w->rope_next.p : nullptr, w->n_ropes ? w->rope_prev.p : nullptr, w->H.p, w->S.p,
-                                                    w->G0.p, w->G1.p, w->L0.p, w->L1.p);
+                                                    w->G0.p, w->G1.p, w->L0.p, w->L1.p, w->RC.p);
         CKL(w); w->launches++;
         CK(cudaMemsetAsync(w->LN.p, 0xFF, size_t(n) * 2 * sizeof(float2), st));
         CK(cudaMemsetAsync(w->M0.p, 0, size_t(n) * 2 * sizeof(float4), st));
@@ -730,6 +738,7 @@ void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
     c.rope_next = w->rope_next.p; c.rope_prev = w->rope_prev.p; c.n_bodies = w->n_bodies;
     c.H = w->H.p; c.S = w->S.p; c.G0 = w->G0.p; c.G1 = w->G1.p; c.L0 = w->L0.p; c.L1 = w->L1.p;
     c.M0 = w->M0.p; c.M1 = w->M1.p; c.M2 = w->M2.p; c.LN = w->LN.p; c.n_units = w->n_units;
+    c.RC = w->RC.p; c.WL = w->WL.p; c.wl_count = w->wl_count.p; c.n_colours = w->n_unit_colours;
     c.K0 = w->K0.p; c.K1 = w->K1.p; c.K2 = w->K2.p; c.n_kunits = w->n_kunits;
     c.RU = w->RU.p; c.RD = w->RD.p; c.RPA = w->RPA.p; c.RPB = w->RPB.p; c.rp_body = w->rp_body.p; c.rp_rope = w->rp_rope.p;
     c.LAT = w->LAT.p; c.n_particles = w->n_particles;
@@ -745,14 +754,14 @@ void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
 void build_stage_table(SfgWorld* w) {
     auto& s = w->h_stages;
     s.clear();
-    auto add = [&](uint32_t kind, uint32_t b, uint32_t e) { if (e > b) s.push_back(Stage{kind, b, e, 0}); };
+    auto add = [&](uint32_t kind, uint32_t b, uint32_t e, uint32_t colour = 0) { if (e > b) s.push_back(Stage{kind, b, e, colour}); };
     add(ST_INTEGRATE, 0, w->n_bodies);
     if (w->n_ropes) for (int c = 0; c < 3; ++c) add(ST_ROPE_STEP, w->rope_colour_start[c], w->rope_colour_start[c + 1]);
     for (uint32_t c = 0; c < w->n_k_colours; ++c) add(ST_CONSTRAINTS, w->k_colour_start[c], w->k_colour_start[c + 1]);
     if (w->n_ropes && w->n_units) add(ST_PRECONTACT, 0, w->n_particles);
-    for (uint32_t c = 0; c < w->n_unit_colours; ++c) add(ST_CONTACTS, w->unit_colour_start[c], w->unit_colour_start[c + 1]);
+    for (uint32_t c = 0; c < w->n_unit_colours; ++c) add(ST_CONTACTS, w->unit_colour_start[c], w->unit_colour_start[c + 1], c);
     add(ST_DERIVE, 0, w->n_bodies);
-    for (uint32_t c = 0; c < w->n_unit_colours; ++c) add(ST_CONTACT_VEL, w->unit_colour_start[c], w->unit_colour_start[c + 1]);
+    for (uint32_t c = 0; c < w->n_unit_colours; ++c) add(ST_CONTACT_VEL, w->unit_colour_start[c], w->unit_colour_start[c + 1], c);
     for (uint32_t c = 0; c < w->n_k_colours; ++c) add(ST_CONSTRAINT_DAMP, w->k_colour_start[c], w->k_colour_start[c + 1]);
     if (w->n_ropes) {
         for (int c = 0; c < 2; ++c) add(ST_ROPE_DAMP, w->damp_colour_start[c], w->damp_colour_start[c + 1]);
@@ -780,6 +789,7 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
         dt = time_scale * frame_dt / double(substeps);
     }
     w->launches = 0;
+    w->frame_dt = float(frame_dt);
     CK(cudaEventRecord(w->ev[0], st));
     if (w->n_bodies) CK(cudaMemsetAsync(w->EA.p, 0, size_t(w->n_bodies) * sizeof(float2), st));
     if (w->n_ropes) CK(cudaMemsetAsync(w->LAT.p, 0xFF, size_t(w->n_bodies) * sizeof(float2), st));
@@ -794,9 +804,14 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
         SolverCtx ctx;
         fill_ctx(w, ctx, float(dt), ff);
         build_stage_table(w);
+        if (w->n_unit_colours) {
+            CK(w->wl_count.ensure(size_t(substeps) * w->n_unit_colours));
+            CK(cudaMemsetAsync(w->wl_count.p, 0, size_t(substeps) * w->n_unit_colours * 4, st));
+            ctx.wl_count = w->wl_count.p;
+        }
         if (w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES) {
             for (uint32_t s = 0; s < substeps; ++s)
-                for (const Stage& sg : w->h_stages) { rc = launch_stage_dyn(w, ctx, sg, s + 1 == substeps); if (rc != SFG_OK) return rc; }
+                for (const Stage& sg : w->h_stages) { rc = launch_stage_dyn(w, ctx, sg, s + 1 == substeps, s); if (rc != SFG_OK) return rc; }
         } else {
             const uint32_t ns = uint32_t(w->h_stages.size());
             CK(w->d_stages.ensure(ns));
@@ -836,6 +851,7 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
     CK(cudaEventRecord(w->ev[3], st));
     CK(cudaStreamSynchronize(st));
     w->ticked = true;
+    w->last_substeps = substeps;
     // stats
     SfgStats& s = w->stats;
     memset(&s, 0, sizeof(s));
@@ -1033,7 +1049,7 @@ int sfg_debug_get_manifolds(SfgWorld* w, float* out, size_t capacity_entries, si
     cudaSetDevice(w->device);
     cudaStream_t st = w->stream;
     CK(w->stage.ensure(size_t(n_entries) * 14 * 4));
-    k_export_manifolds<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->S.p, w->M0.p, w->M1.p, w->M2.p, (float*)w->stage.p);
+    k_export_manifolds<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->last_substeps, w->S.p, w->M0.p, w->M1.p, w->M2.p, (float*)w->stage.p);
     CKL(w);
     CK(cudaMemcpyAsync(out, w->stage.p, size_t(n_entries) * 14 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -284,25 +284,45 @@ __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* 
     if (b.y >= 0) adj[adj_start[b.y] + atomicAdd(cursor + b.y, 1u)] = u;
 }
 
-// Sort key of a coloured unit: colour-major, and inside a colour grouped by narrowphase path (circle-circle /
-// circle-polygon by polygon kind / polygon-polygon by edge count) and visit count, so the 32 lanes of a warp run the
-// same branches. The order inside a colour cannot change results (no shared dynamic body), only divergence.
+// Sort key of a coloured unit: colour-major; inside a colour, units whose bounding circles are clearly apart at tick
+// start come last (the contact stage rejects them with one distance test, so whole warps take the short path), and the
+// rest are grouped by narrowphase path (circle-circle / circle-polygon by polygon kind / polygon-polygon by edge count)
+// and visit count, so the 32 lanes of a warp run the same branches. The order inside a colour cannot change results
+// (no shared dynamic body), only divergence.
+SFG_DI V2 collider_centre(int4 ci, float4 l, const float4* __restrict__ P, const float4* __restrict__ Q, V2* vel) {
+    *vel = mk(0.f, 0.f);
+    if (ci.x < 0) return mk(l.x, l.y);
+    const float4 p = P[ci.x], q = Q[ci.x];
+    return mkrot(q.x, q.y) * mk(l.x, l.y) + mk(p.x + p.z, p.y + p.w);
+}
 __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const uint32_t* __restrict__ colour, const uint2* __restrict__ ids,
-                                                        const float4* __restrict__ CS, const int4* __restrict__ CI, uint32_t* __restrict__ keys) {
+                                                        const float4* __restrict__ CS, const float4* __restrict__ CL,
+                                                        const int4* __restrict__ CI, const float4* __restrict__ P,
+                                                        const float4* __restrict__ Q, const float4* __restrict__ V, float frame_dt,
+                                                        uint32_t* __restrict__ keys) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     uint32_t cls = 0;
     if (CS) {
         const uint2 id = ids[u];
-        const uint32_t k0 = __float_as_uint(CS[id.x].w), k1 = __float_as_uint(CS[id.y].w);
+        const float4 s0 = CS[id.x], s1 = CS[id.y];
+        const int4 c0 = CI[id.x], c1 = CI[id.y];
+        const uint32_t k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w);
         uint32_t path;
         if (k0 == K_POINT && k1 == K_POINT) path = 0;
         else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
         else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
-        const uint32_t mult2 = (CI[id.x].x >= 0 && CI[id.y].x >= 0) ? 1u : 0u;
+        const uint32_t mult2 = (c0.x >= 0 && c1.x >= 0) ? 1u : 0u;
         cls = path * 2 + mult2;
+        // apart now, and by more than the bodies can close in one frame at their current speed (a hint, not a proof)
+        V2 v0, v1;
+        const V2 t0 = collider_centre(c0, CL[id.x], P, Q, &v0), t1 = collider_centre(c1, CL[id.y], P, Q, &v1);
+        if (c0.x >= 0) { const float4 v = V[c0.x]; v0 = mk(v.x, v.y); }
+        if (c1.x >= 0) { const float4 v = V[c1.x]; v1 = mk(v.x, v.y); }
+        const float gap = mag(t1 - t0) - (bound_radius(mkshape(s0)) + bound_radius(mkshape(s1)));
+        if (gap > 0.02f + 1.5f * frame_dt * mag(v1 - v0)) cls |= 16u;
     }
-    keys[u] = colour[u] * 16u + cls;
+    keys[u] = colour[u] * 32u + cls;
 }
 
 constexpr uint32_t UNCOLOURED = 0xFFFFFFFFu;
@@ -409,7 +429,7 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
                                                           const float4* __restrict__ MI, const int* __restrict__ rope_next,
                                                           const int* __restrict__ rope_prev, float4* __restrict__ H, float4* __restrict__ S,
                                                           float4* __restrict__ G0, float4* __restrict__ G1, float4* __restrict__ L0,
-                                                          float4* __restrict__ L1) {
+                                                          float4* __restrict__ L1, float* __restrict__ RC) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_units) return;
     const uint2 id = ids[perm[s]];
@@ -431,8 +451,16 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
     }
     H[s] = make_float4(__int_as_float(c0.x), __int_as_float(c1.x), __uint_as_float(fl), (m0.x + m1.x) / 2.0f);
     S[s] = make_float4(__uint_as_float(id.x), __uint_as_float(id.y), (m0.y + m1.y) / 2.0f, fmaxf(m0.z, m1.z));
-    G0[s] = CS[id.x]; G1[s] = CS[id.y];
-    L0[s] = CL[id.x]; L1[s] = CL[id.y];
+    const float4 g0 = CS[id.x], g1 = CS[id.y], l0 = CL[id.x], l1 = CL[id.y];
+    G0[s] = g0; G1[s] = g1;
+    L0[s] = l0; L1[s] = l1;
+    // bodies (or static collider origins) farther apart than this cannot touch: the colliders' bounding radii, never less
+    // than circle_circle's "closer than sqrt(0.001) always collides" distance, plus how far each collider sits from its
+    // body, plus an f32 safety margin (sfg_solver.cuh stage_contacts)
+    float reach = fmaxf(bound_radius(mkshape(g0)) + bound_radius(mkshape(g1)), 0.0332f);
+    if (c0.x >= 0) reach += sqrtf(l0.x * l0.x + l0.y * l0.y);
+    if (c1.x >= 0) reach += sqrtf(l1.x * l1.x + l1.y * l1.y);
+    RC[s] = reach * 1.001f + 2e-3f;
 }
 __global__ void __launch_bounds__(256) k_build_constraint_units(uint32_t n_units, const uint32_t* __restrict__ perm, const int4* __restrict__ KI,
                                                                 const float4* __restrict__ KA, const float4* __restrict__ KB,

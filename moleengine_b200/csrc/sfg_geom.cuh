@@ -70,6 +70,13 @@ enum : uint32_t { K_POINT = 0, K_SEGMENT = 1, K_RECT = 2, K_TRIANGLE = 3, K_HEXA
 struct Shape { uint32_t kind; float p0, p1, r; };   // p0 = hl | hw | outer_r ; p1 = hh ; r = circle_r
 SFG_DI Shape mkshape(float4 v) { Shape s; s.p0 = v.x; s.p1 = v.y; s.r = v.z; s.kind = __float_as_uint(v.w); return s; }
 
+// radius of the circle around the collider's origin that contains the rounded shape (vertices of Triangle / Hexagon
+// lie at distance p0 from the origin: collider.rs:600-665)
+SFG_DI float bound_radius(const Shape& s) {
+    const float core = s.kind == K_POINT ? 0.f : (s.kind == K_RECT ? sqrtf(s.p0 * s.p0 + s.p1 * s.p1) : s.p0);
+    return core + s.r;
+}
+
 struct Edge { V2 start, dir; float len; };
 struct PEdge { V2 n; Edge e; };
 

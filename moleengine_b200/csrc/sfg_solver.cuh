@@ -234,19 +234,35 @@ SFG_DI void stage_constraint_damp(const SolverCtx& c, uint32_t u) {
 }
 
 // ---------------------------------------------------------------- contacts (solver.rs:275-490, narrowphase inline)
-SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
+SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint32_t colour_begin, uint32_t sub) {
     const float4 h = ldc(c.H + u);
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     const uint32_t fl = __float_as_uint(h.z);
     const float mu_s = h.w;
+    // First reject, on body positions alone (one gather per body, nothing else of the unit is touched): colliders sit
+    // within |local offset| of their body, so bodies farther apart than RC = bounding radii + offsets (+ margin, and never
+    // below circle_circle's sqrt(0.001) rule) cannot produce a contact in any branch of intersection_check. Neither
+    // visit of the unit moves anything then, and the manifold entries keep an old tag = "no contact".
+    const float reach = __ldg(c.RC + u);
+    float4 P0 = make_float4(0, 0, 0, 0), P1 = P0;
+    float4 l0, l1;
+    if (b0 >= 0) P0 = ldb(c.P + b0); else l0 = ldc(c.L0 + u);
+    if (b1 >= 0) P1 = ldb(c.P + b1); else l1 = ldc(c.L1 + u);
+    {
+        const V2 a = b0 >= 0 ? mk(P0.x, P0.y) : mk(l0.x, l0.y), da = mk(P0.z, P0.w);
+        const V2 b = b1 >= 0 ? mk(P1.x, P1.y) : mk(l1.x, l1.y), db = mk(P1.z, P1.w);
+        const V2 d = mk((b.x - a.x) + (db.x - da.x), (b.y - a.y) + (db.y - da.y));
+        if (mag_sq(d) > reach * reach) return;
+    }
+    if (b0 >= 0) l0 = ldc(c.L0 + u);
+    if (b1 >= 0) l1 = ldc(c.L1 + u);
     const Shape sh0 = mkshape(ldc(c.G0 + u)), sh1 = mkshape(ldc(c.G1 + u));
-    const float4 l0 = ldc(c.L0 + u), l1 = ldc(c.L1 + u);
     const Iso loc0 = mkiso(mk(l0.x, l0.y), mkrot(l0.z, l0.w)), loc1 = mkiso(mk(l1.x, l1.y), mkrot(l1.z, l1.w));
 
-    float4 P0 = make_float4(0, 0, 0, 0), Q0 = make_float4(1, 0, 1, 0), P1 = P0, Q1 = Q0;
+    float4 Q0 = make_float4(1, 0, 1, 0), Q1 = Q0;
     float im0 = 0.f, ii0 = 0.f, im1 = 0.f, ii1 = 0.f;
-    if (b0 >= 0) { P0 = ldb(c.P + b0); Q0 = ldb(c.Q + b0); float4 m = ldb(c.MI + b0); im0 = m.x; ii0 = m.y; }
-    if (b1 >= 0) { P1 = ldb(c.P + b1); Q1 = ldb(c.Q + b1); float4 m = ldb(c.MI + b1); im1 = m.x; ii1 = m.y; }
+    if (b0 >= 0) { Q0 = ldb(c.Q + b0); float4 m = ldb(c.MI + b0); im0 = m.x; ii0 = m.y; }
+    if (b1 >= 0) { Q1 = ldb(c.Q + b1); float4 m = ldb(c.MI + b1); im1 = m.x; ii1 = m.y; }
     // pair-local frame: origin at object 0's substep-start position (or its static translation)
     const V2 org = b0 >= 0 ? mk(P0.x, P0.y) : loc0.t;
     const V2 told0 = mk(0.f, 0.f);
@@ -257,17 +273,29 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
     const Rot ro0 = mkrot(Q0.z, Q0.w), ro1 = mkrot(Q1.z, Q1.w);
     const int mult = (fl & UF_MULT2) ? 2 : 1;
     const bool sees = (fl & (UF_SEES0 | UF_SEES1)) != 0;
+    // Second reject, per visit, on the collider centres themselves: every branch of intersection_check that reports a
+    // contact needs the rounded shapes to overlap, so centres farther apart than the two bounding radii (plus an f32
+    // safety margin) give count == 0. The floor keeps circle_circle's "centres closer than sqrt(0.001) always collide"
+    // rule (shape_shape.rs:95-103) out of the shortcut; a NaN distance fails the comparison and takes the exact path.
+    const float reach2 = (bound_radius(sh0) + bound_radius(sh1)) * 1.001f + 1e-3f;
+    const float far_sq = fmaxf(reach2 * reach2, 0.0011f);
 
-    bool prev_zero = false;
+    const uint32_t tag = (sub + 1u) << 8;
+    bool moved = false;
     for (int m = 0; m < mult; ++m) {
         const uint32_t e = u + uint32_t(m) * c.n_units;
-        // second visit of a pair whose first visit found nothing: no pose changed, so the same test gives the same nothing
-        if (prev_zero) { stb(c.M0 + e, make_float4(0.f, 0.f, 0.f, 0.f)); continue; }
         const Iso pw0 = b0 >= 0 ? mkiso(mk(P0.z, P0.w), r0) * loc0 : st0;
         const Iso pw1 = b1 >= 0 ? mkiso(mk(told1.x + P1.z, told1.y + P1.w), r1) * loc1 : st1;
         Manifold mf;
-        intersection_check(pw0, pw1, sh0, sh1, mf);
-        if (mf.count == 0) { stb(c.M0 + e, make_float4(0.f, 0.f, 0.f, 0.f)); prev_zero = true; continue; }
+        mf.count = 0;
+        if (!(mag_sq(pw1.t - pw0.t) > far_sq)) intersection_check(pw0, pw1, sh0, sh1, mf);
+        if (mf.count == 0) {
+            // first visit found nothing: no pose changed, so the second visit finds the same nothing and the unit is done
+            // without a single store. A second visit that finds nothing after a first that did must say so (fresh tag).
+            if (m == 0) return;
+            stb(c.M0 + e, make_float4(__int_as_float(int(tag)), 0.f, 0.f, 0.f));
+            continue;
+        }
         for (int k = 0; k < mf.count; ++k) {                            // solver.rs:308-315
             if (b0 >= 0) mf.off[k][0] = loc0 * mf.off[k][0];
             if (b1 >= 0) mf.off[k][1] = loc1 * mf.off[k][1];
@@ -314,6 +342,7 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
                     float depth = dot(ow0 - ow1, n);
                     if (depth <= 0.f) { lambda_n = 0.f; continue; }
                     lambda_n = -depth / (en0 + en1);
+                    moved = true;
                     apply_correction(P0, r0, im0, ii0, 1.f, lambda_n, n, wn0);
                     apply_correction(P1, r1, im1, ii1, -1.f, lambda_n, n, wn1);
                     if (fl & UF_HAS_SF) {                               // solver.rs:456-487
@@ -328,24 +357,39 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u) {
                 }
             }
         }
-        stb(c.M0 + e, make_float4(__int_as_float(mf.count), lambda_n, mf.n.x, mf.n.y));
+        stb(c.M0 + e, make_float4(__int_as_float(mf.count | int(tag)), lambda_n, mf.n.x, mf.n.y));
         stb(c.M1 + e, make_float4(mf.off[0][0].x, mf.off[0][0].y, mf.off[0][1].x, mf.off[0][1].y));
         if (mf.count == 2) stb(c.M2 + e, make_float4(mf.off[1][0].x, mf.off[1][0].y, mf.off[1][1].x, mf.off[1][1].y));
     }
-    if (fl & UF_SEES0) { stb(c.P + b0, P0); Q0.x = r0.s; Q0.y = r0.b; stb(c.Q + b0, Q0); }
-    if (fl & UF_SEES1) { stb(c.P + b1, P1); Q1.x = r1.s; Q1.y = r1.b; stb(c.Q + b1, Q1); }
+    if (moved) {
+        if (fl & UF_SEES0) { stb(c.P + b0, P0); Q0.x = r0.s; Q0.y = r0.b; stb(c.Q + b0, Q0); }
+        if (fl & UF_SEES1) { stb(c.P + b1, P1); Q1.x = r1.s; Q1.y = r1.b; stb(c.Q + b1, Q1); }
+    }
+    // the first visit found a contact: queue the unit for this substep's velocity sweep (solver.rs:496-618 skips sensors
+    // and pairs that see no forces). One atomic per group of converged lanes.
+    if (!(fl & UF_SENSOR) && sees) {
+        const uint32_t act = __activemask(), lane = threadIdx.x & 31u;
+        const int leader = __ffs(int(act)) - 1;
+        uint32_t base = 0;
+        if (int(lane) == leader) base = atomicAdd(c.wl_count + sub * c.n_colours + colour, uint32_t(__popc(act)));
+        base = __shfl_sync(act, base, leader);
+        __stcg(c.WL + colour_begin + base + uint32_t(__popc(act & ((1u << lane) - 1u))), u);
+    }
 }
 
 // solver.rs:496-618
-SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u) {
+SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u, uint32_t sub) {
     const float4 h = ldc(c.H + u);
     const uint32_t fl = __float_as_uint(h.z);
-    if ((fl & UF_SENSOR) || !(fl & (UF_SEES0 | UF_SEES1))) return;
     const int mult = (fl & UF_MULT2) ? 2 : 1;
+    const uint32_t tag = sub + 1u;
     float4 m0[2];
     m0[0] = ldb(c.M0 + u);
     m0[1] = mult == 2 ? ldb(c.M0 + u + c.n_units) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (__float_as_int(m0[0].x) == 0 && __float_as_int(m0[1].x) == 0) return;
+    int cnt[2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) { const uint32_t bits = __float_as_uint(m0[m].x); cnt[m] = (bits >> 8) == tag ? int(bits & M0_COUNT_MASK) : 0; }
+    if (cnt[0] == 0 && cnt[1] == 0) return;
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     const float4 s = ldc(c.S + u);
     const float mu_d = s.z, rest_mat = s.w;
@@ -353,11 +397,15 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u) {
     Rot r0 = mkrot(1.f, 0.f), r1 = r0;
     float im0 = 0.f, ii0 = 0.f, im1 = 0.f, ii1 = 0.f;
     V2 ea = mk(0.f, 0.f);
-    if (b0 >= 0) { float4 q = ldb(c.Q + b0); r0 = mkrot(q.x, q.y); V0 = ldb(c.V + b0); OV0 = ldb(c.OV + b0); float4 mi = ldb(c.MI + b0); im0 = mi.x; ii0 = mi.y; float2 a = ldb(c.EA + b0); ea = ea + mk(a.x, a.y); }
-    if (b1 >= 0) { float4 q = ldb(c.Q + b1); r1 = mkrot(q.x, q.y); V1 = ldb(c.V + b1); OV1 = ldb(c.OV + b1); float4 mi = ldb(c.MI + b1); im1 = mi.x; ii1 = mi.y; float2 a = ldb(c.EA + b1); ea = ea + mk(a.x, a.y); }
+    // old velocities and external accelerations only feed the restitution term (solver.rs:555-576): e = 0 never reads them
+    const bool bouncy = rest_mat != 0.f;
+    if (b0 >= 0) { float4 q = ldb(c.Q + b0); r0 = mkrot(q.x, q.y); V0 = ldb(c.V + b0); float4 mi = ldb(c.MI + b0); im0 = mi.x; ii0 = mi.y;
+                   if (bouncy) { OV0 = ldb(c.OV + b0); float2 a = ldb(c.EA + b0); ea = ea + mk(a.x, a.y); } }
+    if (b1 >= 0) { float4 q = ldb(c.Q + b1); r1 = mkrot(q.x, q.y); V1 = ldb(c.V + b1); float4 mi = ldb(c.MI + b1); im1 = mi.x; ii1 = mi.y;
+                   if (bouncy) { OV1 = ldb(c.OV + b1); float2 a = ldb(c.EA + b1); ea = ea + mk(a.x, a.y); } }
     const float rest_gate = c.dt * c.dt * mag_sq(ea);
     for (int m = 0; m < mult; ++m) {
-        const int count = __float_as_int(m0[m].x);
+        const int count = cnt[m];
         if (count == 0) continue;
         const uint32_t e = u + uint32_t(m) * c.n_units;
         const float lambda_n = m0[m].y;
@@ -371,7 +419,7 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u) {
             V2 rel = pv0 - pv1;
             float nv = dot(rel, n);
             float onv = dot(opv0 - opv1, n);
-            float rest = (onv * onv < rest_gate) ? 0.f : rest_mat;
+            float rest = (!bouncy || onv * onv < rest_gate) ? 0.f : rest_mat;
             float dnv = -nv - rest * fmaxf(onv, 0.f);
             float dtv = 0.f;
             if (fl & UF_HAS_DF) {
@@ -395,15 +443,15 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u) {
 }
 
 // ---------------------------------------------------------------- drivers
-SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_substep) {
+SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_substep, uint32_t sub, uint32_t colour, uint32_t begin) {
     switch (kind) {
     case ST_INTEGRATE: stage_integrate(c, i); break;
     case ST_ROPE_STEP: stage_rope_step(c, i); break;
     case ST_CONSTRAINTS: stage_constraints(c, i); break;
     case ST_PRECONTACT: stage_precontact(c, i); break;
-    case ST_CONTACTS: stage_contacts(c, i); break;
+    case ST_CONTACTS: stage_contacts(c, i, colour, begin, sub); break;
     case ST_DERIVE: stage_derive(c, i, last_substep); break;
-    case ST_CONTACT_VEL: stage_contact_vel(c, i); break;
+    case ST_CONTACT_VEL: stage_contact_vel(c, __ldcg(c.WL + i), sub); break;   // i indexes the colour's worklist
     case ST_CONSTRAINT_DAMP: stage_constraint_damp(c, i); break;
     case ST_ROPE_DAMP: stage_rope_damp(c, i); break;
     case ST_ROPE_LATERAL: stage_rope_lateral(c, i); break;
@@ -413,9 +461,11 @@ SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_s
 }
 
 template <uint32_t KIND>
-__global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx c, uint32_t begin, uint32_t end, int last_substep) {
+__global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx c, uint32_t begin, uint32_t end, int last_substep, uint32_t sub,
+                                               uint32_t colour) {
+    if (KIND == ST_CONTACT_VEL) end = begin + __ldcg(c.wl_count + sub * c.n_colours + colour);   // only the units queued by the position sweep
     const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < end) run_stage(c, KIND, i, last_substep != 0);
+    if (i < end) run_stage(c, KIND, i, last_substep != 0, sub, colour, begin);
 }
 
 // Grid-wide barrier of the persistent kernel: one release-atomic per CTA on a monotonically increasing counter, a
@@ -449,10 +499,10 @@ __global__ void __launch_bounds__(768, 1) k_solve_persistent(const __grid_consta
         const bool last = s + 1 == substeps;
         for (uint32_t k = 0; k < n_stages; ++k) {
             const Stage st = stages[k];
-            const uint32_t n = st.end - st.begin;
+            const uint32_t n = st.kind == ST_CONTACT_VEL ? __ldcg(c.wl_count + s * c.n_colours + st.colour) : st.end - st.begin;
             for (uint32_t chunk = first_chunk; chunk * 32u < n; chunk += chunk_stride) {
                 const uint32_t i = chunk * 32u + lane;
-                if (i < n) run_stage(c, st.kind, st.begin + i, last);
+                if (i < n) run_stage(c, st.kind, st.begin + i, last, s, st.colour, st.begin);
             }
             grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t(s * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
         }

@@ -9,7 +9,12 @@
 //             CM float4 (mu_s, mu_d, e, flags)   CI int4 (body, layer, domain, flags)   AABB float4
 //  pair units (sorted colour-major, rebuilt every tick)
 //             H  (body0, body1, flags, mu_s)   S (hi, lo, mu_d, e)   G0 G1 shapes   L0 L1 local poses
-//             M0 (count, lambda_n, n.x, n.y)  M1 / M2 point 0 / 1 (off0.xy, off1.xy); entry = copy * n_units + unit
+//             RC float: body centres farther apart than this cannot touch (bounding radii + local offsets + margin)
+//             M0 (count | tag << 8, lambda_n, n.x, n.y)  M1 / M2 point 0 / 1 (off0.xy, off1.xy); entry = copy * n_units + unit
+//                tag = substep + 1 of the visit that wrote the entry: an entry with another tag counts as "no contact",
+//                so visits that find nothing write nothing
+//             WL u32: per colour (same ranges as the units) the units that found a contact in the current substep;
+//                wl_count[substep * n_colours + colour] = how many. The velocity sweep walks these lists only.
 //
 // Keeping (x_old, dx) instead of x lets every kernel form differences of nearby points without the
 // cancellation that absolute f32 coordinates suffer far from the origin, and makes the velocity
@@ -63,9 +68,12 @@ struct SolverCtx {
     uint32_t n_bodies;
     // pair units
     const float4 *H, *S, *G0, *G1, *L0, *L1;
+    const float* RC;
     float4 *M0, *M1, *M2;
     float2* LN;
-    uint32_t n_units;
+    uint32_t* WL;
+    uint32_t* wl_count;
+    uint32_t n_units, n_colours;
     // constraint units (sorted colour-major)
     const float4 *K0, *K1, *K2;   // (owner, target, flags, -) (compliance, lin damp, ang damp, distance) (off0.xy, off1.xy)
     uint32_t n_kunits;
@@ -87,6 +95,7 @@ enum StageKind : uint32_t {
     ST_INTEGRATE = 0, ST_ROPE_STEP, ST_CONSTRAINTS, ST_PRECONTACT, ST_CONTACTS, ST_DERIVE, ST_CONTACT_VEL,
     ST_CONSTRAINT_DAMP, ST_ROPE_DAMP, ST_ROPE_LATERAL, ST_FOLD,
 };
-struct Stage { uint32_t kind, begin, end, pad; };
+struct Stage { uint32_t kind, begin, end, colour; };   // colour: index of the contact colour (contact stages only)
+constexpr uint32_t M0_COUNT_MASK = 0xFFu;
 
 }  // namespace sfg
