@@ -90,7 +90,8 @@ struct SfgWorld {
     std::vector<uint32_t> unit_colour_start;   // n_unit_colours + 1
     DBuf<uint2> U_ids;
     DBuf<int2> U_ub;
-    DBuf<uint32_t> U_prio, U_colour, deg, adj_start, adj, cursor, jp_counters, jp_hist, perm0, perm1, ckey0, ckey1;
+    DBuf<uint2> adj2;   // body -> (unit, priority)
+    DBuf<uint32_t> U_prio, U_colour, deg, adj_start, cursor, jp_counters, jp_hist, perm0, perm1, ckey0, ckey1;
     DBuf<float4> H, S, G0, G1, L0, L1, M0, M1, M2;
     DBuf<float2> LN;
     DBuf<float> RC;
@@ -290,29 +291,40 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     *perm_out = nullptr;
     if (n_units == 0) { colour_start.push_back(0); return SFG_OK; }
     const uint32_t nb = w->n_bodies;
-    // adjacency (deg was accumulated by the unit-setup kernel)
-    CK(w->adj_start.ensure(nb + 2)); CK(w->cursor.ensure(nb + 1)); CK(w->adj.ensure(size_t(n_units) * 2 + 1));
+    // adjacency (deg was accumulated by the unit-setup kernel) + bucket keys of the colouring order
+    constexpr uint32_t HIST_CAP = 65536;
+    CK(w->adj_start.ensure(nb + 2)); CK(w->cursor.ensure(nb + 1)); CK(w->adj2.ensure(size_t(n_units) * 2 + 1));
     CK(w->scan_tmp.ensure(scan_tmp_words(nb + 1)));
+    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(16)); CK(w->jp_hist.ensure(HIST_CAP));
+    CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units)); CK(w->perm0.ensure(n_units)); CK(w->perm1.ensure(n_units));
+    CK(w->sort_tmp.ensure(sort_tmp_words(n_units)));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_dataflow, 1024, 0));
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(uint32_t(per_sm * w->n_sms), nblk(n_units, 1024)));
+    // a bucket must span far fewer units than the co-resident threads (progress argument in k_colour_dataflow):
+    // 2^bits buckets of ~n / 2^bits units each (priorities are hashes), kept under 1/8 of the resident threads
+    int bucket_bits = 8;
+    while (bucket_bits < 24 && (size_t(n_units) >> bucket_bits) * 8 > size_t(grid) * 1024) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
-    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, w->adj_start.p, w->cursor.p, w->adj.p); CKL(w); w->launches++;
-    // Jones-Plassmann in one cooperative launch
-    constexpr uint32_t HIST_CAP = 65536;
-    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(JP_MAX_ROUNDS + 16)); CK(w->jp_hist.ensure(HIST_CAP));
-    CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units));   // reused as the two worklists before they hold sort keys
+    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
+    CKL(w); w->launches++;
+    const uint32_t* order;
+    {
+        int launches = 0;
+        const int where = radix_sort_pairs(w->ckey0.p, w->perm0.p, w->ckey1.p, w->perm1.p, n_units, bucket_bits, w->sort_tmp.p, st, &launches);
+        w->launches += launches;
+        order = where ? w->perm1.p : w->perm0.p;
+    }
     CK(cudaMemsetAsync(colour.p, 0xFF, size_t(n_units) * 4, st));
-    CK(cudaMemsetAsync(w->jp_counters.p, 0, (JP_MAX_ROUNDS + 16) * 4, st));
+    CK(cudaMemsetAsync(w->jp_counters.p, 0, 16 * 4, st));
     CK(cudaMemsetAsync(w->jp_hist.p, 0, HIST_CAP * 4, st));
     {
-        int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_jp_colour, 1024, 0));
-        uint32_t grid = std::min<uint32_t>(uint32_t(per_sm * w->n_sms), std::max<uint32_t>(nblk(n_units), 1));
         uint32_t hist_cap = HIST_CAP;
-        const uint32_t* adj_start = w->adj_start.p; const uint32_t* adj = w->adj.p;
+        const uint32_t* adj_start = w->adj_start.p; const uint2* adj = w->adj2.p;
         uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_hist.p;
-        uint32_t* l0 = w->ckey0.p; uint32_t* l1 = w->ckey1.p;
-        void* args[] = {&n_units, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &ctrl, &hist, &hist_cap, &l0, &l1};
-        CK(cudaLaunchCooperativeKernel((void*)k_jp_colour, dim3(grid), dim3(1024), args, 0, st));
+        void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &ctrl, &hist, &hist_cap};
+        CK(cudaLaunchCooperativeKernel((void*)k_colour_dataflow, dim3(grid), dim3(1024), args, 0, st));
         w->launches++;
     }
     uint32_t jp_ctrl[8] = {0};
@@ -330,8 +342,6 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     colour_start[n_colours] = run;
     if (run != n_units) return fail(w, SFG_E_CAPACITY, "colouring left units uncoloured");
     // stable sort by colour: perm = unit indices in colour-major order
-    CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units)); CK(w->perm0.ensure(n_units)); CK(w->perm1.ensure(n_units));
-    CK(w->sort_tmp.ensure(sort_tmp_words(n_units)));
     k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p,
                                                     w->frame_dt, w->ckey0.p); CKL(w); w->launches++;
     k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
@@ -391,14 +401,14 @@ void sfg_world_destroy(SfgWorld* w) {
     DBuf<float2>* f2[] = {&w->EA, &w->PCD, &w->LAT, &w->LN};
     for (auto* b : f2) b->release();
     DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->warp_counts, &w->scan_tmp, &w->U_prio,
-                            &w->U_colour, &w->deg, &w->adj_start, &w->adj, &w->cursor, &w->jp_counters, &w->jp_hist, &w->perm0, &w->perm1,
+                            &w->U_colour, &w->deg, &w->adj_start, &w->cursor, &w->jp_counters, &w->jp_hist, &w->perm0, &w->perm1,
                             &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour};
     for (auto* b : u1) b->release();
     DBuf<int>* i1[] = {&w->rope_next, &w->rope_prev, &w->rp_body, &w->rp_rope};
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);

@@ -275,13 +275,19 @@ __global__ void __launch_bounds__(256) k_constraint_unit_setup(uint32_t n_units,
     if (b0 >= 0) atomicAdd(deg + b0, 1u);
     if (b1 >= 0) atomicAdd(deg + b1, 1u);
 }
-__global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ adj_start,
-                                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ adj) {
+// adjacency lists body -> (unit, priority of the unit); also the bucket key of the colouring pass (descending priority)
+__global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
+                                                  const uint32_t* __restrict__ adj_start, uint32_t* __restrict__ cursor,
+                                                  uint2* __restrict__ adj, int bucket_shift, uint32_t* __restrict__ bucket_key,
+                                                  uint32_t* __restrict__ order) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const int2 b = ub[u];
-    if (b.x >= 0) adj[adj_start[b.x] + atomicAdd(cursor + b.x, 1u)] = u;
-    if (b.y >= 0) adj[adj_start[b.y] + atomicAdd(cursor + b.y, 1u)] = u;
+    const uint32_t p = prio[u];
+    if (b.x >= 0) adj[adj_start[b.x] + atomicAdd(cursor + b.x, 1u)] = make_uint2(u, p);
+    if (b.y >= 0) adj[adj_start[b.y] + atomicAdd(cursor + b.y, 1u)] = make_uint2(u, p);
+    bucket_key[u] = (~p) >> bucket_shift;
+    order[u] = u;
 }
 
 // Sort key of a coloured unit: colour-major; inside a colour, units whose bounding circles are clearly apart at tick
@@ -326,52 +332,38 @@ __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const 
 }
 
 constexpr uint32_t UNCOLOURED = 0xFFFFFFFFu;
-constexpr uint32_t JP_MAX_ROUNDS = 8192;
 
-// Jones-Plassmann: a unit takes the smallest colour unused by its higher-priority neighbours once all of
-// them are coloured; the fixed point equals greedy colouring in descending priority (what the oracle runs).
-// One cooperative launch; units that are not ready go to the next round's worklist (warp-aggregated append), so
-// later rounds only touch what is left. ctrl: [0] barrier, [1] max colour + 1, [4] rounds used, [8 + r] worklist size after round r.
-// [4] rounds used. hist = units per colour.
-SFG_DI void jp_barrier(unsigned int* counter, unsigned int& target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        target += gridDim.x;
-        __threadfence();
-        atomicAdd(counter, 1u);
-        unsigned int seen;
-        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory"); } while (seen < target);
-        __threadfence();
-    }
-    __syncthreads();
-}
-__global__ void __launch_bounds__(1024) k_jp_colour(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
-                                                   const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
-                                                   const uint32_t* __restrict__ adj, uint32_t* colour, uint32_t* ctrl,
-                                                   uint32_t* hist, uint32_t hist_cap, uint32_t* list0, uint32_t* list1) {
+// Greedy colouring in descending priority (include/sfg_hash.h): a unit takes the smallest colour unused by its
+// higher-priority neighbours. The definition is sequential; here it runs in ONE pass as a dataflow: units are
+// bucket-sorted by the top bits of the priority (k_adj_fill + one radix pass), warps take 32-unit chunks of that order
+// round-robin, and a unit simply polls the colour words of its higher-priority neighbours until all are set. The
+// result is the same fixed point Jones-Plassmann rounds converge to (bit-identical to the oracle's greedy loop),
+// without a grid barrier per round. No fences: the polled word IS the data.
+// Progress: the highest-priority uncoloured unit never waits, every unit of an earlier bucket is coloured by then, and
+// a bucket spans far fewer chunks than there are co-resident warps (checked on the host), so the warp that owns its
+// chunk has finished all its earlier chunks and is running it.
+// ctrl: [1] max colour + 1, [4] 1. hist = units per colour.
+__global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, const uint32_t* __restrict__ order, const int2* __restrict__ ub,
+                                                         const uint32_t* __restrict__ prio, const uint2* __restrict__ ids,
+                                                         const uint32_t* __restrict__ adj_start, const uint2* __restrict__ adj,
+                                                         uint32_t* colour, uint32_t* ctrl, uint32_t* hist, uint32_t hist_cap) {
     __shared__ uint32_t s_hist[64];
     __shared__ uint32_t s_max;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const uint32_t lane = threadIdx.x & 31;
     if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_max = 0;
     __syncthreads();
-    unsigned int target = 0;
-    uint32_t n_cur = n_units;
-    for (uint32_t round = 0; round < JP_MAX_ROUNDS && n_cur; ++round) {
-        const uint32_t* cur = (round & 1) ? list1 : list0;
-        uint32_t* nxt = (round & 1) ? list0 : list1;
-        uint32_t* nxt_count = ctrl + 8 + round;                 // one size slot per round: never reset, one barrier per round
-        const uint32_t n_iter = (n_cur + nth - 1) / nth;
-        for (uint32_t it = 0; it < n_iter; ++it) {
-            const uint32_t idx = it * nth + tid;
-            bool pending = false;
-            uint32_t u = 0;
-            if (idx < n_cur) {
-                u = round == 0 ? idx : cur[idx];
-                const int2 b = ub[u];
-                const uint32_t pu = prio[u];
-                const uint2 iu = ids[u];
+    const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+    const uint32_t n_warps = gridDim.x * warps_per_cta;
+    // chunk c -> CTA c mod gridDim (spread over SMs), warp slot (c / gridDim) mod warps_per_cta
+    for (uint32_t chunk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x; chunk * 32u < n_units; chunk += n_warps) {
+        const uint32_t idx = chunk * 32u + lane;
+        bool done = idx >= n_units;
+        uint32_t u = 0, pu = 0;
+        int2 b = make_int2(-1, -1);
+        uint2 iu = make_uint2(0, 0);
+        if (!done) { u = order[idx]; b = ub[u]; pu = prio[u]; iu = ids[u]; }
+        while (__any_sync(0xFFFFFFFFu, !done)) {
+            if (!done) {
                 bool ready = true;
                 uint32_t result = 0;
                 for (uint32_t win = 0; ready; win += 64) {   // window of 64 colours at a time
@@ -382,13 +374,12 @@ __global__ void __launch_bounds__(1024) k_jp_colour(uint32_t n_units, const int2
                         if (body < 0) continue;
                         const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
                         for (uint32_t a = a0; a < a1; ++a) {
-                            const uint32_t v = adj[a];
-                            if (v == u) continue;
-                            const uint32_t pv = prio[v];
-                            bool higher = pv > pu;
-                            if (pv == pu) { const uint2 iv = ids[v]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
+                            const uint2 vp = adj[a];
+                            if (vp.x == u) continue;
+                            bool higher = vp.y > pu;
+                            if (vp.y == pu) { const uint2 iv = ids[vp.x]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
                             if (!higher) continue;
-                            const uint32_t cv = __ldcg(colour + v);
+                            const uint32_t cv = ld_relaxed(colour + vp.x);
                             if (cv == UNCOLOURED) { ready = false; break; }
                             if (cv >= win && cv < win + 64) used |= 1ull << (cv - win);
                             else if (cv >= win + 64) beyond = true;
@@ -399,27 +390,18 @@ __global__ void __launch_bounds__(1024) k_jp_colour(uint32_t n_units, const int2
                     if (!beyond) { result = win + 64; break; }
                 }
                 if (ready) {
-                    __stcg(colour + u, result);
+                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(colour + u), "r"(result) : "memory");
                     if (result < 64) atomicAdd(&s_hist[result], 1u);
                     else if (result < hist_cap) atomicAdd(hist + result, 1u);
                     atomicMax(&s_max, result + 1u);
-                } else pending = true;
-            }
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pending);
-            if (ballot) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(nxt_count, __popc(ballot));
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (pending) nxt[base + __popc(ballot & ((1u << lane) - 1u))] = u;
+                    done = true;
+                } else __nanosleep(100);
             }
         }
-        jp_barrier(ctrl, target);
-        n_cur = __ldcg(nxt_count);
-        if (tid == 0) ctrl[4] = round + 1;
     }
     __syncthreads();
     if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(hist + threadIdx.x, s_hist[threadIdx.x]);
-    if (threadIdx.x == 0 && s_max) atomicMax(ctrl + 1, s_max);
+    if (threadIdx.x == 0) { if (s_max) atomicMax(ctrl + 1, s_max); ctrl[4] = 1u; }
 }
 
 // after the stable sort by colour: write the streaming columns of each pair unit

@@ -27,6 +27,12 @@ namespace sfg {
 
 constexpr int MAX_LEVELS = 8;
 
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct GridParams {
     float ox, oy;
     int n_levels;                 // grid levels; colliders larger than the top cell go to the "huge" list
