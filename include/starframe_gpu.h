@@ -62,6 +62,7 @@ typedef struct SfgBody {
 #define SFG_BODY_IGNORES_GRAVITY 2u
 #define SFG_BODY_MASS_FINITE 4u
 #define SFG_BODY_INERTIA_FINITE 8u
+#define SFG_BODY_ASLEEP 16u          /* output only (sfg_get_bodies): the body's island was skipped in the last tick (physics.rs:711-741) */
 
 /* collider.rs:19-29 Collider, :197-200 ColliderShape, :378-410 ColliderPolygon, :903-911 material */
 typedef struct SfgCollider {
@@ -214,6 +215,10 @@ int sfg_debug_get_constraint_entries(SfgWorld* w, uint32_t* out_index_copy, uint
 int sfg_debug_get_manifolds(SfgWorld* w, float* out, size_t capacity_entries, size_t* n_out);
 /* per collider slot: tick-time AABB (min.xy, max.xy) */
 int sfg_debug_get_aabbs(SfgWorld* w, float* out, size_t capacity_colliders);
+/* islands of the last tick (physics.rs:598-705): IslandId {first_body, edge_sum} (physics.rs:178-185), body count,
+ * flags: 1 cannot sleep, 2 a body moved since the last tick, 4 a body is fast after the solve, 8 asleep (skipped) */
+int sfg_debug_get_islands(SfgWorld* w, uint32_t* first_body, uint64_t* edge_sum, uint32_t* body_count, uint32_t* flags,
+                          size_t capacity, size_t* n_out);
 /* standalone device narrowphase: n pairs of (pose, shape) -> 14 floats each (as above, lambda=0).
  * poses: 2*n rows of (x, y, rot_s, rot_b); shapes: 2*n rows of (kind, p0, p1, circle_r) as floats. */
 int sfg_debug_intersection_check(int device, uint32_t n, const float* poses, const float* shapes, float* out);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libstarframe_gpu.so")
 
 SFG_OK, SFG_E_INVALID, SFG_E_CUDA, SFG_E_CAPACITY, SFG_E_NO_DEVICE, SFG_E_STATE = 0, 1, 2, 3, 4, 5
 
-BODY_ALIVE, BODY_IGNORES_GRAVITY, BODY_MASS_FINITE, BODY_INERTIA_FINITE = 1, 2, 4, 8
+BODY_ALIVE, BODY_IGNORES_GRAVITY, BODY_MASS_FINITE, BODY_INERTIA_FINITE, BODY_ASLEEP = 1, 2, 4, 8, 16
 POLY_POINT, POLY_SEGMENT, POLY_RECT, POLY_TRIANGLE, POLY_HEXAGON = 0, 1, 2, 3, 4
 COLL_ALIVE, COLL_SENSOR, COLL_HAS_STATIC_FRICTION, COLL_HAS_DYNAMIC_FRICTION = 1, 2, 4, 8
 LIMIT_EQ, LIMIT_LT, LIMIT_GT, CONSTRAINT_CAN_SLEEP = 0, 1, 2, 4
@@ -59,7 +59,7 @@ EXPORTS = [
     "sfg_set_mask_matrix", "sfg_default_tuning", "sfg_default_mask_matrix", "sfg_set_bodies", "sfg_update_bodies",
     "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_tick", "sfg_get_bodies",
     "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_query_point_batch", "sfg_debug_get_pairs",
-    "sfg_debug_get_contact_entries", "sfg_debug_get_constraint_entries", "sfg_debug_get_manifolds", "sfg_debug_get_aabbs",
+    "sfg_debug_get_contact_entries", "sfg_debug_get_constraint_entries", "sfg_debug_get_manifolds", "sfg_debug_get_aabbs", "sfg_debug_get_islands",
     "sfg_debug_intersection_check", "sfg_debug_spherecast_collider", "sfg_debug_geometry",
 ]
 
@@ -109,6 +109,7 @@ def load():
     lib.sfg_debug_get_constraint_entries.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     lib.sfg_debug_get_manifolds.argtypes = [vp, vp, sz, C.POINTER(sz)]
     lib.sfg_debug_get_aabbs.argtypes = [vp, vp, sz]
+    lib.sfg_debug_get_islands.argtypes = [vp, vp, vp, vp, vp, sz, C.POINTER(sz)]
     lib.sfg_debug_intersection_check.argtypes = [i32, u32, vp, vp, vp]
     lib.sfg_debug_spherecast_collider.argtypes = [i32, u32, vp, vp, vp, vp]
     lib.sfg_debug_geometry.argtypes = [i32, u32, u32, vp, vp, vp]

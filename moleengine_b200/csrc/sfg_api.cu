@@ -13,6 +13,7 @@
 #include "../../include/starframe_gpu.h"
 #include "sfg_broadphase.cuh"
 #include "sfg_cast.cuh"
+#include "sfg_islands.cuh"
 #include "sfg_solver.cuh"
 #include "sfg_sort.cuh"
 
@@ -48,7 +49,7 @@ struct TickHeader {            // small device block read back once per tick pha
 struct SfgWorld {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     SfgTuning tuning{};
     uint64_t mask[64];
@@ -111,6 +112,12 @@ struct SfgWorld {
     // casts
     DBuf<SfgRay> d_rays;
     DBuf<SfgCastHit> d_hits;
+    // islands + sleeping (sfg_islands.cuh)
+    DBuf<uint32_t> isl_parent, isl_flags, isl_count, sl_ticks, sl_valid, isl_counters;
+    DBuf<unsigned long long> isl_sum, sl_sum;
+    DBuf<ContactRec> ct[2];       // contact list of the last tick (with retention for sleeping islands), double-buffered
+    uint32_t ct_n = 0, ct_cur = 0;
+    bool islands_valid = false;   // the last tick ran the island pass
     // stats
     SfgStats stats{};
     uint32_t launches = 0;
@@ -402,13 +409,14 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : f2) b->release();
     DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->warp_counts, &w->scan_tmp, &w->U_prio,
                             &w->U_colour, &w->deg, &w->adj_start, &w->cursor, &w->jp_counters, &w->jp_hist, &w->perm0, &w->perm1,
-                            &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour};
+                            &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour, &w->isl_parent, &w->isl_flags, &w->isl_count, &w->sl_ticks, &w->sl_valid,
+                            &w->isl_counters};
     for (auto* b : u1) b->release();
     DBuf<int>* i1[] = {&w->rope_next, &w->rope_prev, &w->rp_body, &w->rp_rope};
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -419,6 +427,7 @@ int sfg_world_clear(SfgWorld* w) {   // physics.rs:386-393
     if (!w) return SFG_E_INVALID;
     w->n_bodies = w->n_colls = w->n_constraints = w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0;
     w->n_units = w->n_kunits = 0;
+    w->ct_n = 0; w->islands_valid = false;
     w->ticked = false;
     memset(&w->stats, 0, sizeof(w->stats));
     return SFG_OK;
@@ -456,6 +465,10 @@ int sfg_set_bodies(SfgWorld* w, uint32_t n, const SfgBody* b) {
     CK(w->P.ensure(n)); CK(w->Q.ensure(n)); CK(w->V.ensure(n)); CK(w->OV.ensure(n)); CK(w->MI.ensure(n)); CK(w->EA.ensure(n));
     if (n != w->n_bodies) { w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0; w->n_constraints = 0; }   // slot space changed: re-upload ropes / constraints
     w->n_bodies = n;
+    // a full upload starts a new world as far as sleeping is concerned: no island is being watched, no contact retained
+    CK(w->sl_valid.ensure(n + 1)); CK(w->sl_ticks.ensure(n + 1)); CK(w->sl_sum.ensure(n + 1));
+    CK(cudaMemsetAsync(w->sl_valid.p, 0, size_t(n + 1) * 4, w->stream));
+    w->ct_n = 0; w->islands_valid = false;
     return upload_bodies(w, 0, n, b);
 }
 int sfg_update_bodies(SfgWorld* w, uint32_t first, uint32_t count, const SfgBody* b) {
@@ -761,6 +774,65 @@ void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
         }
 }
 
+bool sleeping_enabled(const SfgWorld* w) {
+    return !(w->tuning.flags & SFG_TUNE_NO_SLEEPING) && w->tuning.fall_asleep_frames != 0xFFFFFFFFu;
+}
+void fill_island_ctx(SfgWorld* w, IslandCtx& c) {
+    memset(&c, 0, sizeof(c));
+    c.n_bodies = w->n_bodies; c.n_units = w->n_units; c.n_constraints = w->n_constraints; c.n_links = w->n_rope_units;
+    c.U_ids = w->U_ids.p; c.CI = w->CI.p; c.KI = w->KI.p; c.RU = w->RU.p; c.MI = w->MI.p; c.V = w->V.p;
+    c.parent = w->isl_parent.p; c.isl_sum = w->isl_sum.p; c.isl_flags = w->isl_flags.p; c.isl_count = w->isl_count.p;
+    c.sl_sum = w->sl_sum.p; c.sl_ticks = w->sl_ticks.p; c.sl_valid = w->sl_valid.p; c.counters = w->isl_counters.p;
+    c.sleep_vel_threshold = w->tuning.sleep_vel_threshold; c.fall_asleep_frames = w->tuning.fall_asleep_frames;
+}
+// physics.rs:598-741: islands of the constraint graph, then which of them stay asleep this tick
+int island_pass(SfgWorld* w) {
+    cudaStream_t st = w->stream;
+    const uint32_t nb = w->n_bodies;
+    if (nb == 0) return SFG_OK;
+    CK(w->isl_parent.ensure(nb + 1)); CK(w->isl_flags.ensure(nb + 1)); CK(w->isl_count.ensure(nb + 1)); CK(w->isl_sum.ensure(nb + 1));
+    CK(w->isl_counters.ensure(8));
+    IslandCtx c;
+    fill_island_ctx(w, c);
+    const uint32_t n_edges = c.n_units + c.n_constraints + c.n_links;
+    k_isl_init<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
+    if (n_edges) {
+        k_isl_union<<<nblk(n_edges), 256, 0, st>>>(c); CKL(w); w->launches++;
+        k_isl_sums<<<nblk(n_edges), 256, 0, st>>>(c); CKL(w); w->launches++;
+    }
+    k_isl_bodies_pre<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
+    k_isl_decide<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
+    k_isl_mark<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
+    return SFG_OK;
+}
+// physics.rs:1097-1144: publish contacts (keeping those of sleeping islands), then watch slow islands
+int island_post(SfgWorld* w) {
+    cudaStream_t st = w->stream;
+    const uint32_t nb = w->n_bodies;
+    if (nb == 0) return SFG_OK;
+    IslandCtx c;
+    fill_island_ctx(w, c);
+    const uint32_t n_entries = w->n_units * 2;
+    DBuf<ContactRec>& old_list = w->ct[w->ct_cur];
+    DBuf<ContactRec>& new_list = w->ct[w->ct_cur ^ 1];
+    CK(new_list.ensure(size_t(w->ct_n) + n_entries + 1));
+    uint32_t* cursor = w->isl_counters.p + 4;
+    CK(cudaMemsetAsync(cursor, 0, 4, st));
+    if (w->ct_n) {
+        k_contacts_retain<<<nblk(w->ct_n), 256, 0, st>>>(w->ct_n, old_list.p, w->sl_sum.p, w->sl_ticks.p, w->sl_valid.p, nb, w->tuning.fall_asleep_frames,
+                                                        new_list.p, cursor);
+        CKL(w); w->launches++;
+    }
+    if (n_entries) {
+        k_contacts_append<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->LN.p, w->H.p, w->S.p, w->isl_parent.p, w->isl_sum.p, new_list.p, cursor);
+        CKL(w); w->launches++;
+    }
+    k_isl_bodies_post<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
+    k_isl_fall_asleep<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
+    w->ct_cur ^= 1;
+    return SFG_OK;
+}
+
 void build_stage_table(SfgWorld* w) {
     auto& s = w->h_stages;
     s.clear();
@@ -806,6 +878,8 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
     rc = broadphase(w, float(frame_dt));
     if (rc != SFG_OK) return rc;
     CK(cudaEventRecord(w->ev[1], st));
+    const bool sleeping = sleeping_enabled(w);
+    if (sleeping) { rc = island_pass(w); if (rc != SFG_OK) return rc; }
     rc = build_graph(w);
     if (rc != SFG_OK) return rc;
     CK(cudaEventRecord(w->ev[2], st));
@@ -859,7 +933,13 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
         }
     }
     CK(cudaEventRecord(w->ev[3], st));
+    if (sleeping) { rc = island_post(w); if (rc != SFG_OK) return rc; }
+    uint32_t isl_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (sleeping && w->n_bodies) CK(cudaMemcpyAsync(isl_counts, w->isl_counters.p, sizeof(isl_counts), cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(w->ev[4], st));
     CK(cudaStreamSynchronize(st));
+    w->islands_valid = sleeping;
+    if (sleeping) w->ct_n = isl_counts[4];
     w->ticked = true;
     w->last_substeps = substeps;
     // stats
@@ -871,10 +951,11 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
     s.n_rope_particles = w->n_particles; s.n_ropes = w->n_ropes; s.substeps = substeps;
     s.grid_levels = uint32_t(w->grid.n_levels); s.grid_cells = w->grid.n_cells; s.cell_size = w->grid.cell[0];
     s.kernel_launches = w->launches;
+    s.n_islands = isl_counts[0]; s.n_sleeping_bodies = isl_counts[1]; s.n_contacts = sleeping ? isl_counts[4] : 0u;
     cudaEventElapsedTime(&s.ms_broadphase, w->ev[0], w->ev[1]);
     cudaEventElapsedTime(&s.ms_graph, w->ev[1], w->ev[2]);
     cudaEventElapsedTime(&s.ms_solver, w->ev[2], w->ev[3]);
-    cudaEventElapsedTime(&s.ms_total, w->ev[0], w->ev[3]);
+    cudaEventElapsedTime(&s.ms_total, w->ev[0], w->ev[4]);
     s.reserved[0] = uint32_t(w->h_stages.size());
     s.reserved[1] = w->stats_jp_rounds;
     return SFG_OK;
@@ -930,9 +1011,22 @@ int sfg_get_poses(SfgWorld* w, uint32_t first, uint32_t count, float* poses) {
 int sfg_get_contacts(SfgWorld* w, SfgContactInfo* out, size_t capacity, size_t* n_out) {
     if (!w || !n_out) return SFG_E_INVALID;
     *n_out = 0;
-    if (!w->ticked || w->n_units == 0) return SFG_OK;
+    if (!w->ticked) return SFG_OK;
     cudaSetDevice(w->device);
     cudaStream_t st = w->stream;
+    if (w->islands_valid) {   // the tick already published the list (with the contacts of sleeping islands retained)
+        *n_out = w->ct_n;
+        const uint32_t got = uint32_t(std::min<size_t>(capacity, w->ct_n));
+        if (!got || !out) return SFG_OK;
+        static_assert(sizeof(SfgContactInfo) == 16, "SfgContactInfo is 4 words");
+        CK(w->stage.ensure(size_t(got) * sizeof(SfgContactInfo)));
+        k_contacts_export<<<nblk(got), 256, 0, st>>>(got, w->ct[w->ct_cur].p, (uint32_t*)w->stage.p);
+        CKL(w);
+        CK(cudaMemcpyAsync(out, w->stage.p, size_t(got) * sizeof(SfgContactInfo), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return SFG_OK;
+    }
+    if (w->n_units == 0) return SFG_OK;
     const uint32_t n_entries = w->n_units * 2;
     const uint32_t cap = uint32_t(std::min<size_t>(capacity, n_entries));
     CK(w->stage.ensure(size_t(cap) * sizeof(SfgContactInfo) + 16));
@@ -1063,6 +1157,40 @@ int sfg_debug_get_manifolds(SfgWorld* w, float* out, size_t capacity_entries, si
     CKL(w);
     CK(cudaMemcpyAsync(out, w->stage.p, size_t(n_entries) * 14 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+// islands of the last tick: first_body (= smallest slot), edge_sum, body count, flags (1 cannot sleep, 2 moved since the last
+// tick, 4 fast after the solve, 8 asleep = skipped this tick)
+int sfg_debug_get_islands(SfgWorld* w, uint32_t* first_body, uint64_t* edge_sum, uint32_t* body_count, uint32_t* flags, size_t capacity,
+                          size_t* n_out) {
+    if (!w || !n_out) return SFG_E_INVALID;
+    *n_out = 0;
+    if (!w->islands_valid || w->n_bodies == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    const uint32_t cap = uint32_t(std::min<size_t>(capacity, w->n_bodies));
+    const size_t bytes = 16 + size_t(cap) * (4 + 8 + 4 + 4) + 64;
+    CK(w->stage.ensure(bytes));
+    uint32_t* cursor = (uint32_t*)w->stage.p;
+    unsigned long long* d_sum = (unsigned long long*)(w->stage.p + 16);
+    uint32_t* d_first = (uint32_t*)(d_sum + cap); uint32_t* d_cnt = d_first + cap; uint32_t* d_fl = d_cnt + cap;
+    CK(cudaMemsetAsync(cursor, 0, 4, st));
+    IslandCtx c;
+    fill_island_ctx(w, c);
+    k_isl_export<<<nblk(w->n_bodies), 256, 0, st>>>(c, cap, cursor, d_first, d_sum, d_cnt, d_fl);
+    CKL(w);
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, cursor, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = total;
+    const uint32_t got = std::min(total, cap);
+    if (got && first_body && edge_sum && body_count && flags) {
+        CK(cudaMemcpyAsync(first_body, d_first, size_t(got) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(edge_sum, d_sum, size_t(got) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(body_count, d_cnt, size_t(got) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(flags, d_fl, size_t(got) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     return SFG_OK;
 }
 int sfg_debug_get_aabbs(SfgWorld* w, float* out, size_t capacity_colliders) {

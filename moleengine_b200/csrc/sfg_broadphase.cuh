@@ -424,11 +424,15 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
     if ((f0 & f1) & CF_HAS_SF) fl |= UF_HAS_SF;
     if ((f0 & f1) & CF_HAS_DF) fl |= UF_HAS_DF;
     if (c0.x >= 0) {
-        if (__float_as_uint(MI[c0.x].z) & (BF_MASS | BF_INERTIA)) fl |= UF_SEES0;
+        const uint32_t bf = __float_as_uint(MI[c0.x].z);
+        if (bf & (BF_MASS | BF_INERTIA)) fl |= UF_SEES0;
+        if (bf & BF_ASLEEP) fl |= UF_ASLEEP;
         if (rope_next && rope_next[c0.x] >= 0 && rope_prev[c0.x] >= 0) fl |= UF_ROPE0;
     }
     if (c1.x >= 0) {
-        if (__float_as_uint(MI[c1.x].z) & (BF_MASS | BF_INERTIA)) fl |= UF_SEES1;
+        const uint32_t bf = __float_as_uint(MI[c1.x].z);
+        if (bf & (BF_MASS | BF_INERTIA)) fl |= UF_SEES1;
+        if (bf & BF_ASLEEP) fl |= UF_ASLEEP;
         if (rope_next && rope_next[c1.x] >= 0 && rope_prev[c1.x] >= 0) fl |= UF_ROPE1;
     }
     H[s] = make_float4(__int_as_float(c0.x), __int_as_float(c1.x), __uint_as_float(fl), (m0.x + m1.x) / 2.0f);

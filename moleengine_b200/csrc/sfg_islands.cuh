@@ -1,0 +1,213 @@
+// Islands and sleeping on the device (once per tick, between the broadphase and the colouring).
+//
+// Reference: /root/reference/src/physics.rs:598-741 (recursive DFS islands + sleeping filter), :1097-1144 (contact
+// retention, fall asleep), :178-202 (IslandId / SleepingIsland). The DFS is replaced by a lock-free union-find whose
+// roots are the smallest body slot of each component, which is exactly IslandId::first_body (DFS roots are taken in
+// ascending slot order, :674-677). IslandId::edge_sum is a wrapping sum over directed graph edges,
+//      two-body edge (rope link, two-body constraint, body-body pair) seen from body a:  (a + 1) * (b + 1)
+//      one-body edge (body-world constraint, body-static pair):                           (a + 1)
+// (:634, :651, :662, :669) and does not depend on the visit order, so atomics reproduce it bit for bit; every two-body
+// edge is stored on both endpoints (:519-532, :556-569) and therefore counted twice.
+//
+// Sleeping records live in a table indexed by first_body: the reference keeps at most one record per IslandId and drops
+// every record that no island matched in the current tick (:739), so two records can never share a first_body.
+#pragma once
+#include "sfg_state.cuh"
+
+namespace sfg {
+
+enum : uint32_t { IF_NO_SLEEP = 1u, IF_MOVING = 2u, IF_FAST = 4u, IF_ASLEEP = 8u, IF_ROOT = 16u };
+
+struct IslandCtx {
+    uint32_t n_bodies, n_units, n_constraints, n_links;
+    const uint2* U_ids;           // candidate pairs (collider slots)
+    const int4* CI;               // collider -> body
+    const int4* KI;               // constraints (owner, target, flags, -)
+    const int4* RU;               // rope links (curr, next, after, rope)
+    float4* MI;
+    const float4* V;
+    uint32_t* parent;             // union-find forest, then the island root (= first_body) of every body
+    unsigned long long* isl_sum;  // per root: edge_sum
+    uint32_t* isl_flags;          // per root: IF_*
+    uint32_t* isl_count;          // per root: bodies
+    unsigned long long* sl_sum;   // sleeping record at first_body
+    uint32_t* sl_ticks;
+    uint32_t* sl_valid;
+    uint32_t* counters;           // [0] islands, [1] sleeping bodies, [2] asleep islands
+    float sleep_vel_threshold;
+    uint32_t fall_asleep_frames;
+};
+
+__device__ __forceinline__ uint32_t uf_find(const uint32_t* parent, uint32_t x) {
+    uint32_t p;
+    while ((p = __ldcg(parent + x)) != x) x = p;
+    return x;
+}
+// hook the larger root under the smaller one: the final root of a component is its smallest slot
+__device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
+    uint32_t ra = uf_find(parent, a), rb = uf_find(parent, b);
+    while (ra != rb) {
+        if (ra < rb) { const uint32_t t = ra; ra = rb; rb = t; }
+        const uint32_t old = atomicCAS(parent + ra, ra, rb);
+        if (old == ra) return;
+        ra = uf_find(parent, old);
+        rb = uf_find(parent, rb);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_isl_init(IslandCtx c) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    c.parent[b] = b; c.isl_sum[b] = 0ull; c.isl_flags[b] = 0u; c.isl_count[b] = 0u;
+    float4 m = c.MI[b];
+    const uint32_t fl = __float_as_uint(m.z);
+    if (fl & BF_ASLEEP) { m.z = __uint_as_float(fl & ~BF_ASLEEP); c.MI[b] = m; }
+    if (b < 4) c.counters[b] = 0u;
+}
+
+// edge index space: [0, n_units) pairs, then constraints, then rope links
+__device__ __forceinline__ bool isl_edge(const IslandCtx& c, uint32_t i, int* a, int* b, uint32_t* no_sleep) {
+    *no_sleep = 0u;
+    if (i < c.n_units) {
+        const uint2 id = c.U_ids[i];
+        *a = c.CI[id.x].x; *b = c.CI[id.y].x;
+        return true;
+    }
+    i -= c.n_units;
+    if (i < c.n_constraints) {
+        const int4 k = c.KI[i];
+        *a = k.x; *b = k.y;
+        if (!(uint32_t(k.z) & 4u)) *no_sleep = 1u;      // SFG_CONSTRAINT_CAN_SLEEP
+        return true;
+    }
+    i -= c.n_constraints;
+    if (i < c.n_links) {
+        const int4 r = c.RU[i];
+        *a = r.x; *b = r.y;
+        *no_sleep = 1u;                                   // physics.rs:620
+        return true;
+    }
+    return false;
+}
+__global__ void __launch_bounds__(256) k_isl_union(IslandCtx c) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    int a, b; uint32_t ns;
+    if (!isl_edge(c, i, &a, &b, &ns)) return;
+    if (a >= 0 && b >= 0 && a != b) uf_union(c.parent, uint32_t(a), uint32_t(b));
+}
+__global__ void __launch_bounds__(256) k_isl_sums(IslandCtx c) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    int a, b; uint32_t ns;
+    if (!isl_edge(c, i, &a, &b, &ns)) return;
+    if (a < 0 && b < 0) return;
+    const uint32_t root = uf_find(c.parent, uint32_t(a >= 0 ? a : b));
+    unsigned long long add;
+    if (a >= 0 && b >= 0) add = 2ull * ((unsigned long long)(a) + 1ull) * ((unsigned long long)(b) + 1ull);
+    else add = (unsigned long long)(a >= 0 ? a : b) + 1ull;
+    atomicAdd(c.isl_sum + root, add);
+    if (ns) atomicOr(c.isl_flags + root, IF_NO_SLEEP);
+}
+// per body: final label, island size, "moved between frames" test on the incoming velocities (physics.rs:722-731)
+__global__ void __launch_bounds__(256) k_isl_bodies_pre(IslandCtx c) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE)) { c.sl_valid[b] = 0u; return; }
+    const uint32_t root = uf_find(c.parent, b);
+    c.parent[b] = root;
+    atomicAdd(c.isl_count + root, 1u);
+    const float4 v = c.V[b];
+    if (v.x * v.x + v.y * v.y + v.z * v.z >= c.sleep_vel_threshold) atomicOr(c.isl_flags + root, IF_MOVING);
+    if (root != b) c.sl_valid[b] = 0u;     // a record is only ever found through the island whose first_body it names
+}
+// per island root: the retain() of physics.rs:714-737 and the record clean-up of :739
+__global__ void __launch_bounds__(256) k_isl_decide(IslandCtx c) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE) || c.parent[b] != b) return;
+    uint32_t fl = c.isl_flags[b] | IF_ROOT;
+    const bool match = c.sl_valid[b] && c.sl_sum[b] == c.isl_sum[b];
+    bool continues = false, keep = true;
+    if (match && !(fl & IF_MOVING)) { continues = true; keep = c.sl_ticks[b] < c.fall_asleep_frames; }
+    if (!continues) c.sl_valid[b] = 0u;
+    if (!keep) { fl |= IF_ASLEEP; atomicAdd(c.counters + 2, 1u); }
+    c.isl_flags[b] = fl;
+    atomicAdd(c.counters + 0, 1u);
+}
+__global__ void __launch_bounds__(256) k_isl_mark(IslandCtx c) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    float4 m = c.MI[b];
+    const uint32_t fl = __float_as_uint(m.z);
+    if (!(fl & BF_ALIVE)) return;
+    if (c.isl_flags[c.parent[b]] & IF_ASLEEP) {
+        m.z = __uint_as_float(fl | BF_ASLEEP);
+        c.MI[b] = m;
+        atomicAdd(c.counters + 1, 1u);
+    }
+}
+// after the solve: physics.rs:1128-1144
+__global__ void __launch_bounds__(256) k_isl_bodies_post(IslandCtx c) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    const uint32_t fl = __float_as_uint(c.MI[b].z);
+    if (!(fl & BF_ALIVE) || (fl & BF_ASLEEP)) return;
+    const float4 v = c.V[b];
+    if (!(v.x * v.x + v.y * v.y + v.z * v.z < c.sleep_vel_threshold)) atomicOr(c.isl_flags + c.parent[b], IF_FAST);
+}
+__global__ void __launch_bounds__(256) k_isl_fall_asleep(IslandCtx c) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE) || c.parent[b] != b) return;
+    const uint32_t fl = c.isl_flags[b];
+    if (fl & (IF_ASLEEP | IF_NO_SLEEP | IF_FAST)) return;
+    if (c.sl_valid[b] && c.sl_sum[b] == c.isl_sum[b]) c.sl_ticks[b] += 1u;
+    else { c.sl_valid[b] = 1u; c.sl_sum[b] = c.isl_sum[b]; c.sl_ticks[b] = 0u; }
+}
+
+// ---- contact list with retention (physics.rs:1097-1122) ----
+struct ContactRec { uint32_t c0, c1; float nx, ny; uint32_t root, pad; unsigned long long sum; };
+
+// keep last tick's contacts of islands that are asleep now (record found and slept long enough)
+__global__ void __launch_bounds__(256) k_contacts_retain(uint32_t n_old, const ContactRec* __restrict__ old_list, const unsigned long long* sl_sum,
+                                                         const uint32_t* sl_ticks, const uint32_t* sl_valid, uint32_t n_bodies,
+                                                         uint32_t fall_asleep_frames, ContactRec* __restrict__ out, uint32_t* cursor) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_old) return;
+    const ContactRec r = old_list[i];
+    if (r.root >= n_bodies) return;
+    if (sl_valid[r.root] && sl_sum[r.root] == r.sum && sl_ticks[r.root] >= fall_asleep_frames) out[atomicAdd(cursor, 1u)] = r;
+}
+// this tick's latched contacts (solver.rs:318-320), tagged with the island they belong to
+__global__ void __launch_bounds__(256) k_contacts_append(uint32_t n_entries, uint32_t n_units, const float2* __restrict__ LN,
+                                                         const float4* __restrict__ H, const float4* __restrict__ S,
+                                                         const uint32_t* __restrict__ parent, const unsigned long long* __restrict__ isl_sum,
+                                                         ContactRec* __restrict__ out, uint32_t* cursor) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    const float2 n = LN[e];
+    if (isnan(n.x) && isnan(n.y)) return;
+    const float4 h = H[e % n_units], s = S[e % n_units];
+    const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
+    ContactRec r;
+    r.c0 = __float_as_uint(s.x); r.c1 = __float_as_uint(s.y); r.nx = n.x; r.ny = n.y; r.pad = 0u;
+    r.root = parent[b0 >= 0 ? b0 : b1];
+    r.sum = isl_sum[r.root];
+    out[atomicAdd(cursor, 1u)] = r;
+}
+__global__ void __launch_bounds__(256) k_contacts_export(uint32_t n, const ContactRec* __restrict__ list, uint32_t* __restrict__ out4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ContactRec r = list[i];
+    out4[4 * i + 0] = r.c0; out4[4 * i + 1] = r.c1; out4[4 * i + 2] = __float_as_uint(r.nx); out4[4 * i + 3] = __float_as_uint(r.ny);
+}
+__global__ void __launch_bounds__(256) k_isl_export(IslandCtx c, uint32_t cap, uint32_t* cursor, uint32_t* first_body, unsigned long long* sums,
+                                                    uint32_t* counts, uint32_t* flags) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE) || c.parent[b] != b) return;
+    const uint32_t pos = atomicAdd(cursor, 1u);
+    if (pos >= cap) return;
+    first_body[pos] = b; sums[pos] = c.isl_sum[b]; counts[pos] = c.isl_count[b]; flags[pos] = c.isl_flags[b];
+}
+
+}  // namespace sfg

@@ -36,7 +36,7 @@ SFG_DI V2 force_at(const ForceParams& ff, V2 pos) {
 SFG_DI void stage_integrate(const SolverCtx& c, uint32_t i) {
     float4 mi = ldb(c.MI + i);
     const uint32_t fl = __float_as_uint(mi.z);
-    if (!(fl & BF_ALIVE)) return;
+    if ((fl & (BF_ALIVE | BF_ASLEEP)) != BF_ALIVE) return;   // sleeping islands are skipped entirely (physics.rs:798-803)
     float4 p = ldb(c.P + i), q = ldb(c.Q + i), v = ldb(c.V + i);
     V2 pos = mk(p.x + p.z, p.y + p.w);
     if (!(fl & BF_NOGRAV) && (fl & BF_MASS)) {
@@ -54,7 +54,7 @@ SFG_DI void stage_integrate(const SolverCtx& c, uint32_t i) {
 // solver.rs:91-97 (+ fold of the displacement into the position after the last substep)
 SFG_DI void stage_derive(const SolverCtx& c, uint32_t i, bool fold) {
     float4 mi = ldb(c.MI + i);
-    if (!(__float_as_uint(mi.z) & BF_ALIVE)) return;
+    if ((__float_as_uint(mi.z) & (BF_ALIVE | BF_ASLEEP)) != BF_ALIVE) return;
     float4 p = ldb(c.P + i), q = ldb(c.Q + i), v = ldb(c.V + i);
     v.x = p.z * c.inv_dt; v.y = p.w * c.inv_dt;
     Rot d = mkrot(q.x, q.y) * mkrot(q.z, -q.w);
@@ -159,6 +159,7 @@ SFG_DI void stage_constraints(const SolverCtx& c, uint32_t u) {
     const int mult = target >= 0 ? 2 : 1;
     float4 P0 = ldb(c.P + owner), Q0 = ldb(c.Q + owner);
     float4 mi0 = ldb(c.MI + owner);
+    if (__float_as_uint(mi0.z) & BF_ASLEEP) return;
     float4 P1 = make_float4(0, 0, 0, 0), Q1 = make_float4(1, 0, 1, 0), mi1 = make_float4(0, 0, 0, 0);
     if (target >= 0) { P1 = ldb(c.P + target); Q1 = ldb(c.Q + target); mi1 = ldb(c.MI + target); }
     Rot r0 = mkrot(Q0.x, Q0.y), r1 = mkrot(Q1.x, Q1.y);
@@ -190,6 +191,7 @@ SFG_DI void stage_constraint_damp(const SolverCtx& c, uint32_t u) {
     const int owner = __float_as_int(k0.x), target = __float_as_int(k0.y);
     const int mult = target >= 0 ? 2 : 1;
     float4 Q0 = ldb(c.Q + owner), V0 = ldb(c.V + owner), mi0 = ldb(c.MI + owner);
+    if (__float_as_uint(mi0.z) & BF_ASLEEP) return;
     float4 Q1 = make_float4(1, 0, 1, 0), V1 = make_float4(0, 0, 0, 0), mi1 = make_float4(0, 0, 0, 0);
     if (target >= 0) { Q1 = ldb(c.Q + target); V1 = ldb(c.V + target); mi1 = ldb(c.MI + target); }
     const V2 or0 = mkrot(Q0.x, Q0.y) * mk(k2.x, k2.y);
@@ -238,6 +240,7 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
     const float4 h = ldc(c.H + u);
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     const uint32_t fl = __float_as_uint(h.z);
+    if (fl & UF_ASLEEP) return;
     const float mu_s = h.w;
     // First reject, on body positions alone (one gather per body, nothing else of the unit is touched): colliders sit
     // within |local offset| of their body, so bodies farther apart than RC = bounding radii + offsets (+ margin, and never

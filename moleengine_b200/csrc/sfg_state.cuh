@@ -56,10 +56,10 @@ struct Bounds {                   // filled by k_aabb with ordered-int atomics
 // unit flags
 enum : uint32_t {
     UF_MULT2 = 1u, UF_SENSOR = 2u, UF_HAS_SF = 4u, UF_HAS_DF = 8u, UF_SEES0 = 16u, UF_SEES1 = 32u,
-    UF_ROPE0 = 64u, UF_ROPE1 = 128u,
+    UF_ROPE0 = 64u, UF_ROPE1 = 128u, UF_ASLEEP = 256u,
 };
 // body flag bits kept in MI.z (same values as SFG_BODY_*)
-enum : uint32_t { BF_ALIVE = 1u, BF_NOGRAV = 2u, BF_MASS = 4u, BF_INERTIA = 8u };
+enum : uint32_t { BF_ALIVE = 1u, BF_NOGRAV = 2u, BF_MASS = 4u, BF_INERTIA = 8u, BF_ASLEEP = 16u /* set per tick by the island pass */ };
 // collider flag bits kept in CM.w / CI.w (same values as SFG_COLL_*)
 enum : uint32_t { CF_ALIVE = 1u, CF_SENSOR = 2u, CF_HAS_SF = 4u, CF_HAS_DF = 8u };
 

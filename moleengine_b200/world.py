@@ -167,6 +167,15 @@ class GpuWorld:
             self._ck(self.lib.sfg_debug_get_manifolds(self.h, abi.ptr(out), n.value, C.byref(n)))
         return out
 
+    def debug_islands(self):
+        """Islands of the last tick: first_body, edge_sum, body_count, flags (1 cannot sleep, 2 moved, 4 fast, 8 asleep)."""
+        n = C.c_size_t()
+        self._ck(self.lib.sfg_debug_get_islands(self.h, None, None, None, None, 0, C.byref(n)))
+        fb, es, bc, fl = np.zeros(n.value, np.uint32), np.zeros(n.value, np.uint64), np.zeros(n.value, np.uint32), np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self.lib.sfg_debug_get_islands(self.h, abi.ptr(fb), abi.ptr(es), abi.ptr(bc), abi.ptr(fl), n.value, C.byref(n)))
+        return fb, es, bc, fl
+
     def debug_aabbs(self, n_colliders):
         out = np.zeros((n_colliders, 4), np.float32)
         self._ck(self.lib.sfg_debug_get_aabbs(self.h, abi.ptr(out), n_colliders))

@@ -29,7 +29,7 @@ def load():
         lib.sfo_create.restype = C.c_void_p
         lib.sfo_create.argtypes = [C.c_int]
         lib.sfo_n_pairs.restype = lib.sfo_n_pair_units.restype = lib.sfo_n_constraint_units.restype = C.c_size_t
-        lib.sfo_n_entries.restype = lib.sfo_n_contacts.restype = C.c_size_t
+        lib.sfo_n_entries.restype = lib.sfo_n_contacts.restype = lib.sfo_n_islands.restype = C.c_size_t
         lib.sfo_query_point.restype = C.c_uint32
         vp = C.c_void_p
         for name, args in {
@@ -43,7 +43,7 @@ def load():
             "sfo_get_constraint_units": [vp, vp, vp, vp], "sfo_n_entries": [vp], "sfo_get_manifolds": [vp, vp],
             "sfo_n_contacts": [vp], "sfo_get_contacts": [vp, vp, vp], "sfo_get_aabbs": [vp, vp],
             "sfo_cast_batch": [vp, C.c_uint32, vp, vp, C.c_int],
-            "sfo_query_point": [vp, C.c_double, C.c_double, C.c_uint32, vp, C.c_uint32], "sfo_get_stats": [vp, vp],
+            "sfo_query_point": [vp, C.c_double, C.c_double, C.c_uint32, vp, C.c_uint32], "sfo_get_stats": [vp, vp], "sfo_n_islands": [vp], "sfo_get_islands": [vp, vp, vp, vp, vp],
             "sfo_intersection_check": [C.c_int, C.c_uint32, vp, vp, vp],
             "sfo_spherecast_collider": [C.c_int, C.c_uint32, vp, vp, vp, vp],
             "sfo_geometry": [C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp], "sfo_clip_edge": [vp, vp, vp],
@@ -162,6 +162,14 @@ class OracleWorld:
         out = np.zeros(cap, np.int32)
         n = self.lib.sfo_query_point(self.h, x, y, domain, _p(out), cap)
         return out[: min(n, cap)]
+
+    def islands(self):
+        """Every island of the last MODE_REFERENCE tick: first_body, edge_sum, body_count, flags (1 cannot sleep, 8 asleep)."""
+        n = self.lib.sfo_n_islands(self.h)
+        a = [np.zeros(n, np.uint64) for _ in range(4)]
+        if n:
+            self.lib.sfo_get_islands(self.h, *[_p(x) for x in a])
+        return a
 
     def stats(self):
         out = np.zeros(8, np.uint64)

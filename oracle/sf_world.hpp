@@ -104,6 +104,8 @@ struct IWorld {
     virtual void cast_batch(uint32_t n, const SfgRay* rays, double* out6, int use_bvh) const = 0;
     virtual uint32_t query_point(double x, double y, uint32_t domain, int32_t* out, uint32_t cap) const = 0;
     virtual void get_stats(uint64_t* out8) const = 0;
+    virtual size_t n_all_islands() const = 0;
+    virtual void get_all_islands(uint64_t* first_body, uint64_t* edge_sum, uint64_t* body_count, uint64_t* flags) const = 0;
 };
 
 template <class R>
@@ -230,6 +232,8 @@ public:
     std::vector<uint32_t> e_constr;                  // constraint index per constraint entry
     std::vector<uint32_t> e_bodies, e_ropes;         // island-ordered body slots / rope indices
     std::vector<Island> islands;
+    struct IslandRec { uint64_t first_body, edge_sum, body_count, flags; };   // every island of the last tick; flags: 1 cannot sleep, 8 asleep
+    std::vector<IslandRec> all_islands;
     std::vector<Sleeping> sleeping;
     std::vector<ContactInfoS<R>> contact_infos;
     std::vector<PairUnit> pair_units;
@@ -461,6 +465,7 @@ public:
         // sleeping filter (physics.rs:711-741)
         const bool sleeping_on = !(tuning.flags & SFG_TUNE_NO_SLEEPING) && tuning.fall_asleep_frames != UINT32_MAX;
         for (auto& s : sleeping) s.continues = false;
+        all_islands.clear();
         std::vector<Island> kept;
         for (auto& is : isl) {
             bool keep = true;
@@ -476,6 +481,7 @@ public:
                         break;
                     }
             if (keep) kept.push_back(is);
+            all_islands.push_back({is.first_body, is.edge_sum, is.body_count, uint64_t(is.can_sleep ? 0 : 1) | uint64_t(keep ? 0 : 8)});
         }
         sleeping.erase(std::remove_if(sleeping.begin(), sleeping.end(), [](const Sleeping& s) { return !s.continues; }), sleeping.end());
         std::stable_sort(kept.begin(), kept.end(), [](const Island& a, const Island& b) { return a.body_count > b.body_count; });
@@ -1070,6 +1076,13 @@ public:
     }
     void get_aabbs(double* o) const override {
         for (size_t i = 0; i < aabbs.size(); ++i) { o[4 * i] = aabbs[i].min.x; o[4 * i + 1] = aabbs[i].min.y; o[4 * i + 2] = aabbs[i].max.x; o[4 * i + 3] = aabbs[i].max.y; }
+    }
+    size_t n_all_islands() const override { return all_islands.size(); }
+    void get_all_islands(uint64_t* first_body, uint64_t* edge_sum, uint64_t* body_count, uint64_t* flags) const override {
+        for (size_t i = 0; i < all_islands.size(); ++i) {
+            first_body[i] = all_islands[i].first_body; edge_sum[i] = all_islands[i].edge_sum;
+            body_count[i] = all_islands[i].body_count; flags[i] = all_islands[i].flags;
+        }
     }
     void get_stats(uint64_t* o) const override {
         o[0] = kept_pairs.size() / 2; o[1] = e_pair.size(); o[2] = e_constr.size(); o[3] = stat_colours_pairs;
