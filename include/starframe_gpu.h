@@ -62,6 +62,8 @@ typedef struct SfgBody {
 #define SFG_BODY_IGNORES_GRAVITY 2u
 #define SFG_BODY_MASS_FINITE 4u
 #define SFG_BODY_INERTIA_FINITE 8u
+#define SFG_BODY_INACTIVE 64u        /* output only: in a slab-decomposed world, outside this rank's slab and halo (stale copy) */
+#define SFG_BODY_GHOST 32u           /* output only: in a slab-decomposed world, a halo copy owned by a neighbouring slab */
 #define SFG_BODY_ASLEEP 16u          /* output only (sfg_get_bodies): the body's island was skipped in the last tick (physics.rs:711-741) */
 
 /* collider.rs:19-29 Collider, :197-200 ColliderShape, :378-410 ColliderPolygon, :903-911 material */
@@ -184,6 +186,24 @@ int sfg_set_ropes(SfgWorld* w, uint32_t n_ropes, const SfgRope* ropes, uint32_t 
 
 /* ---- PhysicsWorld::tick (physics.rs:396-1158) ---- */
 int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff);
+/* The same tick in three calls, for callers that must act between substeps (slab halo exchange):
+ * begin = boxes, pairs, islands, colouring; substeps(count) = the next `count` XPBD substeps; end = contacts, sleeping, stats. */
+int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff);
+int sfg_tick_substeps(SfgWorld* w, uint32_t count);
+int sfg_tick_end(SfgWorld* w);
+
+/* ---- one large world cut into x-slabs, one per GPU (north_star: "spatial slabs, boundary-body halo exchange over NVLink").
+ * Every rank uploads the WHOLE world (same slots everywhere) and then owns the bodies whose x lies in [x_lo, x_hi); bodies
+ * outside the slab and its halo sit the tick out on this rank. Per tick the caller runs
+ *   sfg_slab_begin; pack(mode 0, side) -> send to that neighbour / receive -> unpack      (refresh: who is near the cut)
+ *   sfg_tick_begin; then per substep: sfg_tick_substeps(1); pack(mode 1) -> exchange -> unpack (not after the last); sfg_tick_end
+ * The buffers are DEVICE memory owned by the caller ((capacity_records + 1) * 64 bytes; record 0 is a header carrying the
+ * count), so the transport (NCCL send/recv, peer copies) stays outside the library. side 0 = towards lower x, 1 = higher x.
+ * A slab world never sleeps (islands across a cut are not tracked). x_hi <= x_lo switches slab mode off. */
+int sfg_slab_configure(SfgWorld* w, float x_lo, float x_hi, float halo);
+int sfg_slab_begin(SfgWorld* w);
+int sfg_slab_pack(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records, uint32_t* count_out);
+int sfg_slab_unpack(SfgWorld* w, const void* device_in, uint32_t capacity_records);
 
 /* ---- results: bodies written back (physics.rs:1150-1157), contacts (:1097-1122, :1165) ---- */
 int sfg_get_bodies(SfgWorld* w, uint32_t first_slot, uint32_t count, SfgBody* out);

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libstarframe_gpu.so")
 SFG_OK, SFG_E_INVALID, SFG_E_CUDA, SFG_E_CAPACITY, SFG_E_NO_DEVICE, SFG_E_STATE = 0, 1, 2, 3, 4, 5
 
 BODY_ALIVE, BODY_IGNORES_GRAVITY, BODY_MASS_FINITE, BODY_INERTIA_FINITE, BODY_ASLEEP = 1, 2, 4, 8, 16
+BODY_GHOST, BODY_INACTIVE = 32, 64
 POLY_POINT, POLY_SEGMENT, POLY_RECT, POLY_TRIANGLE, POLY_HEXAGON = 0, 1, 2, 3, 4
 COLL_ALIVE, COLL_SENSOR, COLL_HAS_STATIC_FRICTION, COLL_HAS_DYNAMIC_FRICTION = 1, 2, 4, 8
 LIMIT_EQ, LIMIT_LT, LIMIT_GT, CONSTRAINT_CAN_SLEEP = 0, 1, 2, 4
@@ -57,7 +58,7 @@ stats_dtype = np.dtype([("n_bodies", "<u4"), ("n_colliders", "<u4"), ("n_pairs",
 EXPORTS = [
     "sfg_abi_version", "sfg_world_create", "sfg_world_destroy", "sfg_world_clear", "sfg_last_error", "sfg_set_tuning",
     "sfg_set_mask_matrix", "sfg_default_tuning", "sfg_default_mask_matrix", "sfg_set_bodies", "sfg_update_bodies",
-    "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_tick", "sfg_get_bodies",
+    "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_tick", "sfg_tick_begin", "sfg_tick_substeps", "sfg_tick_end", "sfg_slab_configure", "sfg_slab_begin", "sfg_slab_pack", "sfg_slab_unpack", "sfg_get_bodies",
     "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_query_point_batch", "sfg_debug_get_pairs",
     "sfg_debug_get_contact_entries", "sfg_debug_get_constraint_entries", "sfg_debug_get_manifolds", "sfg_debug_get_aabbs", "sfg_debug_get_islands",
     "sfg_debug_intersection_check", "sfg_debug_spherecast_collider", "sfg_debug_geometry",
@@ -97,6 +98,13 @@ def load():
     lib.sfg_set_constraints.argtypes = [vp, u32, vp]
     lib.sfg_set_ropes.argtypes = [vp, u32, vp, u32, vp]
     lib.sfg_tick.argtypes = [vp, C.c_double, i32, C.c_double, vp]
+    lib.sfg_tick_begin.argtypes = [vp, C.c_double, i32, C.c_double, vp]
+    lib.sfg_tick_substeps.argtypes = [vp, u32]
+    lib.sfg_tick_end.argtypes = [vp]
+    lib.sfg_slab_configure.argtypes = [vp, C.c_float, C.c_float, C.c_float]
+    lib.sfg_slab_begin.argtypes = [vp]
+    lib.sfg_slab_pack.argtypes = [vp, i32, i32, vp, u32, C.POINTER(u32)]
+    lib.sfg_slab_unpack.argtypes = [vp, vp, u32]
     lib.sfg_get_bodies.argtypes = [vp, u32, u32, vp]
     lib.sfg_get_contacts.argtypes = [vp, vp, sz, C.POINTER(sz)]
     lib.sfg_set_poses.argtypes = [vp, u32, u32, vp]

@@ -118,6 +118,15 @@ struct SfgWorld {
     DBuf<ContactRec> ct[2];       // contact list of the last tick (with retention for sleeping islands), double-buffered
     uint32_t ct_n = 0, ct_cur = 0;
     bool islands_valid = false;   // the last tick ran the island pass
+    // tick in flight (sfg_tick_begin .. sfg_tick_end)
+    bool in_tick = false, tick_sleeping = false;
+    uint32_t tick_substeps = 0, tick_next_substep = 0;
+    SolverCtx tick_ctx;
+    // slab decomposition (sfg_slab_*)
+    bool slab_on = false, slab_was_on = false;
+    float slab_lo = 0.f, slab_hi = 0.f, slab_halo = 0.f;
+    uint32_t slab_epoch = 0;
+    DBuf<uint32_t> slab_stamp;
     // stats
     SfgStats stats{};
     uint32_t launches = 0;
@@ -155,7 +164,7 @@ __global__ void k_unpack_bodies(const SfgBody* in, uint32_t n, uint32_t first, f
     Q[s] = make_float4(b.rot_s, b.rot_b, b.rot_s, b.rot_b);
     V[s] = make_float4(b.vx, b.vy, b.w, 0.f);
     MI[s] = make_float4((b.flags & SFG_BODY_MASS_FINITE) ? b.inv_mass : 0.f, (b.flags & SFG_BODY_INERTIA_FINITE) ? b.inv_inertia : 0.f,
-                        __uint_as_float(b.flags & 15u), 0.f);
+                        __uint_as_float((b.flags & 15u) | ((b.flags & SFG_BODY_ALIVE) ? BF_EXISTS : 0u)), 0.f);
 }
 __global__ void k_pack_bodies(SfgBody* out, uint32_t n, uint32_t first, const float4* P, const float4* Q, const float4* V, const float4* MI) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,7 +174,9 @@ __global__ void k_pack_bodies(SfgBody* out, uint32_t n, uint32_t first, const fl
     SfgBody b;
     b.x = p.x + p.z; b.y = p.y + p.w; b.rot_s = q.x; b.rot_b = q.y;
     b.vx = v.x; b.vy = v.y; b.w = v.z;
-    b.flags = __float_as_uint(m.z);
+    const uint32_t z = __float_as_uint(m.z);
+    b.flags = (z & 30u) | ((z & BF_EXISTS) ? SFG_BODY_ALIVE : 0u) | ((z & BF_GHOST) ? SFG_BODY_GHOST : 0u) |
+              (((z & BF_EXISTS) && !(z & BF_ALIVE)) ? SFG_BODY_INACTIVE : 0u);
     b.inv_mass = m.x; b.inv_inertia = m.y;
     b.reserved[0] = b.reserved[1] = 0;
     out[i] = b;
@@ -280,6 +291,55 @@ __global__ void k_dbg_geometry(uint32_t op, uint32_t n, const float* args, const
 __global__ void k_iota(uint32_t* p, uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = i;
+}
+
+// ---- slab decomposition: one world cut into x-intervals, one per GPU; bodies near a cut are exchanged as 64-byte records
+struct HaloRec { uint32_t slot, pad[3]; float4 P, Q, V; };
+__global__ void k_slab_classify(uint32_t nb, const float4* P, float4* MI, const uint32_t* stamp, uint32_t epoch, float lo, float hi, float halo, int on) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    float4 m = MI[b];
+    uint32_t fl = __float_as_uint(m.z) & ~(BF_ALIVE | BF_GHOST | BF_ZONE_L | BF_ZONE_R);
+    if (fl & BF_EXISTS) {
+        if (!on) fl |= BF_ALIVE;
+        else {
+            const float4 p = P[b];
+            const float x = p.x + p.z;
+            const bool owned = x >= lo && x < hi;
+            if (owned) { fl |= BF_ALIVE; if (x < lo + halo) fl |= BF_ZONE_L; if (x >= hi - halo) fl |= BF_ZONE_R; }
+            else if (stamp[b] == epoch) fl |= BF_ALIVE | BF_GHOST;     // a neighbour sent it in this tick's refresh
+        }
+    }
+    m.z = __uint_as_float(fl);
+    MI[b] = m;
+}
+// mode 0: by position (the refresh that opens a tick, before the classification exists); mode 1: by this tick's flags
+__global__ void k_slab_pack(uint32_t nb, int mode, int side, float lo, float hi, float halo, const float4* P, const float4* Q, const float4* V,
+                            const float4* MI, HaloRec* out, uint32_t cap, uint32_t* cursor) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t fl = __float_as_uint(MI[b].z);
+    const float4 p = P[b];
+    bool send;
+    if (mode == 0) {
+        const float x = p.x + p.z;
+        send = (fl & BF_EXISTS) && x >= lo && x < hi && (side == 0 ? x < lo + halo : x >= hi - halo);
+    } else send = (fl & BF_ALIVE) && !(fl & BF_GHOST) && (fl & (side == 0 ? BF_ZONE_L : BF_ZONE_R));
+    if (!send) return;
+    const uint32_t pos = atomicAdd(cursor, 1u);
+    if (pos >= cap) return;
+    HaloRec r;
+    r.slot = b; r.pad[0] = r.pad[1] = r.pad[2] = 0u; r.P = p; r.Q = Q[b]; r.V = V[b];
+    out[1 + pos] = r;
+}
+__global__ void k_slab_unpack(const HaloRec* in, uint32_t cap, uint32_t nb, float4* P, float4* Q, float4* V, uint32_t* stamp, uint32_t epoch) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = min(in[0].slot, cap);
+    if (i >= n) return;
+    const HaloRec r = in[1 + i];
+    if (r.slot >= nb) return;
+    P[r.slot] = r.P; Q[r.slot] = r.Q; V[r.slot] = r.V;
+    stamp[r.slot] = epoch;
 }
 
 int ensure_device(int device) {
@@ -416,7 +476,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -661,7 +721,7 @@ int broadphase(SfgWorld* w, float frame_dt) {
     h0.bounds.min_x = h0.bounds.min_y = 0x7FFFFFFF; h0.bounds.max_x = h0.bounds.max_y = int(0x80000000u); h0.bounds.max_extent = int(0x80000000u);
     CK(cudaMemcpyAsync(w->hdr.p, &h0, sizeof(h0), cudaMemcpyHostToDevice, st));
     const float pad = w->tuning.max_expected_acceleration * frame_dt;
-    k_aabb<<<nblk(nc), 256, 0, st>>>(nc, w->CS.p, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p, frame_dt, pad, w->AABB.p, &w->hdr.p->bounds);
+    k_aabb<<<nblk(nc), 256, 0, st>>>(nc, w->CS.p, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p, w->MI.p, frame_dt, pad, w->AABB.p, &w->hdr.p->bounds);
     CKL(w); w->launches++;
     TickHeader h;
     CK(cudaMemcpyAsync(&h, w->hdr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -774,6 +834,15 @@ void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
         }
 }
 
+int slab_classify(SfgWorld* w) {
+    const uint32_t nb = w->n_bodies;
+    if (nb == 0) return SFG_OK;
+    CK(w->slab_stamp.ensure(nb + 1));
+    k_slab_classify<<<nblk(nb), 256, 0, w->stream>>>(nb, w->P.p, w->MI.p, w->slab_stamp.p, w->slab_epoch, w->slab_lo, w->slab_hi, w->slab_halo, w->slab_on ? 1 : 0);
+    CKL(w); w->launches++;
+    w->slab_was_on = w->slab_on;
+    return SFG_OK;
+}
 bool sleeping_enabled(const SfgWorld* w) {
     return !(w->tuning.flags & SFG_TUNE_NO_SLEEPING) && w->tuning.fall_asleep_frames != 0xFFFFFFFFu;
 }
@@ -855,13 +924,17 @@ void build_stage_table(SfgWorld* w) {
 
 extern "C" {
 
-int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff) {
+// A tick in three parts, so that a slab-decomposed world can exchange halo bodies between substeps (sfg_slab_*):
+// begin = boxes, candidate pairs, islands, colouring; substeps = the persistent solver kernel over a range of substeps;
+// end = contact list, sleeping bookkeeping, statistics. sfg_tick runs all three.
+int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff) {
     if (!w) return SFG_E_INVALID;
     if (!(frame_dt > 0.0)) return fail(w, SFG_E_INVALID, "frame_dt must be > 0");
     if (ff && ff->n_terms > 4) return fail(w, SFG_E_INVALID, "force field: at most 4 terms");
     int rc = ensure_device(w->device);
     if (rc != SFG_OK) return fail(w, rc, "no CUDA device (there is no CPU fallback)");
     cudaStream_t st = w->stream;
+    w->in_tick = false;
     // physics.rs:404-418
     uint32_t substeps;
     double dt;
@@ -875,63 +948,95 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
     CK(cudaEventRecord(w->ev[0], st));
     if (w->n_bodies) CK(cudaMemsetAsync(w->EA.p, 0, size_t(w->n_bodies) * sizeof(float2), st));
     if (w->n_ropes) CK(cudaMemsetAsync(w->LAT.p, 0xFF, size_t(w->n_bodies) * sizeof(float2), st));
+    if (w->slab_on || w->slab_was_on) { rc = slab_classify(w); if (rc != SFG_OK) return rc; }
     rc = broadphase(w, float(frame_dt));
     if (rc != SFG_OK) return rc;
     CK(cudaEventRecord(w->ev[1], st));
-    const bool sleeping = sleeping_enabled(w);
-    if (sleeping) { rc = island_pass(w); if (rc != SFG_OK) return rc; }
+    w->tick_sleeping = sleeping_enabled(w) && !w->slab_on;   // islands across a slab seam are not tracked: slabs never sleep
+    if (w->tick_sleeping) { rc = island_pass(w); if (rc != SFG_OK) return rc; }
     rc = build_graph(w);
     if (rc != SFG_OK) return rc;
     CK(cudaEventRecord(w->ev[2], st));
-
+    w->tick_substeps = substeps; w->tick_next_substep = 0;
     if (substeps > 0 && w->n_bodies) {
-        SolverCtx ctx;
-        fill_ctx(w, ctx, float(dt), ff);
+        fill_ctx(w, w->tick_ctx, float(dt), ff);
         build_stage_table(w);
         if (w->n_unit_colours) {
             CK(w->wl_count.ensure(size_t(substeps) * w->n_unit_colours));
             CK(cudaMemsetAsync(w->wl_count.p, 0, size_t(substeps) * w->n_unit_colours * 4, st));
-            ctx.wl_count = w->wl_count.p;
+            w->tick_ctx.wl_count = w->wl_count.p;
         }
-        if (w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES) {
-            for (uint32_t s = 0; s < substeps; ++s)
-                for (const Stage& sg : w->h_stages) { rc = launch_stage_dyn(w, ctx, sg, s + 1 == substeps, s); if (rc != SFG_OK) return rc; }
-        } else {
+        if (!(w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES)) {
             const uint32_t ns = uint32_t(w->h_stages.size());
             CK(w->d_stages.ensure(ns));
             CK(cudaMemcpyAsync(w->d_stages.p, w->h_stages.data(), ns * sizeof(Stage), cudaMemcpyHostToDevice, st));
-            int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, 768, 0));
-            if (per_sm < 1) return fail(w, SFG_E_CUDA, "persistent solver kernel does not fit on an SM");
-            uint32_t max_range = 0;
-            for (const Stage& sg : w->h_stages) max_range = std::max(max_range, sg.end - sg.begin);
-            const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range, 768)));
-            const Stage* dst = w->d_stages.p;
-            uint32_t n_stages = ns, n_sub = substeps;
-            unsigned int* bar = &w->hdr.p->barrier;
-            CK(cudaMemsetAsync(bar, 0, 4, st));
-            // debug: SFG_TRACE=<file> dumps per-stage, per-CTA (arrival, release) %globaltimer stamps of the barrier
-            const char* trace_path = getenv("SFG_TRACE");
-            unsigned long long* trace = nullptr;
-            const size_t trace_n = size_t(2) * n_sub * ns * grid;
-            if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; }
-            void* args[] = {&ctx, (void*)&dst, &n_stages, &n_sub, (void*)&bar, (void*)&trace};
-            CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(768), args, 0, st));
-            w->launches++;
-            if (trace_path) {
-                std::vector<unsigned long long> h(trace_n);
-                CK(cudaMemcpyAsync(h.data(), trace, trace_n * 8, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (FILE* f = fopen(trace_path, "wb")) {
-                    uint32_t hdr4[4] = {n_sub, ns, grid, 0};
-                    fwrite(hdr4, 4, 4, f);
-                    for (const Stage& sg : w->h_stages) { uint32_t r[4] = {sg.kind, sg.begin, sg.end, 0}; fwrite(r, 4, 4, f); }
-                    fwrite(h.data(), 8, trace_n, f);
-                    fclose(f);
-                }
-            }
+            CK(cudaMemsetAsync(&w->hdr.p->barrier, 0, 4, st));
         }
     }
+    w->in_tick = true;
+    return SFG_OK;
+}
+
+int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
+    if (!w) return SFG_E_INVALID;
+    if (!w->in_tick) return fail(w, SFG_E_STATE, "sfg_tick_substeps outside sfg_tick_begin / sfg_tick_end");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    const uint32_t substeps = w->tick_substeps, first = w->tick_next_substep;
+    if (uint64_t(first) + count > substeps) return fail(w, SFG_E_INVALID, "more substeps than the tick has");
+    w->tick_next_substep = first + count;
+    if (count == 0 || w->n_bodies == 0) return SFG_OK;
+    const SolverCtx& ctx = w->tick_ctx;
+    int rc;
+    if (w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES) {
+        for (uint32_t s = first; s < first + count; ++s)
+            for (const Stage& sg : w->h_stages) { rc = launch_stage_dyn(w, ctx, sg, s + 1 == substeps, s); if (rc != SFG_OK) return rc; }
+        return SFG_OK;
+    }
+    const uint32_t ns = uint32_t(w->h_stages.size());
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, 768, 0));
+    if (per_sm < 1) return fail(w, SFG_E_CUDA, "persistent solver kernel does not fit on an SM");
+    uint32_t max_range = 0;
+    for (const Stage& sg : w->h_stages) max_range = std::max(max_range, sg.end - sg.begin);
+    const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range, 768)));
+    const Stage* dst = w->d_stages.p;
+    uint32_t n_stages = ns, sub_begin = first, sub_end = first + count, n_sub = substeps;
+    unsigned int* bar = &w->hdr.p->barrier;
+    CK(cudaMemsetAsync(bar, 0, 4, st));
+    // debug: SFG_TRACE=<file> dumps per-stage, per-CTA (arrival, release) %globaltimer stamps of the barrier
+    const char* trace_path = getenv("SFG_TRACE");
+    unsigned long long* trace = nullptr;
+    const size_t trace_n = size_t(2) * count * ns * grid;
+    if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; }
+    void* args[] = {(void*)&ctx, (void*)&dst, &n_stages, &sub_begin, &sub_end, &n_sub, (void*)&bar, (void*)&trace};
+    CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(768), args, 0, st));
+    w->launches++;
+    if (trace_path) {
+        std::vector<unsigned long long> h(trace_n);
+        CK(cudaMemcpyAsync(h.data(), trace, trace_n * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (FILE* f = fopen(trace_path, "wb")) {
+            uint32_t hdr4[4] = {count, ns, grid, 0};
+            fwrite(hdr4, 4, 4, f);
+            for (const Stage& sg : w->h_stages) { uint32_t r[4] = {sg.kind, sg.begin, sg.end, 0}; fwrite(r, 4, 4, f); }
+            fwrite(h.data(), 8, trace_n, f);
+            fclose(f);
+        }
+    }
+    return SFG_OK;
+}
+
+int sfg_tick_end(SfgWorld* w) {
+    if (!w) return SFG_E_INVALID;
+    if (!w->in_tick) return fail(w, SFG_E_STATE, "sfg_tick_end without sfg_tick_begin");
+    if (w->tick_next_substep != w->tick_substeps) return fail(w, SFG_E_STATE, "sfg_tick_end before all substeps ran");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    w->in_tick = false;
+    const bool sleeping = w->tick_sleeping;
+    const uint32_t substeps = w->tick_substeps;
+    int rc;
     CK(cudaEventRecord(w->ev[3], st));
     if (sleeping) { rc = island_post(w); if (rc != SFG_OK) return rc; }
     uint32_t isl_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -958,6 +1063,65 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
     cudaEventElapsedTime(&s.ms_total, w->ev[0], w->ev[4]);
     s.reserved[0] = uint32_t(w->h_stages.size());
     s.reserved[1] = w->stats_jp_rounds;
+    return SFG_OK;
+}
+
+int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff) {
+    int rc = sfg_tick_begin(w, frame_dt, has_time_scale, time_scale, ff);
+    if (rc != SFG_OK) return rc;
+    rc = sfg_tick_substeps(w, w->tick_substeps);
+    if (rc != SFG_OK) return rc;
+    return sfg_tick_end(w);
+}
+
+// ---- slab decomposition (north_star "spatial slabs with boundary-body halo exchange")
+int sfg_slab_configure(SfgWorld* w, float x_lo, float x_hi, float halo) {
+    if (!w) return SFG_E_INVALID;
+    if (x_hi > x_lo && !(halo > 0.f)) return fail(w, SFG_E_INVALID, "slab halo must be > 0");
+    cudaSetDevice(w->device);
+    w->slab_on = x_hi > x_lo;
+    w->slab_lo = x_lo; w->slab_hi = x_hi; w->slab_halo = halo;
+    CK(w->slab_stamp.ensure(size_t(w->n_bodies) + 1));
+    CK(cudaMemsetAsync(w->slab_stamp.p, 0, (size_t(w->n_bodies) + 1) * 4, w->stream));
+    w->slab_epoch = 0;
+    return SFG_OK;
+}
+int sfg_slab_begin(SfgWorld* w) {
+    if (!w) return SFG_E_INVALID;
+    if (!w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
+    w->slab_epoch += 1;
+    return SFG_OK;
+}
+int sfg_slab_pack(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records, uint32_t* count_out) {
+    if (!w || !device_out || !count_out || side < 0 || side > 1 || mode < 0 || mode > 1) return SFG_E_INVALID;
+    if (!w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    *count_out = 0;
+    HaloRec* out = (HaloRec*)device_out;
+    CK(cudaMemsetAsync(out, 0, sizeof(HaloRec), st));
+    if (w->n_bodies) {
+        k_slab_pack<<<nblk(w->n_bodies), 256, 0, st>>>(w->n_bodies, mode, side, w->slab_lo, w->slab_hi, w->slab_halo, w->P.p, w->Q.p, w->V.p, w->MI.p, out,
+                                                     capacity_records, &out[0].slot);
+        CKL(w); w->launches++;
+    }
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, &out[0].slot, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *count_out = n;
+    if (n > capacity_records) return fail(w, SFG_E_CAPACITY, "halo buffer too small for the boundary zone");
+    return SFG_OK;
+}
+int sfg_slab_unpack(SfgWorld* w, const void* device_in, uint32_t capacity_records) {
+    if (!w || !device_in) return SFG_E_INVALID;
+    if (!w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
+    if (capacity_records == 0 || w->n_bodies == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    CK(w->slab_stamp.ensure(size_t(w->n_bodies) + 1));
+    k_slab_unpack<<<nblk(capacity_records), 256, 0, w->stream>>>((const HaloRec*)device_in, capacity_records, w->n_bodies, w->P.p, w->Q.p, w->V.p,
+                                                               w->slab_stamp.p, w->slab_epoch);
+    CKL(w); w->launches++;
+    CK(cudaStreamSynchronize(w->stream));
     return SFG_OK;
 }
 

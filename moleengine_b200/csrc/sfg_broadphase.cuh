@@ -22,15 +22,16 @@ inline float ord2f_host(int i) { int j = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; m
 
 __global__ void __launch_bounds__(256) k_aabb(uint32_t n_colls, const float4* __restrict__ CS, const float4* __restrict__ CL,
                                               const int4* __restrict__ CI, const float4* __restrict__ P, const float4* __restrict__ Q,
-                                              const float4* __restrict__ V, float frame_dt, float pad, float4* __restrict__ AABB,
-                                              Bounds* __restrict__ bounds) {
+                                              const float4* __restrict__ V, const float4* __restrict__ MI, float frame_dt, float pad,
+                                              float4* __restrict__ AABB, Bounds* __restrict__ bounds) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = false;
     float4 box = make_float4(0, 0, 0, 0);
     uint32_t domain = 0;
     if (i < n_colls) {
         const int4 ci = CI[i];
-        if (ci.w & CF_ALIVE) {
+        // a collider whose body sits this tick out (outside the slab and its halo) is not in the broadphase
+        if ((ci.w & CF_ALIVE) && (ci.x < 0 || (__float_as_uint(MI[ci.x].z) & BF_ALIVE))) {
             live = true;
             domain = uint32_t(ci.z);
             const Shape s = mkshape(CS[i]);
@@ -53,6 +54,10 @@ __global__ void __launch_bounds__(256) k_aabb(uint32_t n_colls, const float4* __
                 box = shape_aabb_exact(s, mk(l.x, l.y), mkrot(l.z, l.w));
             }
             AABB[i] = box;
+        } else {
+            // not in this tick's broadphase: k_cell_keys gives a non-finite box the dead key, the cast kernels never reach it
+            const float qnan = __int_as_float(0x7FC00000);
+            AABB[i] = make_float4(qnan, qnan, qnan, qnan);
         }
     }
     // bounds: warp reduce, one atomic per warp

@@ -494,11 +494,12 @@ SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, unsigned l
 // to warps round-robin ACROSS CTAs (chunk c of 32 units -> CTA c mod gridDim, warp slot c / gridDim), so a run of
 // expensive units (they are grouped by narrowphase path) is spread over all SMs; then all CTAs meet at a barrier.
 __global__ void __launch_bounds__(768, 1) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
-                                                             uint32_t n_stages, uint32_t substeps, unsigned int* barrier_counter, unsigned long long* trace) {
+                                                             uint32_t n_stages, uint32_t sub_begin, uint32_t sub_end, uint32_t substeps,
+                                                             unsigned int* barrier_counter, unsigned long long* trace) {
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
     const uint32_t first_chunk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, chunk_stride = gridDim.x * warps_per_cta;
     unsigned int target = 0;
-    for (uint32_t s = 0; s < substeps; ++s) {
+    for (uint32_t s = sub_begin; s < sub_end; ++s) {   // substeps [sub_begin, sub_end) of a tick of `substeps`
         const bool last = s + 1 == substeps;
         for (uint32_t k = 0; k < n_stages; ++k) {
             const Stage st = stages[k];
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(768, 1) k_solve_persistent(const __grid_consta
                 const uint32_t i = chunk * 32u + lane;
                 if (i < n) run_stage(c, st.kind, st.begin + i, last, s, st.colour, st.begin);
             }
-            grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t(s * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
+            grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
         }
     }
 }

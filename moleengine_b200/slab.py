@@ -1,0 +1,146 @@
+"""One large world cut into x-slabs, one per GPU (north_star's second partition).
+
+Every rank uploads the whole world (identical slots) and owns the bodies whose x lies in its interval. Bodies within
+`halo` of a cut are mirrored on the neighbour as ghosts: the owner's copy is authoritative, the neighbour solves the
+ghost too (so that pairs across the cut see both bodies move inside a substep) and has it overwritten by the owner's
+state after every substep. The only data that crosses ranks are 64-byte body records between x-neighbours:
+
+    per tick:  refresh (who is near the cut, by position)          1 exchange
+               after every substep but the last (owner -> ghost)    substeps - 1 exchanges
+
+The C library packs / unpacks device buffers (sfg_slab_pack / sfg_slab_unpack); this module owns the buffers (torch
+tensors) and the transport: torch.distributed point-to-point ops (NCCL over NVLink on GPUs, gloo in the CPU tests) or
+plain device copies when several slabs live in one process (tests). Results next to a cut are only statistically equal
+to the single-GPU run: the Gauss-Seidel order differs there.
+"""
+import math
+
+REC_WORDS = 16   # one record = 64 bytes = 16 float32 words; record 0 of a buffer is the header (word 0 = count)
+
+
+def slab_bounds(rank, n_ranks, x_min, x_max):
+    """Equal-width x-interval of `rank`; the outermost slabs extend to infinity so that no body is ever unowned."""
+    if n_ranks <= 0 or not (0 <= rank < n_ranks):
+        raise ValueError("bad rank / n_ranks")
+    w = (x_max - x_min) / n_ranks
+    lo = -math.inf if rank == 0 else x_min + rank * w
+    hi = math.inf if rank == n_ranks - 1 else x_min + (rank + 1) * w
+    return lo, hi
+
+
+def neighbours(rank, n_ranks):
+    """(left, right) ranks or None at the ends; side 0 = towards lower x."""
+    return (rank - 1 if rank > 0 else None, rank + 1 if rank + 1 < n_ranks else None)
+
+
+class DistTransport:
+    """torch.distributed point-to-point exchange with both x-neighbours in one batch (no collective over all ranks)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def exchange(self, rank, n_ranks, send, recv):
+        import torch
+        import torch.distributed as dist
+        ops = []
+        for side, peer in enumerate(neighbours(rank, n_ranks)):
+            if peer is None:
+                continue
+            ops.append(dist.P2POp(dist.isend, send[side], peer, self.group))
+            ops.append(dist.P2POp(dist.irecv, recv[side], peer, self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            if send[0].is_cuda:
+                torch.cuda.current_stream().synchronize()
+
+
+class LocalTransport:
+    """All slabs in one process (tests): the 'wire' is a copy between the drivers' buffers."""
+
+    def __init__(self):
+        self.drivers = {}
+
+    def register(self, driver):
+        self.drivers[driver.rank] = driver
+
+    def exchange_all(self):
+        for d in self.drivers.values():
+            for side, peer in enumerate(neighbours(d.rank, d.n_ranks)):
+                if peer is not None:
+                    d.recv[side].copy_(self.drivers[peer].send[1 - side])
+
+
+class SlabDriver:
+    """Runs the ticks of one slab. `world` needs: slab_configure, slab_begin, slab_pack(mode, side, ptr, cap) -> count,
+    slab_unpack(ptr, cap), tick_begin(frame_dt, time_scale, ff), tick_substeps(n), tick_end() — GpuWorld has them."""
+
+    def __init__(self, world, rank, n_ranks, x_min, x_max, halo, substeps, capacity=16384, device=None, transport=None):
+        import torch
+        self.world, self.rank, self.n_ranks, self.substeps, self.capacity = world, rank, n_ranks, substeps, capacity
+        self.lo, self.hi = slab_bounds(rank, n_ranks, x_min, x_max)
+        self.halo = halo
+        self.transport = transport if transport is not None else DistTransport()
+        f32max = 3.0e38
+        world.slab_configure(max(self.lo, -f32max), min(self.hi, f32max), halo)
+        words = (capacity + 1) * REC_WORDS
+        self.send = [torch.zeros(words, dtype=torch.float32, device=device) for _ in range(2)]
+        self.recv = [torch.zeros(words, dtype=torch.float32, device=device) for _ in range(2)]
+        self.sent_records = 0      # bodies sent in the last tick (both sides, all exchanges)
+        self.exchanges = 0
+        if isinstance(self.transport, LocalTransport):
+            self.transport.register(self)
+
+    def pack(self, mode):
+        n = 0
+        for side, peer in enumerate(neighbours(self.rank, self.n_ranks)):
+            if peer is not None:
+                n += self.world.slab_pack(mode, side, self.send[side].data_ptr(), self.capacity)
+        self.sent_records += n
+
+    def unpack(self):
+        for side, peer in enumerate(neighbours(self.rank, self.n_ranks)):
+            if peer is not None:
+                self.world.slab_unpack(self.recv[side].data_ptr(), self.capacity)
+
+    def _exchange(self, mode):
+        self.pack(mode)
+        self.transport.exchange(self.rank, self.n_ranks, self.send, self.recv)
+        self.unpack()
+        self.exchanges += 1
+
+    def tick(self, frame_dt=1.0 / 60.0, forcefield=None):
+        """One frame: refresh the halo, then `substeps` substeps with an owner -> ghost exchange between them."""
+        self.sent_records, self.exchanges = 0, 0
+        w = self.world
+        w.slab_begin()
+        self._exchange(0)
+        w.tick_begin(frame_dt, None, forcefield)
+        for s in range(self.substeps):
+            w.tick_substeps(1)
+            if s + 1 < self.substeps:
+                self._exchange(1)
+        w.tick_end()
+
+
+def tick_local(drivers, transport, frame_dt=1.0 / 60.0, forcefield=None):
+    """Lock-step tick of several slabs living in one process (tests): same call order as SlabDriver.tick on every rank."""
+    def exchange(mode):
+        for d in drivers:
+            d.pack(mode)
+        transport.exchange_all()
+        for d in drivers:
+            d.unpack()
+    for d in drivers:
+        d.sent_records = 0
+        d.world.slab_begin()
+    exchange(0)
+    for d in drivers:
+        d.world.tick_begin(frame_dt, None, forcefield)
+    for s in range(drivers[0].substeps):
+        for d in drivers:
+            d.world.tick_substeps(1)
+        if s + 1 < drivers[0].substeps:
+            exchange(1)
+    for d in drivers:
+        d.world.tick_end()

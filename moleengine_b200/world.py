@@ -87,6 +87,31 @@ class GpuWorld:
         self._ck(self.lib.sfg_tick(self.h, frame_dt, 0 if time_scale is None else 1,
                                    0.0 if time_scale is None else time_scale, abi.ptr(ff)))
 
+    # ---- the tick in three parts + slab halo exchange (moleengine_b200/slab.py drives these) ----------------
+    def tick_begin(self, frame_dt=1.0 / 60.0, time_scale=None, forcefield=None):
+        ff = abi.gravity_field() if forcefield is None else forcefield
+        self._ck(self.lib.sfg_tick_begin(self.h, frame_dt, 0 if time_scale is None else 1, 0.0 if time_scale is None else time_scale, abi.ptr(ff)))
+
+    def tick_substeps(self, count):
+        self._ck(self.lib.sfg_tick_substeps(self.h, count))
+
+    def tick_end(self):
+        self._ck(self.lib.sfg_tick_end(self.h))
+
+    def slab_configure(self, x_lo, x_hi, halo):
+        self._ck(self.lib.sfg_slab_configure(self.h, x_lo, x_hi, halo))
+
+    def slab_begin(self):
+        self._ck(self.lib.sfg_slab_begin(self.h))
+
+    def slab_pack(self, mode, side, device_ptr, capacity_records):
+        n = C.c_uint32()
+        self._ck(self.lib.sfg_slab_pack(self.h, mode, side, C.c_void_p(device_ptr), capacity_records, C.byref(n)))
+        return n.value
+
+    def slab_unpack(self, device_ptr, capacity_records):
+        self._ck(self.lib.sfg_slab_unpack(self.h, C.c_void_p(device_ptr), capacity_records))
+
     def get_bodies(self, first=0, count=None):
         count = self.n_bodies - first if count is None else count
         out = np.zeros(count, abi.body_dtype)

@@ -1,0 +1,100 @@
+"""Slab decomposition on the GPU: one world cut into x-slabs, each slab its own SfgWorld, halo bodies
+exchanged through the C ABI's pack / unpack between substeps. Here all slabs live in one process on cuda:0 and the
+"wire" is a device copy (slab.LocalTransport); bench.py runs the same driver over NCCL with one process per GPU.
+
+Away from a cut a slab sees exactly the pairs the whole world sees, so those bodies must follow the single-world run
+closely; next to a cut the Gauss-Seidel order differs, so only statistics are compared there (north_star)."""
+import numpy as np
+import pytest
+
+from moleengine_b200 import GpuWorld, abi, scenes, slab
+
+pytestmark = pytest.mark.gpu
+
+
+def _state(b):
+    return np.stack([b["x"], b["y"], b["rot_s"], b["rot_b"], b["vx"], b["vy"], b["w"]], 1).astype(np.float64)
+
+
+def _assemble(worlds, n_bodies):
+    """Every body from the rank that owned it in the last tick."""
+    out = np.zeros(n_bodies, abi.body_dtype)
+    owners = np.zeros(n_bodies, np.int32)
+    for w in worlds:
+        b = w.get_bodies()
+        owned = ((b["flags"] & abi.BODY_ALIVE) != 0) & ((b["flags"] & (abi.BODY_GHOST | abi.BODY_INACTIVE)) == 0)
+        out[owned] = b[owned]
+        owners += owned
+    return out, owners
+
+
+@pytest.mark.parametrize("n_slabs", [2, 3])
+def test_slabs_follow_the_single_world(n_slabs):
+    import torch
+    sc = scenes.c3_mixed(120, 30, seed=0xC3)
+    nb = len(sc["bodies"])
+    x0 = float(sc["bodies"]["x"].min()), float(sc["bodies"]["x"].max())
+    tun = abi.default_tuning(substeps=4, flags=abi.TUNE_NO_SLEEPING)
+    ref = GpuWorld(tuning=tun)
+    ref.load_scene(sc)
+    transport = slab.LocalTransport()
+    worlds, drivers = [], []
+    for r in range(n_slabs):
+        w = GpuWorld(tuning=tun)
+        w.load_scene(sc)
+        worlds.append(w)
+        drivers.append(slab.SlabDriver(w, r, n_slabs, x0[0], x0[1], halo=4.0, substeps=4, capacity=4096, device=torch.device("cuda", 0),
+                                       transport=transport))
+    ticks = 40
+    for _ in range(ticks):
+        ref.tick()
+        slab.tick_local(drivers, transport)
+    got, owners = _assemble(worlds, nb)
+    alive = (sc["bodies"]["flags"] & abi.BODY_ALIVE) != 0
+    assert np.array_equal(owners[alive], np.ones(int(alive.sum()), np.int32)), "every body has exactly one owner"
+    want = ref.get_bodies()
+    sg, sw = _state(got)[alive], _state(want)[alive]
+    dpos = np.hypot(sg[:, 0] - sw[:, 0], sg[:, 1] - sw[:, 1])
+    cuts = [slab.slab_bounds(r, n_slabs, x0[0], x0[1])[1] for r in range(n_slabs - 1)]
+    dist_to_cut = np.min(np.abs(sw[:, 0:1] - np.array(cuts)[None, :]), axis=1)
+    far = dist_to_cut > 12.0
+    sent = sum(d.sent_records for d in drivers)
+    print({"bodies": int(alive.sum()), "far": int(far.sum()), "dpos_far_max": float(dpos[far].max()), "dpos_far_median": float(np.median(dpos[far])),
+           "dpos_near_max": float(dpos[~far].max()), "dpos_near_median": float(np.median(dpos[~far])), "records_last_tick": sent,
+           "active_per_slab": [int(w.stats()["n_colliders"]) for w in worlds]})
+    assert sent > 0, "nothing crossed the cuts"
+    # far from a cut: the same pairs, the same colours in the neighbourhood, the same arithmetic
+    assert np.median(dpos[far]) < 1e-6 and (dpos[far] < 1e-4).mean() > 0.98
+    # near a cut: same physics, different Gauss-Seidel order at the seam
+    assert np.median(dpos[~far]) < 1e-3 and dpos.max() < 0.5
+    m = 1.0 / np.maximum(want["inv_mass"][alive].astype(np.float64), 1e-9)
+    m[want["inv_mass"][alive] == 0] = 0.0
+    pg, pw = (m[:, None] * sg[:, 4:6]).sum(0), (m[:, None] * sw[:, 4:6]).sum(0)
+    kg, kw = 0.5 * (m * (sg[:, 4] ** 2 + sg[:, 5] ** 2)).sum(), 0.5 * (m * (sw[:, 4] ** 2 + sw[:, 5] ** 2)).sum()
+    assert np.abs(pg - pw).max() <= 2e-3 * max(np.abs(pw).max(), 1.0)
+    assert abs(kg - kw) <= 2e-3 * kw
+    # each slab only carried its share of the world through the broadphase
+    assert max(int(w.stats()["n_colliders"]) for w in worlds) < 0.75 * len(sc["colliders"])
+    for w in worlds + [ref]:
+        w.close()
+
+
+def test_slab_mode_can_be_switched_off():
+    sc = scenes.c3_mixed(40, 10, seed=5)
+    tun = abi.default_tuning(substeps=2, flags=abi.TUNE_NO_SLEEPING)
+    a, b = GpuWorld(tuning=tun), GpuWorld(tuning=tun)
+    a.load_scene(sc); b.load_scene(sc)
+    x0 = float(sc["bodies"]["x"].min()), float(sc["bodies"]["x"].max())
+    b.slab_configure(x0[0] - 1.0, 0.5 * (x0[0] + x0[1]), 4.0)
+    b.slab_begin()
+    b.tick()                                              # half the world sits this tick out
+    assert int(b.stats()["n_colliders"]) < int(0.8 * len(sc["colliders"]))
+    gb = b.get_bodies()
+    assert ((gb["flags"] & abi.BODY_INACTIVE) != 0).any()
+    b.load_scene(sc)                                      # fresh state, slab off again
+    b.slab_configure(0.0, 0.0, 0.0)
+    a.tick(); b.tick()
+    ga, gb = a.get_bodies(), b.get_bodies()
+    for f in ("x", "y", "rot_s", "rot_b", "vx", "vy", "w", "flags"):
+        assert np.array_equal(ga[f], gb[f])
+    a.close(); b.close()
