@@ -111,6 +111,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", default="full", choices=["full", "tenth", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-slab", action="store_true", help="skip the slab-decomposed strong-scaling arm (N > 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -197,6 +198,35 @@ def main():
     e2e_value = world_size * nb * SUBSTEPS / e2e_s
     checksum = float(np.abs(host_np[:1000, 1]).sum())   # the step's result is read on the host
 
+    # ---------------- slab arm (N > 1): ONE 1 M-body world cut into N x-slabs, halo bodies exchanged between x-neighbours
+    # over NCCL point-to-point after every substep (north_star's second partition; strong scaling, reported next to `value`)
+    slab_info = None
+    if world_size > 1 and not args.no_slab:
+        from moleengine_b200 import slab
+        scs = sc if rank == 0 else workload(args.scale, 0xC3)        # every rank uploads the SAME world (seed 0xC3)
+        gs = GpuWorld(tuning=abi.default_tuning(substeps=SUBSTEPS, flags=abi.TUNE_NO_SLEEPING), device=local_rank)
+        gs.load_scene(scs)
+        xs = scs["bodies"]["x"]
+        halo = 4.0
+        drv = slab.SlabDriver(gs, rank, world_size, float(xs.min()), float(xs.max()), halo=halo, substeps=SUBSTEPS, capacity=65536,
+                              device=torch.device("cuda", local_rank))
+        for _ in range(args.warmup):
+            drv.tick(FRAME_DT, ff)
+        barrier()
+        t0 = time.perf_counter()
+        dev_ms, recs = 0.0, 0
+        for _ in range(args.steps):
+            drv.tick(FRAME_DT, ff)
+            dev_ms += float(gs.stats()["ms_total"]); recs += drv.sent_records
+        barrier()
+        slab_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+        recs_all = max_over_ranks(recs / args.steps)
+        slab_info = {"value": len(scs["bodies"]) * SUBSTEPS / slab_s, "unit": "body-substeps/s", "scaling": "strong", "ms_per_step": slab_s * 1e3,
+                     "device_ms_per_step_rank0": dev_ms / args.steps, "slabs": world_size, "halo_m": halo, "exchanges_per_tick": drv.exchanges,
+                     "halo_records_per_tick_max_rank": recs_all, "halo_bytes_per_tick_max_rank": recs_all * 64,
+                     "active_colliders_rank0": int(gs.stats()["n_colliders"]), "transport": "torch.distributed NCCL send/recv between x-neighbours"}
+        gs.close()
+
     if rank != 0:
         g.close()
         if world_size > 1:
@@ -248,6 +278,8 @@ def main():
         "phases_ms": {"broadphase": broad_ms / args.steps, "graph": graph_ms / args.steps, "solver": solver_ms / args.steps, "device_total": total_ms / args.steps},
         "cpu_baseline": cpu,
     }
+    if slab_info is not None:
+        out["slab"] = slab_info
     print(json.dumps(out))
     g.close()
     if world_size > 1:

@@ -137,6 +137,15 @@ typedef struct SfgRay {
     uint32_t domain;
     uint32_t reserved;
 } SfgRay;
+/* physics.rs:1215-1219 query_shape arguments: PhysicsPose + ColliderShape + CollisionLayerMask (collision.rs:112-128) */
+typedef struct SfgShapeQuery {
+    float x, y, rot_s, rot_b;        /* pose */
+    float p0, p1, circle_r;          /* ColliderShape, same encoding as SfgCollider */
+    uint32_t kind;                   /* SFG_POLY_* */
+    uint64_t layer_mask;             /* bit l set = colliders on layer l are reported */
+    uint32_t domain;
+    uint32_t reserved;
+} SfgShapeQuery;
 /* physics.rs:131-149 CastHit; collider = -1 means None */
 typedef struct SfgCastHit {
     int32_t collider;
@@ -222,6 +231,10 @@ int sfg_cast_batch(SfgWorld* w, uint32_t n, const SfgRay* rays, SfgCastHit* out)
  *      `max_hits` collider slots (-1 padded) ---- */
 int sfg_query_point_batch(SfgWorld* w, uint32_t n, const float* points_xy, const uint32_t* domains,
                           uint32_t max_hits, int32_t* out_colliders, uint32_t* out_counts);
+/* PhysicsWorld::query_shape (physics.rs:1215-1245), batched: up to max_hits collider slots per query (-1 padded) and the
+ * full count. Like every query it uses the spatial index and boxes of the last tick and the current poses. */
+int sfg_query_shape_batch(SfgWorld* w, uint32_t n, const SfgShapeQuery* queries, uint32_t max_hits, int32_t* out_colliders,
+                          uint32_t* out_counts);
 
 /* ---- parity hooks (tests only; not part of the drop-in surface) ---- */
 /* candidate pairs of the last tick as [later, earlier] collider slots, unsorted */

@@ -45,6 +45,8 @@ forcefield_dtype = np.dtype([("n_terms", "<u4"), ("terms", force_term_dtype, (4,
 contact_dtype = np.dtype([("collider0", "<u4"), ("collider1", "<u4"), ("nx", "<f4"), ("ny", "<f4")])
 ray_dtype = np.dtype([("sx", "<f4"), ("sy", "<f4"), ("dx", "<f4"), ("dy", "<f4"), ("radius", "<f4"),
                       ("max_distance", "<f4"), ("domain", "<u4"), ("reserved", "<u4")])
+shape_query_dtype = np.dtype([("x", "<f4"), ("y", "<f4"), ("rot_s", "<f4"), ("rot_b", "<f4"), ("p0", "<f4"), ("p1", "<f4"),
+                              ("circle_r", "<f4"), ("kind", "<u4"), ("layer_mask", "<u8"), ("domain", "<u4"), ("reserved", "<u4")])
 hit_dtype = np.dtype([("collider", "<i4"), ("t", "<f4"), ("px", "<f4"), ("py", "<f4"), ("nx", "<f4"), ("ny", "<f4"),
                       ("reserved", "<u4", (2,))])
 stats_dtype = np.dtype([("n_bodies", "<u4"), ("n_colliders", "<u4"), ("n_pairs", "<u4"), ("n_contact_entries", "<u4"),
@@ -59,7 +61,7 @@ EXPORTS = [
     "sfg_abi_version", "sfg_world_create", "sfg_world_destroy", "sfg_world_clear", "sfg_last_error", "sfg_set_tuning",
     "sfg_set_mask_matrix", "sfg_default_tuning", "sfg_default_mask_matrix", "sfg_set_bodies", "sfg_update_bodies",
     "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_tick", "sfg_tick_begin", "sfg_tick_substeps", "sfg_tick_end", "sfg_slab_configure", "sfg_slab_begin", "sfg_slab_pack", "sfg_slab_unpack", "sfg_get_bodies",
-    "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_query_point_batch", "sfg_debug_get_pairs",
+    "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_query_point_batch", "sfg_query_shape_batch", "sfg_debug_get_pairs",
     "sfg_debug_get_contact_entries", "sfg_debug_get_constraint_entries", "sfg_debug_get_manifolds", "sfg_debug_get_aabbs", "sfg_debug_get_islands",
     "sfg_debug_intersection_check", "sfg_debug_spherecast_collider", "sfg_debug_geometry",
 ]
@@ -112,6 +114,7 @@ def load():
     lib.sfg_get_stats.argtypes = [vp, vp]
     lib.sfg_cast_batch.argtypes = [vp, u32, vp, vp]
     lib.sfg_query_point_batch.argtypes = [vp, u32, vp, vp, u32, vp, vp]
+    lib.sfg_query_shape_batch.argtypes = [vp, u32, vp, u32, vp, vp]
     lib.sfg_debug_get_pairs.argtypes = [vp, vp, sz, C.POINTER(sz)]
     lib.sfg_debug_get_contact_entries.argtypes = [vp, vp, vp, vp, sz, C.POINTER(sz)]
     lib.sfg_debug_get_constraint_entries.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]

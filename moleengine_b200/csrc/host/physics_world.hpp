@@ -446,6 +446,21 @@ public:
         }
         return res;
     }
+    // physics.rs:1215-1245; mask: bit l set = layer l is reported (CollisionLayerMask, collision.rs:112-128)
+    std::vector<std::pair<ColliderKey, std::optional<BodyKey>>> query_shape(PhysicsPose pose, ColliderShape shape, uint64_t mask) {
+        SfgShapeQuery q{};
+        q.x = float(pose.translation.x); q.y = float(pose.translation.y); q.rot_s = float(pose.rotation.s); q.rot_b = float(pose.rotation.b);
+        q.kind = uint32_t(shape.polygon); q.p0 = float(shape.p0); q.p1 = float(shape.p1); q.circle_r = float(shape.circle_r);
+        q.layer_mask = mask;
+        int32_t out[64]; uint32_t cnt = 0;
+        ck(sfg_query_shape_batch(raw_, 1, &q, 64, out, &cnt));
+        std::vector<std::pair<ColliderKey, std::optional<BodyKey>>> res;
+        for (uint32_t i = 0; i < cnt && i < 64; ++i) {
+            auto idx = entity_set.colliders.index_of_slot(uint32_t(out[i]));
+            if (idx) res.push_back({ColliderKey{*idx}, entity_set.get_collider_body_key(ColliderKey{*idx})});
+        }
+        return res;
+    }
     SfgWorld* raw() { return raw_; }
 };
 

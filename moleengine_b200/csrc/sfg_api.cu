@@ -524,11 +524,15 @@ int sfg_set_bodies(SfgWorld* w, uint32_t n, const SfgBody* b) {
     cudaSetDevice(w->device);
     CK(w->P.ensure(n)); CK(w->Q.ensure(n)); CK(w->V.ensure(n)); CK(w->OV.ensure(n)); CK(w->MI.ensure(n)); CK(w->EA.ensure(n));
     if (n != w->n_bodies) { w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0; w->n_constraints = 0; }   // slot space changed: re-upload ropes / constraints
+    // a new slot space starts a new world as far as sleeping is concerned: no island is being watched, no contact retained.
+    // (Re-uploading the same slots every tick, as the PhysicsWorld mirror does, keeps the records: physics.rs:711-741 only
+    // looks at velocities and at the island's identity.)
+    if (n != w->n_bodies || !w->sl_valid.p) {
+        CK(w->sl_valid.ensure(n + 1)); CK(w->sl_ticks.ensure(n + 1)); CK(w->sl_sum.ensure(n + 1));
+        CK(cudaMemsetAsync(w->sl_valid.p, 0, size_t(n + 1) * 4, w->stream));
+        w->ct_n = 0; w->islands_valid = false;
+    }
     w->n_bodies = n;
-    // a full upload starts a new world as far as sleeping is concerned: no island is being watched, no contact retained
-    CK(w->sl_valid.ensure(n + 1)); CK(w->sl_ticks.ensure(n + 1)); CK(w->sl_sum.ensure(n + 1));
-    CK(cudaMemsetAsync(w->sl_valid.p, 0, size_t(n + 1) * 4, w->stream));
-    w->ct_n = 0; w->islands_valid = false;
     return upload_bodies(w, 0, n, b);
 }
 int sfg_update_bodies(SfgWorld* w, uint32_t first, uint32_t count, const SfgBody* b) {
@@ -1250,6 +1254,30 @@ int sfg_query_point_batch(SfgWorld* w, uint32_t n, const float* points_xy, const
     CK(cudaMemcpyAsync(d_pts, points_xy, b_pts, cudaMemcpyHostToDevice, st));
     if (domains) CK(cudaMemcpyAsync(d_dom, domains, b_dom, cudaMemcpyHostToDevice, st));
     k_query_point<<<nblk(n, 128), 128, 0, st>>>(c, n, d_pts, domains ? d_dom : nullptr, max_hits, d_out, d_cnt);
+    CKL(w);
+    CK(cudaMemcpyAsync(out_colliders, d_out, b_out, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_counts, d_cnt, b_cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+int sfg_query_shape_batch(SfgWorld* w, uint32_t n, const SfgShapeQuery* queries, uint32_t max_hits, int32_t* out_colliders, uint32_t* out_counts) {
+    if (!w || (n && (!queries || !out_colliders || !out_counts)) || max_hits == 0) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    static_assert(sizeof(SfgShapeQuery) == sizeof(ShapeQuery), "SfgShapeQuery and the device record must match");
+    for (uint32_t i = 0; i < n; ++i) if (queries[i].kind > SFG_POLY_HEXAGON) return fail(w, SFG_E_INVALID, "unknown collider polygon kind");
+    cudaSetDevice(w->device);
+    CastCtx c;
+    int rc = fill_cast_ctx(w, c);
+    if (rc != SFG_OK) return rc;
+    cudaStream_t st = w->stream;
+    if (w->n_live == 0) { for (uint32_t i = 0; i < n; ++i) out_counts[i] = 0; for (size_t i = 0; i < size_t(n) * max_hits; ++i) out_colliders[i] = -1; return SFG_OK; }
+    const size_t b_q = size_t(n) * sizeof(ShapeQuery), b_out = size_t(n) * max_hits * 4, b_cnt = size_t(n) * 4;
+    CK(w->stage.ensure(b_q + b_out + b_cnt + 64));
+    unsigned char* p = w->stage.p;
+    ShapeQuery* d_q = (ShapeQuery*)p; int* d_out = (int*)(p + b_q); uint32_t* d_cnt = (uint32_t*)(p + b_q + b_out);
+    CK(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, st));
+    k_query_shape<<<nblk(n, 128), 128, 0, st>>>(c, n, d_q, max_hits, d_out, d_cnt);
     CKL(w);
     CK(cudaMemcpyAsync(out_colliders, d_out, b_out, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_counts, d_cnt, b_cnt, cudaMemcpyDeviceToHost, st));

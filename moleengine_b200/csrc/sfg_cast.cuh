@@ -136,4 +136,45 @@ __global__ void __launch_bounds__(128) k_query_point(const __grid_constant__ Cas
     counts[i] = cnt;
 }
 
+// physics.rs:1215-1245 query_shape: colliders whose tick-time box strictly overlaps the shape's box (bvh.rs:292-336, the same
+// iterator the pair search uses), whose layer is in the caller's mask, and for which intersection_check on the CURRENT
+// poses is non-zero. One thread per query; the query box may cover many cells.
+struct ShapeQuery { float x, y, rot_s, rot_b; float p0, p1, circle_r; uint32_t kind; unsigned long long layer_mask; uint32_t domain, reserved; };
+__global__ void __launch_bounds__(128) k_query_shape(const __grid_constant__ CastCtx c, uint32_t n, const ShapeQuery* __restrict__ qs, uint32_t max_hits,
+                                                     int* __restrict__ out, uint32_t* __restrict__ counts) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ShapeQuery q = qs[i];
+    Shape qs_shape; qs_shape.kind = q.kind; qs_shape.p0 = q.p0; qs_shape.p1 = q.p1; qs_shape.r = q.circle_r;
+    const Iso qpose = mkiso(mk(q.x, q.y), mkrot(q.rot_s, q.rot_b));
+    const float4 box = shape_aabb_exact(qs_shape, qpose.t, qpose.r);
+    const GridParams& g = c.g;
+    uint32_t cnt = 0;
+    auto visit = [&](uint32_t cj) {
+        const int4 J = c.SI[cj];
+        if (uint32_t(J.w) != q.domain) return;
+        if (!aabb_overlap(box, c.SA[cj])) return;
+        if (!((q.layer_mask >> (J.z & 0xFF)) & 1ull)) return;
+        Manifold m;
+        intersection_check(qpose, collider_pose(c, J.x, J.y), qs_shape, mkshape(c.CS[J.x]), m);
+        if (m.count == 0) return;
+        if (cnt < max_hits) out[size_t(i) * max_hits + cnt] = J.x;
+        ++cnt;
+    };
+    if (q.domain < g.n_domains && isfinite(box.x) && isfinite(box.y) && isfinite(box.z) && isfinite(box.w)) {
+        for (int l = 0; l < g.n_levels; ++l) {
+            int ix0, iy0, ix1, iy1;
+            cell_of(g, l, box.x, box.y, &ix0, &iy0);
+            cell_of(g, l, box.z, box.w, &ix1, &iy1);
+            for (int y = max(iy0 - 1, 0); y <= min(iy1 + 1, g.ny[l] - 1); ++y) {
+                const uint32_t row = g.base[l] + (q.domain * uint32_t(g.ny[l]) + uint32_t(y)) * uint32_t(g.nx[l]);
+                for (uint32_t cj = c.start[row + max(ix0 - 1, 0)]; cj < c.start[row + min(ix1 + 1, g.nx[l] - 1) + 1]; ++cj) visit(cj);
+            }
+        }
+        for (uint32_t cj = c.start[g.n_cells]; cj < c.start[g.n_cells + 1]; ++cj) visit(cj);
+    }
+    for (uint32_t k = cnt; k < max_hits; ++k) out[size_t(i) * max_hits + k] = -1;
+    counts[i] = cnt;
+}
+
 }  // namespace sfg

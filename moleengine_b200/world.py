@@ -156,6 +156,13 @@ class GpuWorld:
         self._ck(self.lib.sfg_query_point_batch(self.h, len(pts), abi.ptr(pts), abi.ptr(dom), max_hits, abi.ptr(out), abi.ptr(cnt)))
         return out, cnt
 
+    def query_shape_batch(self, queries, max_hits=16):
+        assert queries.dtype == abi.shape_query_dtype
+        out = np.zeros((len(queries), max_hits), np.int32)
+        cnt = np.zeros(len(queries), np.uint32)
+        self._ck(self.lib.sfg_query_shape_batch(self.h, len(queries), abi.ptr(queries), max_hits, abi.ptr(out), abi.ptr(cnt)))
+        return out, cnt
+
     # ---- parity hooks ----------------------------------------------------------------------------
     def debug_pairs(self):
         n = C.c_size_t()

@@ -31,6 +31,7 @@ def load():
         lib.sfo_n_pairs.restype = lib.sfo_n_pair_units.restype = lib.sfo_n_constraint_units.restype = C.c_size_t
         lib.sfo_n_entries.restype = lib.sfo_n_contacts.restype = lib.sfo_n_islands.restype = C.c_size_t
         lib.sfo_query_point.restype = C.c_uint32
+        lib.sfo_query_shape.restype = C.c_uint32
         vp = C.c_void_p
         for name, args in {
             "sfo_destroy": [vp], "sfo_set_tuning": [vp, vp], "sfo_set_mask_matrix": [vp, vp],
@@ -43,7 +44,7 @@ def load():
             "sfo_get_constraint_units": [vp, vp, vp, vp], "sfo_n_entries": [vp], "sfo_get_manifolds": [vp, vp],
             "sfo_n_contacts": [vp], "sfo_get_contacts": [vp, vp, vp], "sfo_get_aabbs": [vp, vp],
             "sfo_cast_batch": [vp, C.c_uint32, vp, vp, C.c_int],
-            "sfo_query_point": [vp, C.c_double, C.c_double, C.c_uint32, vp, C.c_uint32], "sfo_get_stats": [vp, vp], "sfo_n_islands": [vp], "sfo_get_islands": [vp, vp, vp, vp, vp],
+            "sfo_query_point": [vp, C.c_double, C.c_double, C.c_uint32, vp, C.c_uint32], "sfo_get_stats": [vp, vp], "sfo_query_shape": [vp, vp, vp, C.c_uint32], "sfo_n_islands": [vp], "sfo_get_islands": [vp, vp, vp, vp, vp],
             "sfo_intersection_check": [C.c_int, C.c_uint32, vp, vp, vp],
             "sfo_spherecast_collider": [C.c_int, C.c_uint32, vp, vp, vp, vp],
             "sfo_geometry": [C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp], "sfo_clip_edge": [vp, vp, vp],
@@ -161,6 +162,13 @@ class OracleWorld:
     def query_point(self, x, y, domain=0, cap=64):
         out = np.zeros(cap, np.int32)
         n = self.lib.sfo_query_point(self.h, x, y, domain, _p(out), cap)
+        return out[: min(n, cap)]
+
+    def query_shape(self, query, cap=64):
+        """query: one record of moleengine_b200.abi.shape_query_dtype."""
+        out = np.zeros(cap, np.int32)
+        q = np.ascontiguousarray(query).reshape(1)
+        n = self.lib.sfo_query_shape(self.h, _p(q), _p(out), cap)
         return out[: min(n, cap)]
 
     def islands(self):

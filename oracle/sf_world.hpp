@@ -103,6 +103,7 @@ struct IWorld {
     virtual void get_aabbs(double* out4) const = 0;
     virtual void cast_batch(uint32_t n, const SfgRay* rays, double* out6, int use_bvh) const = 0;
     virtual uint32_t query_point(double x, double y, uint32_t domain, int32_t* out, uint32_t cap) const = 0;
+    virtual uint32_t query_shape(const SfgShapeQuery& q, int32_t* out, uint32_t cap) const = 0;
     virtual void get_stats(uint64_t* out8) const = 0;
     virtual size_t n_all_islands() const = 0;
     virtual void get_all_islands(uint64_t* first_body, uint64_t* edge_sum, uint64_t* body_count, uint64_t* flags) const = 0;
@@ -1029,6 +1030,26 @@ public:
             if (!c.alive || c.domain != domain) continue;
             if (!aabbs[ci].contains_point(p)) continue;
             if (point_collider_bool(p, collider_world_pose(c), c.shape)) { if (n < cap) out[n] = int32_t(ci); ++n; }
+        }
+        return n;
+    }
+
+    uint32_t query_shape(const SfgShapeQuery& q, int32_t* out, uint32_t cap) const override {   // physics.rs:1215-1245
+        uint32_t n = 0;
+        Iso2<R> poses[2];
+        Shape<R> shapes[2];
+        poses[0] = {{R(q.x), R(q.y)}, {R(q.rot_s), R(q.rot_b)}};
+        shapes[0] = {q.kind, R(q.p0), R(q.p1), R(q.circle_r)};
+        const AABB<R> box = shapes[0].aabb(poses[0]);
+        for (size_t ci = 0; ci < colliders.size() && ci < aabbs.size(); ++ci) {
+            const auto& c = colliders[ci];
+            if (!c.alive || c.domain != q.domain) continue;
+            if (!aabbs[ci].intersects(box)) continue;                    // bvh.test_aabb: strict overlap with the tick-time box
+            if (!((q.layer_mask >> c.layer) & 1ull)) continue;             // mask.get(coll.layer)
+            poses[1] = collider_world_pose(c); shapes[1] = c.shape;
+            if (intersection_check(poses, shapes, false).is_zero()) continue;
+            if (n < cap) out[n] = int32_t(ci);
+            ++n;
         }
         return n;
     }

@@ -51,5 +51,7 @@ int main(int argc, char** argv) {
     if (hit) printf("ray t %.5f collider_slot %u is_ball %d\n", hit->t, hit->collider.i.slot, int(hit->collider == ball_coll));
     printf("ball_contacts %zu\n", world.contacts_for_collider(ball_coll).size());
     printf("query_point_hits %zu\n", world.query_point(world.entity_set.get_body(ball)->pose.translation).size());
+    sf::ColliderShape probe; probe.polygon = sf::Polygon::Rect; probe.p0 = 0.6; probe.p1 = 0.6; probe.circle_r = 0.0;
+    printf("query_shape_hits %zu\n", world.query_shape(world.entity_set.get_body(ball)->pose, probe, ~0ull).size());
     return 0;
 }

@@ -99,6 +99,27 @@ def test_c5_worlds_and_casts(oracle):
         want_c = sorted(o32.query_point(float(pts[i, 0]), float(pts[i, 1]), int(doms[i])).tolist())
         got_c = sorted(out[i, : cnt[i]].tolist())
         assert got_c == want_c
+    # shape queries (physics.rs:1215-1245): every polygon kind, with and without rounding, a layer mask that hides layer 0
+    nq = 60
+    qs = np.zeros(nq, abi.shape_query_dtype)
+    rng = np.random.default_rng(5)
+    pick = rng.integers(0, len(sc_after["bodies"]), nq)
+    ang = rng.uniform(0, 6.28, nq)
+    qs["x"] = sc_after["bodies"]["x"][pick] + rng.uniform(-0.4, 0.4, nq); qs["y"] = sc_after["bodies"]["y"][pick] + rng.uniform(-0.4, 0.4, nq)
+    qs["rot_s"] = np.cos(ang / 2); qs["rot_b"] = -np.sin(ang / 2)
+    qs["kind"] = np.arange(nq) % 5
+    qs["p0"] = rng.uniform(0.2, 0.9, nq); qs["p1"] = rng.uniform(0.2, 0.9, nq)
+    qs["circle_r"] = np.where(np.arange(nq) % 2 == 0, 0.15, 0.0) + np.where(qs["kind"] == 0, 0.3, 0.0)
+    qs["layer_mask"] = np.where(np.arange(nq) % 7 == 3, np.uint64(0xFFFFFFFFFFFFFFFE), np.uint64(0xFFFFFFFFFFFFFFFF))
+    qs["domain"] = (pick // (bps * bps)).astype(np.uint32)
+    out, cnt = g.query_shape_batch(qs, max_hits=32)
+    total = 0
+    for i in range(nq):
+        want_c = sorted(o32.query_shape(qs[i]).tolist())
+        got_c = sorted(out[i, : cnt[i]].tolist())
+        assert got_c == want_c, (i, got_c, want_c)
+        total += len(want_c)
+    assert total > nq // 2
     g.close()
 
 

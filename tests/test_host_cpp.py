@@ -39,3 +39,4 @@ def test_sandbox_scene_runs(exe):
     assert int(ray[-1]) == 1 and 0.0 < float(ray[2]) < 12.0   # the ray from above hits the ball resting on the stack
     assert int([l for l in lines if l.startswith("ball_contacts")][0].split()[1]) >= 1
     assert int([l for l in lines if l.startswith("query_point_hits")][0].split()[1]) >= 1
+    assert int([l for l in lines if l.startswith("query_shape_hits")][0].split()[1]) >= 1
