@@ -41,7 +41,8 @@ struct TickHeader {            // small device block read back once per tick pha
     Bounds bounds;
     uint32_t n_pairs;
     uint32_t barrier;
-    uint32_t pad[2];
+    uint32_t n_entries;
+    uint32_t pad[1];
 };
 
 }  // namespace
@@ -82,7 +83,8 @@ struct SfgWorld {
     DBuf<TickHeader> hdr;
     // broadphase scratch
     GridParams grid{};
-    uint32_t n_live = 0;
+    uint32_t n_live = 0, n_entries = 0;
+    DBuf<uint32_t> cell_cnt, cell_off;
     DBuf<uint32_t> keys0, keys1, vals0, vals1, sort_tmp, cell_start, warp_counts, scan_tmp;
     DBuf<float4> SA;
     DBuf<int4> SI;
@@ -469,7 +471,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : f2) b->release();
     DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->warp_counts, &w->scan_tmp, &w->U_prio,
                             &w->U_colour, &w->deg, &w->adj_start, &w->cursor, &w->jp_counters, &w->jp_hist, &w->perm0, &w->perm1,
-                            &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour, &w->isl_parent, &w->isl_flags, &w->isl_count, &w->sl_ticks, &w->sl_valid,
+                            &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour, &w->cell_cnt, &w->cell_off, &w->isl_parent, &w->isl_flags, &w->isl_count, &w->sl_ticks, &w->sl_valid,
                             &w->isl_counters};
     for (auto* b : u1) b->release();
     DBuf<int>* i1[] = {&w->rope_next, &w->rope_prev, &w->rp_body, &w->rp_rope};
@@ -671,7 +673,8 @@ void choose_grid(SfgWorld* w, const Bounds& b) {
             const double nx = std::floor(wx / cell) + 1.0, ny = std::floor(wy / cell) + 1.0;
             total += nx * ny * double(g.n_domains);
         }
-        if (total <= cap || c0 > 1e30) {
+        // the proxy grid repeats level 0 and the big-plain levels repeat the coarse ones
+        if (total + total <= cap || c0 > 1e30) {
             g.n_levels = nl;
             uint32_t base = 0;
             for (int l = 0; l < nl; ++l) {
@@ -682,6 +685,12 @@ void choose_grid(SfgWorld* w, const Bounds& b) {
                 base += uint32_t(g.nx[l]) * uint32_t(g.ny[l]) * g.n_domains;
             }
             g.n_cells = base;
+            base += 1;                                   // the huge list
+            for (int l = 1; l < nl; ++l) { g.bp_base[l] = base; base += uint32_t(g.nx[l]) * uint32_t(g.ny[l]) * g.n_domains; }
+            g.bp_base[0] = base;
+            g.proxy_base = base;
+            base += uint32_t(g.nx[0]) * uint32_t(g.ny[0]) * g.n_domains;
+            g.n_keys = base;
             return;
         }
         c0 *= 1.5;
@@ -734,25 +743,32 @@ int broadphase(SfgWorld* w, float frame_dt) {
     if (w->n_live == 0) { memset(&w->grid, 0, sizeof(w->grid)); return SFG_OK; }
     choose_grid(w, h.bounds);
     const GridParams& g = w->grid;
-    // 2. keys + sort
-    CK(w->keys0.ensure(nc)); CK(w->keys1.ensure(nc)); CK(w->vals0.ensure(nc)); CK(w->vals1.ensure(nc));
-    CK(w->sort_tmp.ensure(sort_tmp_words(nc)));
-    k_cell_keys<<<nblk(nc), 256, 0, st>>>(g, nc, w->AABB.p, w->CI.p, w->keys0.p, w->vals0.p);
+    // 2. entries (home + proxies / big-plain, sfg_state.cuh GridParams) + sort
+    CK(w->cell_cnt.ensure(nc + 1)); CK(w->cell_off.ensure(nc + 1)); CK(w->scan_tmp.ensure(scan_tmp_words(nc + 1)));
+    k_cell_count<<<nblk(nc), 256, 0, st>>>(g, nc, w->AABB.p, w->cell_cnt.p);
+    CKL(w); w->launches++;
+    w->launches += scan_exclusive(w->cell_cnt.p, w->cell_off.p, nc, w->scan_tmp.p, &w->hdr.p->n_entries, st);
+    uint32_t ne = 0;
+    CK(cudaMemcpyAsync(&ne, &w->hdr.p->n_entries, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    w->n_entries = ne;
+    if (ne == 0) { w->n_live = 0; return SFG_OK; }
+    CK(w->keys0.ensure(ne)); CK(w->keys1.ensure(ne)); CK(w->vals0.ensure(ne)); CK(w->vals1.ensure(ne));
+    CK(w->sort_tmp.ensure(sort_tmp_words(ne)));
+    k_cell_emit<<<nblk(nc), 256, 0, st>>>(g, nc, w->AABB.p, w->CI.p, w->cell_off.p, w->keys0.p, w->vals0.p);
     CKL(w); w->launches++;
     int bits = 1;
-    while (bits < 32 && (1ull << bits) <= uint64_t(g.n_cells) + 1) ++bits;
-    // dead keys are 0xFFFFFFFF: sorting on the low `bits` bits would mix them in, so give them the top key of the range
-    // (n_cells + 1 fits in `bits` bits by construction) — k_cell_keys already wrote 0xFFFFFFFF; all low bits set >= n_cells + 1.
+    while (bits < 32 && (1ull << bits) <= uint64_t(g.n_keys) + 1) ++bits;
     int launches = 0;
-    const int where = radix_sort_pairs(w->keys0.p, w->vals0.p, w->keys1.p, w->vals1.p, nc, bits, w->sort_tmp.p, st, &launches);
+    const int where = radix_sort_pairs(w->keys0.p, w->vals0.p, w->keys1.p, w->vals1.p, ne, bits, w->sort_tmp.p, st, &launches);
     w->launches += launches;
     const uint32_t* keys = where ? w->keys1.p : w->keys0.p;
     const uint32_t* vals = where ? w->vals1.p : w->vals0.p;
     // 3. sorted copies + cell starts
-    CK(w->SA.ensure(nc)); CK(w->SI.ensure(nc)); CK(w->cell_start.ensure(size_t(g.n_cells) + 2));
-    k_gather_sorted<<<nblk(nc), 256, 0, st>>>(g, nc, keys, vals, w->AABB.p, w->CI.p, w->SA.p, w->SI.p);
+    CK(w->SA.ensure(ne)); CK(w->SI.ensure(ne)); CK(w->cell_start.ensure(size_t(g.n_keys) + 2));
+    k_gather_sorted<<<nblk(ne), 256, 0, st>>>(g, ne, keys, vals, w->AABB.p, w->CI.p, w->SA.p, w->SI.p);
     CKL(w); w->launches++;
-    k_cell_starts<<<nblk(nc + 1), 256, 0, st>>>(keys, nc, g.n_cells, w->cell_start.p);
+    k_cell_starts<<<nblk(ne + 1), 256, 0, st>>>(keys, ne, g.n_keys, w->cell_start.p);
     CKL(w); w->launches++;
     // 4. candidate pairs in one pass; capacity is last tick's count + 25 % (re-run once if it overflows)
     const uint32_t n_warps = (w->n_live + 31) / 32;
@@ -761,7 +777,7 @@ int broadphase(SfgWorld* w, float frame_dt) {
         CK(w->U_ids.ensure(want));
         const uint32_t cap = uint32_t(std::min<size_t>(w->U_ids.cap, 0xFFFFFFFFu));
         CK(cudaMemsetAsync(&w->hdr.p->n_pairs, 0, 4, st));
-        k_pairs<<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, w->cell_start.p, w->d_mask.p, &w->hdr.p->n_pairs, w->U_ids.p, cap);
+        k_pairs<<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, keys, w->cell_start.p, w->d_mask.p, &w->hdr.p->n_pairs, w->U_ids.p, cap);
         CKL(w); w->launches++;
         uint32_t n_pairs = 0;
         CK(cudaMemcpyAsync(&n_pairs, &w->hdr.p->n_pairs, 4, cudaMemcpyDeviceToHost, st));

@@ -107,30 +107,51 @@ SFG_DI void cell_of(const GridParams& g, int l, float cx, float cy, int* ix, int
     *iy = min(max(y, 0), g.ny[l] - 1);
 }
 
-__global__ void __launch_bounds__(256) k_cell_keys(const __grid_constant__ GridParams g, uint32_t n_colls, const float4* __restrict__ AABB,
-                                                   const int4* __restrict__ CI, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+SFG_DI uint32_t cell_key(const GridParams& g, uint32_t base, int l, uint32_t domain, int ix, int iy) {
+    return base + (domain * uint32_t(g.ny[l]) + uint32_t(iy)) * uint32_t(g.nx[l]) + uint32_t(ix);
+}
+// entries a collider contributes to the sorted list: its home entry, plus proxies or a big-plain entry if it is large
+SFG_DI uint32_t cell_entry_count(const GridParams& g, float4 b, int* level, int* ix0, int* iy0, int* ix1, int* iy1) {
+    const float ext = fmaxf(b.z - b.x, b.w - b.y);
+    const int l = level_of(g, ext);
+    *level = l;
+    if (l == 0 || l >= g.n_levels) return 1u;
+    cell_of(g, 0, b.x, b.y, ix0, iy0);
+    cell_of(g, 0, b.z, b.w, ix1, iy1);
+    const uint32_t n = uint32_t(*ix1 - *ix0 + 1) * uint32_t(*iy1 - *iy0 + 1);
+    return n <= RASTER_MAX ? 1u + n : 2u;
+}
+__global__ void __launch_bounds__(256) k_cell_count(const __grid_constant__ GridParams g, uint32_t n_colls, const float4* __restrict__ AABB,
+                                                    uint32_t* __restrict__ counts) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_colls) return;
-    const int4 ci = CI[i];
-    uint32_t key = 0xFFFFFFFFu;
-    if (ci.w & CF_ALIVE) {
-        const float4 b = AABB[i];
-        const float ext = fmaxf(b.z - b.x, b.w - b.y);
-        if (isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w)) {
-            const int l = level_of(g, ext);
-            if (l >= g.n_levels) key = g.n_cells;
-            else {
-                int ix, iy;
-                cell_of(g, l, 0.5f * (b.x + b.z), 0.5f * (b.y + b.w), &ix, &iy);
-                key = g.base[l] + (uint32_t(ci.z) * uint32_t(g.ny[l]) + uint32_t(iy)) * uint32_t(g.nx[l]) + uint32_t(ix);
-            }
-        }
-    }
-    keys[i] = key;
-    vals[i] = i;
+    const float4 b = AABB[i];          // k_aabb writes NaN boxes for colliders that sit the tick out
+    uint32_t n = 0;
+    if (isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w)) { int l, a0, a1, a2, a3; n = cell_entry_count(g, b, &l, &a0, &a1, &a2, &a3); }
+    counts[i] = n;
+}
+__global__ void __launch_bounds__(256) k_cell_emit(const __grid_constant__ GridParams g, uint32_t n_colls, const float4* __restrict__ AABB,
+                                                   const int4* __restrict__ CI, const uint32_t* __restrict__ offsets,
+                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_colls) return;
+    const float4 b = AABB[i];
+    if (!(isfinite(b.x) && isfinite(b.y) && isfinite(b.z) && isfinite(b.w))) return;
+    int l, ix0, iy0, ix1, iy1;
+    const uint32_t n = cell_entry_count(g, b, &l, &ix0, &iy0, &ix1, &iy1);
+    const uint32_t domain = uint32_t(CI[i].z);
+    uint32_t o = offsets[i];
+    if (l >= g.n_levels) { keys[o] = g.n_cells; vals[o] = i; return; }
+    int ix, iy;
+    cell_of(g, l, 0.5f * (b.x + b.z), 0.5f * (b.y + b.w), &ix, &iy);
+    keys[o] = cell_key(g, g.base[l], l, domain, ix, iy); vals[o] = i; ++o;
+    if (n == 1u) return;
+    if (n == 2u) { keys[o] = cell_key(g, g.bp_base[l], l, domain, ix, iy); vals[o] = i; return; }
+    for (int y = iy0; y <= iy1; ++y)
+        for (int x = ix0; x <= ix1; ++x) { keys[o] = cell_key(g, g.proxy_base, 0, domain, x, y); vals[o] = i; ++o; }
 }
 
-// sorted copies so the pair search streams instead of gathering: SA = box, SI = (slot, body, layer | level << 8, domain)
+// sorted copies so the pair search streams instead of gathering: SA = box, SI = (slot, body, layer | level << 8 | type << 16, domain)
 __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ GridParams g, uint32_t n, const uint32_t* __restrict__ keys,
                                                        const uint32_t* __restrict__ vals, const float4* __restrict__ AABB,
                                                        const int4* __restrict__ CI, float4* __restrict__ SA, int4* __restrict__ SI) {
@@ -140,13 +161,16 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ G
     const uint32_t key = keys[j];
     const int4 ci = CI[slot];
     int level = g.n_levels;
-    for (int l = 0; l < g.n_levels; ++l) if (key >= g.base[l]) level = l;
-    if (key >= g.n_cells) level = g.n_levels;
+    uint32_t type = ET_HOME;
+    if (key >= g.proxy_base) { type = ET_PROXY; level = 0; }
+    else if (key > g.n_cells) { type = ET_BIG_PLAIN; for (int l = 1; l < g.n_levels; ++l) if (key >= g.bp_base[l]) level = l; }
+    else if (key < g.n_cells) { for (int l = 0; l < g.n_levels; ++l) if (key >= g.base[l]) level = l; }
     SA[j] = AABB[slot];
-    SI[j] = make_int4(int(slot), ci.x, ci.y | (level << 8), ci.z);
+    SI[j] = make_int4(int(slot), ci.x, ci.y | (level << 8) | int(type << 16), ci.z);
 }
 
 // start[c] = first sorted index whose key >= c, for c in [0, n_cells + 1]; start[n_cells + 1] = number of live entries
+// (n_cells here = the number of keys, g.n_keys)
 __global__ void __launch_bounds__(256) k_cell_starts(const uint32_t* __restrict__ keys, uint32_t n, uint32_t n_cells, uint32_t* __restrict__ start) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j > n) return;
@@ -162,14 +186,17 @@ __global__ void k_fill_u32(uint32_t* p, uint32_t n, uint32_t v) {
     if (i < n) p[i] = v;
 }
 
-// One lane per collider (in cell-sorted order). Same-level partners are searched in the FORWARD half
-// neighbourhood only (rest of the own cell + cell x+1, then cells x-1..x+1 of row y+1): sorted order is a
-// total order, so every unordered pair inside a 3x3 block is met exactly once. Coarser levels are searched
-// 3x3 (a coarser collider never searches down). Hits are compacted with a warp ballot into a per-warp
-// shared-memory staging buffer and flushed 32+ at a time behind ONE atomic reservation.
+// One lane per HOME entry (in cell-sorted order; home entries sort before the big-plain and proxy ranges). Same-level
+// partners are searched in the FORWARD half neighbourhood only (rest of the own cell + cell x+1, then cells x-1..x+1 of row
+// y+1): sorted order is a total order, so every unordered pair inside a 3x3 block is met exactly once. A small (level-0)
+// collider then looks for large partners in the proxy grid (3x3 around its own cell; a large collider has a proxy in every
+// level-0 cell its box overlaps, and the pair is taken only from the proxy whose cell holds the lower-left corner of the two
+// boxes' intersection, so it is met exactly once) and in the big-plain levels (3x3); a large collider searches the levels
+// from its own upwards. Nobody searches downwards. Hits are compacted with a warp ballot into a per-warp shared-memory
+// staging buffer and flushed 32+ at a time behind ONE atomic reservation.
 constexpr int PAIR_STAGE = 64;
 __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParams g, uint32_t n_live, const float4* __restrict__ SA,
-                                               const int4* __restrict__ SI, const uint32_t* __restrict__ start,
+                                               const int4* __restrict__ SI, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ start,
                                                const unsigned long long* __restrict__ mask, uint32_t* __restrict__ cursor,
                                                uint2* __restrict__ pairs, uint32_t capacity) {
     __shared__ uint2 stage[8][PAIR_STAGE];
@@ -181,12 +208,29 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
     int4 I = make_int4(0, -1, 0, 0);
     if (active) { A = SA[j]; I = SI[j]; }
     const int my_level = (I.z >> 8) & 0xFF, my_layer = I.z & 0xFF;
+    const int nl = g.n_levels;
     const float cx = 0.5f * (A.x + A.z), cy = 0.5f * (A.y + A.w);
     const unsigned long long my_mask = active ? mask[my_layer] : 0ull;
-    // segments: own level: 0 = own row forward, 1 = next row; coarser level l: 3 rows each; last = huge list
-    const int n_own = my_level < g.n_levels ? 2 : 0;
-    const int n_seg = active ? (n_own + max(g.n_levels - my_level - 1, 0) * 3 + 1) : 0;
-    int seg = 0;
+    // Segments of a lane, in order: 0, 1 = own level (rest of the own cell + cell x+1, then cells x-1..x+1 of row y+1);
+    // 2, 3, 4 = proxy rows y-1, y, y+1 (small colliders only); then the RARE ranges: 3 rows per populated coarser level
+    // (big-plain levels for a small collider, levels above its own for a large one) and the huge list. In most worlds
+    // every large collider is rasterised and nothing is huge, so the rare mask is 0 and a lane has 5 cheap segments.
+    const bool small = my_level == 0 && nl > 0, huge = my_level >= nl;
+    uint32_t rare_mask = 0;
+    if (active) {
+        for (int l = small ? 1 : my_level + 1; l < nl; ++l) {
+            const uint32_t kb = small ? g.bp_base[l] : g.base[l], ke = kb + uint32_t(g.nx[l]) * uint32_t(g.ny[l]) * g.n_domains;
+            if (__ldg(start + ke) > __ldg(start + kb)) rare_mask |= 1u << l;
+        }
+        const uint32_t h0 = huge ? j + 1 : __ldg(start + g.n_cells);
+        if (__ldg(start + g.n_cells + 1) > h0) rare_mask |= 1u << 31;
+    }
+    int ix0 = 0, iy0 = 0;
+    if (active && !huge) cell_of(g, my_level, cx, cy, &ix0, &iy0);
+    const int own_nx = huge ? 1 : g.nx[my_level], own_ny = huge ? 1 : g.ny[my_level];
+    const uint32_t own_row = huge ? 0u : g.base[my_level] + (uint32_t(I.w) * uint32_t(own_ny) + uint32_t(iy0)) * uint32_t(own_nx);
+    int seg = active ? (huge ? 5 : 0) : 1000, rare_sub = 0;
+    bool seg_proxy = false, exhausted = !active;
     uint32_t cur = 0, end = 0;
     uint32_t n_buf = 0;
     const uint32_t lt = (1u << lane) - 1u;
@@ -198,28 +242,36 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
         __syncwarp();
         n_buf = 0;
     };
+    auto rows3 = [&](uint32_t base, int l, int dy) {       // cells x-1..x+1 of row y+dy at level l, key range starting at `base`
+        int ix, iy;
+        cell_of(g, l, cx, cy, &ix, &iy);
+        const int y = iy + dy;
+        if (y >= 0 && y < g.ny[l]) {
+            const uint32_t row = base + (uint32_t(I.w) * uint32_t(g.ny[l]) + uint32_t(y)) * uint32_t(g.nx[l]);
+            cur = start[row + max(ix - 1, 0)]; end = start[row + min(ix + 1, g.nx[l] - 1) + 1];
+        } else { cur = 0; end = 0; }
+    };
     for (;;) {
-        while (cur >= end && seg < n_seg) {
-            if (seg == n_seg - 1) {   // huge list; huge-vs-huge forward only
-                cur = my_level >= g.n_levels ? j + 1 : start[g.n_cells]; end = start[g.n_cells + 1];
-            } else if (seg < n_own) {
-                int ix, iy;
-                cell_of(g, my_level, cx, cy, &ix, &iy);
-                const int nx = g.nx[my_level], ny = g.ny[my_level];
-                const uint32_t row = g.base[my_level] + (uint32_t(I.w) * uint32_t(ny) + uint32_t(iy)) * uint32_t(nx);
-                if (seg == 0) { cur = j + 1; end = start[row + min(ix + 1, nx - 1) + 1]; }
-                else if (iy + 1 < ny) { cur = start[row + nx + max(ix - 1, 0)]; end = start[row + nx + min(ix + 1, nx - 1) + 1]; }
-                else { cur = 0; end = 0; }
-            } else {
-                const int k = seg - n_own;
-                const int l = my_level + 1 + k / 3, dy = k % 3 - 1;
-                int ix, iy;
-                cell_of(g, l, cx, cy, &ix, &iy);
-                const int y = iy + dy;
-                if (y >= 0 && y < g.ny[l]) {
-                    const uint32_t row = g.base[l] + (uint32_t(I.w) * uint32_t(g.ny[l]) + uint32_t(y)) * uint32_t(g.nx[l]);
-                    cur = start[row + max(ix - 1, 0)]; end = start[row + min(ix + 1, g.nx[l] - 1) + 1];
-                } else { cur = 0; end = 0; }
+        while (cur >= end && !exhausted) {
+            seg_proxy = false;
+            if (seg == 0) { cur = j + 1; end = start[own_row + min(ix0 + 1, own_nx - 1) + 1]; }
+            else if (seg == 1) {
+                if (iy0 + 1 < own_ny) { cur = start[own_row + own_nx + max(ix0 - 1, 0)]; end = start[own_row + own_nx + min(ix0 + 1, own_nx - 1) + 1]; }
+            } else if (seg < 5) {
+                const int y = iy0 + seg - 3;                 // level 0: the proxy grid has the geometry of the own level
+                if (small && y >= 0 && y < own_ny) {
+                    const uint32_t row = g.proxy_base + (uint32_t(I.w) * uint32_t(own_ny) + uint32_t(y)) * uint32_t(own_nx);
+                    cur = start[row + max(ix0 - 1, 0)]; end = start[row + min(ix0 + 1, own_nx - 1) + 1];
+                    seg_proxy = true;
+                }
+            } else if (rare_mask == 0u) exhausted = true;
+            else {
+                const int l = __ffs(int(rare_mask)) - 1;
+                if (l == 31) { cur = huge ? j + 1 : start[g.n_cells]; end = start[g.n_cells + 1]; rare_mask = 0u; }   // huge-vs-huge forward only
+                else {
+                    rows3(small ? g.bp_base[l] : g.base[l], l, rare_sub - 1);
+                    if (++rare_sub == 3) { rare_sub = 0; rare_mask &= ~(1u << l); }
+                }
             }
             ++seg;
         }
@@ -229,9 +281,16 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
         uint32_t hi = 0, lo = 0;
         if (more) {
             const uint32_t cj = cur++;
-            if (aabb_overlap(A, __ldg(SA + cj))) {       // cells of one key share the domain; only the huge list mixes them
+            const float4 B = __ldg(SA + cj);
+            if (aabb_overlap(A, B)) {       // cells of one key share the domain; only the huge list mixes them
                 const int4 J = __ldg(SI + cj);
-                if (J.w == I.w) {
+                bool take = J.w == I.w;
+                if (take && seg_proxy) {    // only from the proxy in the cell of the intersection's lower-left corner
+                    int mx, my;
+                    cell_of(g, 0, fmaxf(A.x, B.x), fmaxf(A.y, B.y), &mx, &my);
+                    take = __ldg(keys + cj) == cell_key(g, g.proxy_base, 0, uint32_t(I.w), mx, my);
+                }
+                if (take) {
                     const bool i_later = uint32_t(I.x) > uint32_t(J.x);
                     hi = i_later ? uint32_t(I.x) : uint32_t(J.x); lo = i_later ? uint32_t(J.x) : uint32_t(I.x);
                     const int l_lo = i_later ? (J.z & 0xFF) : my_layer;

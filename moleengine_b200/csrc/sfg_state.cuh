@@ -40,9 +40,18 @@ struct GridParams {
     float inv_cell[MAX_LEVELS];
     float cell[MAX_LEVELS];
     int nx[MAX_LEVELS], ny[MAX_LEVELS];
-    uint32_t base[MAX_LEVELS];    // first key of each level
+    uint32_t base[MAX_LEVELS];    // first key of each level: level 0 = all small colliders, level l >= 1 = ALL colliders of that size class
     uint32_t n_cells;             // key n_cells = huge list; 0xFFFFFFFF = dead
+    // Large colliders are found by small ones through one of two extra key ranges, never through base[l >= 1]:
+    //   proxy grid (level-0 geometry): one entry per level-0 cell a large collider's box overlaps ("rasterised"), so a long
+    //   thin platform costs its few neighbours a 3x3 look-up instead of costing every body under a coarse cell a box test;
+    //   big-plain levels: large colliders that would need more than RASTER_MAX proxies, same cells as base[l].
+    uint32_t bp_base[MAX_LEVELS]; // first key of big-plain level l (l >= 1)
+    uint32_t proxy_base;          // first key of the proxy grid
+    uint32_t n_keys;              // one past the last key
 };
+constexpr uint32_t RASTER_MAX = 2048;
+enum : uint32_t { ET_HOME = 0u, ET_BIG_PLAIN = 1u, ET_PROXY = 2u };   // entry type, kept in SI.z bits 16..17
 
 struct Bounds {                   // filled by k_aabb with ordered-int atomics
     int min_x, min_y, max_x, max_y;   // float bits mapped to ordered ints
