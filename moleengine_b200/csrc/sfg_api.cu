@@ -94,7 +94,7 @@ struct SfgWorld {
     DBuf<uint2> U_ids;
     DBuf<int2> U_ub;
     DBuf<uint2> adj2;   // body -> (unit, priority)
-    DBuf<uint32_t> U_prio, U_colour, deg, adj_start, cursor, jp_counters, jp_hist, perm0, perm1, ckey0, ckey1;
+    DBuf<uint32_t> U_prio, U_colour, deg, adj_start, cursor, jp_counters, perm0, perm1, ckey0, ckey1;
     DBuf<float4> H, S, G0, G1, L0, L1, M0, M1, M2;
     DBuf<float2> LN;
     DBuf<float> RC;
@@ -364,7 +364,7 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     constexpr uint32_t HIST_CAP = 65536;
     CK(w->adj_start.ensure(nb + 2)); CK(w->cursor.ensure(nb + 1)); CK(w->adj2.ensure(size_t(n_units) * 2 + 1));
     CK(w->scan_tmp.ensure(scan_tmp_words(nb + 1)));
-    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(16)); CK(w->jp_hist.ensure(HIST_CAP));
+    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(16 + HIST_CAP));   // [0, 16) control words, then units per colour
     CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units)); CK(w->perm0.ensure(n_units)); CK(w->perm1.ensure(n_units));
     CK(w->sort_tmp.ensure(sort_tmp_words(n_units)));
     int per_sm = 0;
@@ -386,25 +386,28 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         order = where ? w->perm1.p : w->perm0.p;
     }
     CK(cudaMemsetAsync(colour.p, 0xFF, size_t(n_units) * 4, st));
-    CK(cudaMemsetAsync(w->jp_counters.p, 0, 16 * 4, st));
-    CK(cudaMemsetAsync(w->jp_hist.p, 0, HIST_CAP * 4, st));
+    CK(cudaMemsetAsync(w->jp_counters.p, 0, (16 + HIST_CAP) * 4, st));
     {
         uint32_t hist_cap = HIST_CAP;
         const uint32_t* adj_start = w->adj_start.p; const uint2* adj = w->adj2.p;
-        uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_hist.p;
+        uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_counters.p + 16;
         void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &ctrl, &hist, &hist_cap};
         CK(cudaLaunchCooperativeKernel((void*)k_colour_dataflow, dim3(grid), dim3(1024), args, 0, st));
         w->launches++;
     }
-    uint32_t jp_ctrl[8] = {0};
-    CK(cudaMemcpyAsync(jp_ctrl, w->jp_counters.p, sizeof(jp_ctrl), cudaMemcpyDeviceToHost, st));
+    // one read-back for the control words and the first 64 colours (a second one only if there are more)
+    uint32_t head[16 + 64];
+    CK(cudaMemcpyAsync(head, w->jp_counters.p, sizeof(head), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    const uint32_t n_colours = jp_ctrl[1];
-    w->stats_jp_rounds = jp_ctrl[4];
+    const uint32_t n_colours = head[1];
+    w->stats_jp_rounds = head[4];
     if (n_colours == 0 || n_colours > HIST_CAP) return fail(w, SFG_E_CAPACITY, "colouring did not converge or needs > 65536 colours");
     std::vector<uint32_t> hist(n_colours);
-    CK(cudaMemcpyAsync(hist.data(), w->jp_hist.p, size_t(n_colours) * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    memcpy(hist.data(), head + 16, std::min<size_t>(n_colours, 64) * 4);
+    if (n_colours > 64) {
+        CK(cudaMemcpyAsync(hist.data() + 64, w->jp_counters.p + 16 + 64, size_t(n_colours - 64) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
     colour_start.resize(n_colours + 1);
     uint32_t run = 0;
     for (uint32_t c = 0; c < n_colours; ++c) { colour_start[c] = run; run += hist[c]; }
@@ -470,7 +473,7 @@ void sfg_world_destroy(SfgWorld* w) {
     DBuf<float2>* f2[] = {&w->EA, &w->PCD, &w->LAT, &w->LN};
     for (auto* b : f2) b->release();
     DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->warp_counts, &w->scan_tmp, &w->U_prio,
-                            &w->U_colour, &w->deg, &w->adj_start, &w->cursor, &w->jp_counters, &w->jp_hist, &w->perm0, &w->perm1,
+                            &w->U_colour, &w->deg, &w->adj_start, &w->cursor, &w->jp_counters, &w->perm0, &w->perm1,
                             &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour, &w->cell_cnt, &w->cell_off, &w->isl_parent, &w->isl_flags, &w->isl_count, &w->sl_ticks, &w->sl_valid,
                             &w->isl_counters};
     for (auto* b : u1) b->release();

@@ -173,12 +173,22 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ G
 // (n_cells here = the number of keys, g.n_keys)
 __global__ void __launch_bounds__(256) k_cell_starts(const uint32_t* __restrict__ keys, uint32_t n, uint32_t n_cells, uint32_t* __restrict__ start) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > n) return;
-    // virtual key n_cells + 1 after the last live entry
-    uint32_t k = j < n ? min(keys[j], n_cells + 1) : n_cells + 1;
-    uint32_t kp = j == 0 ? 0u : min(keys[j - 1], n_cells + 1) + 1u;
-    if (j == 0) kp = 0u;
-    for (uint32_t cidx = kp; cidx <= k; ++cidx) start[cidx] = j;
+    const uint32_t lane = threadIdx.x & 31u;
+    // entry j owns the keys (key[j - 1], key[j]]; a virtual key n_cells + 1 follows the last live entry
+    uint32_t k = 0, kp = 1;                     // empty range for threads past the end
+    if (j <= n) {
+        k = j < n ? min(keys[j], n_cells + 1) : n_cells + 1;
+        kp = j == 0 ? 0u : min(keys[j - 1], n_cells + 1) + 1u;
+    }
+    const bool wide = k + 1u > kp + 32u;       // a run of empty cells (an unpopulated level): the whole warp fills it
+    if (!wide) for (uint32_t cidx = kp; cidx <= k; ++cidx) start[cidx] = j;
+    uint32_t todo = __ballot_sync(0xFFFFFFFFu, wide);
+    while (todo) {
+        const int src = __ffs(int(todo)) - 1;
+        const uint32_t a = __shfl_sync(0xFFFFFFFFu, kp, src), b = __shfl_sync(0xFFFFFFFFu, k, src), v = __shfl_sync(0xFFFFFFFFu, j, src);
+        for (uint32_t cidx = a + lane; cidx <= b; cidx += 32u) start[cidx] = v;
+        todo &= todo - 1u;
+    }
 }
 // empty world: every start is 0
 __global__ void k_fill_u32(uint32_t* p, uint32_t n, uint32_t v) {

@@ -43,15 +43,26 @@ __device__ __forceinline__ uint32_t uf_find(const uint32_t* parent, uint32_t x) 
     while ((p = __ldcg(parent + x)) != x) x = p;
     return x;
 }
+// find with path halving: every node on the way is re-pointed at its grandparent. Racing writers only ever store an
+// ancestor of the node, so the forest stays a forest with the same roots.
+__device__ __forceinline__ uint32_t uf_find_halve(uint32_t* parent, uint32_t x) {
+    uint32_t p = __ldcg(parent + x);
+    while (p != x) {
+        const uint32_t gp = __ldcg(parent + p);
+        if (gp != p) __stcg(parent + x, gp);
+        x = p; p = gp;
+    }
+    return x;
+}
 // hook the larger root under the smaller one: the final root of a component is its smallest slot
 __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
-    uint32_t ra = uf_find(parent, a), rb = uf_find(parent, b);
+    uint32_t ra = uf_find_halve(parent, a), rb = uf_find_halve(parent, b);
     while (ra != rb) {
         if (ra < rb) { const uint32_t t = ra; ra = rb; rb = t; }
         const uint32_t old = atomicCAS(parent + ra, ra, rb);
         if (old == ra) return;
-        ra = uf_find(parent, old);
-        rb = uf_find(parent, rb);
+        ra = uf_find_halve(parent, old);
+        rb = uf_find_halve(parent, rb);
     }
 }
 
