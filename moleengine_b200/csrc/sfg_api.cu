@@ -29,7 +29,7 @@ struct DBuf {
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
-        size_t want = n + n / 4 + 64;
+        size_t want = n + n / 2 + 64;   // 50 % headroom: cudaFree + cudaMalloc stall the tick, and pair counts creep up as piles form
         cudaError_t e = cudaMalloc(&p, want * sizeof(T));
         if (e == cudaSuccess) cap = want;
         return e;

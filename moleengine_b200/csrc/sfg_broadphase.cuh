@@ -436,34 +436,61 @@ __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, cons
         int2 b = make_int2(-1, -1);
         uint2 iu = make_uint2(0, 0);
         if (!done) { u = order[idx]; b = ub[u]; pu = prio[u]; iu = ids[u]; }
+        // the scan keeps its place across retries: side, position in that body's list, colours 0..63 seen so far
+        int side = 0;
+        uint32_t a = 0, a1 = 0;
+        unsigned long long used = 0ull;
+        bool beyond = false, side_open = false;
         while (__any_sync(0xFFFFFFFFu, !done)) {
             if (!done) {
                 bool ready = true;
-                uint32_t result = 0;
-                for (uint32_t win = 0; ready; win += 64) {   // window of 64 colours at a time
-                    unsigned long long used = 0ull;
-                    bool beyond = false;
-                    for (int side = 0; side < 2 && ready; ++side) {
+                while (side < 2) {
+                    if (!side_open) {
                         const int body = side ? b.y : b.x;
-                        if (body < 0) continue;
-                        const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
-                        for (uint32_t a = a0; a < a1; ++a) {
-                            const uint2 vp = adj[a];
-                            if (vp.x == u) continue;
-                            bool higher = vp.y > pu;
-                            if (vp.y == pu) { const uint2 iv = ids[vp.x]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
-                            if (!higher) continue;
-                            const uint32_t cv = ld_relaxed(colour + vp.x);
-                            if (cv == UNCOLOURED) { ready = false; break; }
-                            if (cv >= win && cv < win + 64) used |= 1ull << (cv - win);
-                            else if (cv >= win + 64) beyond = true;
-                        }
+                        if (body < 0) { ++side; continue; }
+                        a = adj_start[body]; a1 = adj_start[body + 1]; side_open = true;
+                    }
+                    for (; a < a1; ++a) {
+                        const uint2 vp = adj[a];
+                        if (vp.x == u) continue;
+                        bool higher = vp.y > pu;
+                        if (vp.y == pu) { const uint2 iv = ids[vp.x]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
+                        if (!higher) continue;
+                        const uint32_t cv = ld_relaxed(colour + vp.x);
+                        if (cv == UNCOLOURED) { ready = false; break; }
+                        if (cv < 64) used |= 1ull << cv; else beyond = true;
                     }
                     if (!ready) break;
-                    if (used != ~0ull) { result = win + uint32_t(__ffsll((long long)~used) - 1); break; }
-                    if (!beyond) { result = win + 64; break; }
+                    ++side; side_open = false;
                 }
                 if (ready) {
+                    uint32_t result;
+                    if (used != ~0ull) result = uint32_t(__ffsll((long long)~used) - 1);
+                    else if (!beyond) result = 64;
+                    else {
+                        // more than 64 colours around this unit (rare): every higher neighbour is coloured by now, rescan by windows
+                        result = 0;
+                        for (uint32_t win = 64;; win += 64) {
+                            unsigned long long w_used = 0ull;
+                            bool w_beyond = false;
+                            for (int sd = 0; sd < 2; ++sd) {
+                                const int body = sd ? b.y : b.x;
+                                if (body < 0) continue;
+                                for (uint32_t q = adj_start[body], q1 = adj_start[body + 1]; q < q1; ++q) {
+                                    const uint2 vp = adj[q];
+                                    if (vp.x == u) continue;
+                                    bool higher = vp.y > pu;
+                                    if (vp.y == pu) { const uint2 iv = ids[vp.x]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
+                                    if (!higher) continue;
+                                    const uint32_t cv = ld_relaxed(colour + vp.x);
+                                    if (cv >= win && cv < win + 64) w_used |= 1ull << (cv - win);
+                                    else if (cv >= win + 64) w_beyond = true;
+                                }
+                            }
+                            if (w_used != ~0ull) { result = win + uint32_t(__ffsll((long long)~w_used) - 1); break; }
+                            if (!w_beyond) { result = win + 64; break; }
+                        }
+                    }
                     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(colour + u), "r"(result) : "memory");
                     if (result < 64) atomicAdd(&s_hist[result], 1u);
                     else if (result < hist_cap) atomicAdd(hist + result, 1u);

@@ -115,8 +115,21 @@ __global__ void __launch_bounds__(256) k_isl_sums(IslandCtx c) {
     unsigned long long add;
     if (a >= 0 && b >= 0) add = 2ull * ((unsigned long long)(a) + 1ull) * ((unsigned long long)(b) + 1ull);
     else add = (unsigned long long)(a >= 0 ? a : b) + 1ull;
-    atomicAdd(c.isl_sum + root, add);
-    if (ns) atomicOr(c.isl_flags + root, IF_NO_SLEEP);
+    // one atomic per group of lanes that share a root (a pile is ONE island: 32 lanes, one address)
+    const uint32_t act = __activemask();
+    const uint32_t peers = __match_any_sync(act, root);
+    const int leader = __ffs(int(peers)) - 1, lane = int(threadIdx.x & 31u);
+    unsigned long long total = 0ull;
+    uint32_t any_ns = 0u;
+    for (uint32_t m = peers; m; m &= m - 1u) {
+        const int src = __ffs(int(m)) - 1;
+        total += __shfl_sync(peers, add, src);
+        any_ns |= __shfl_sync(peers, ns, src);
+    }
+    if (lane == leader) {
+        atomicAdd(c.isl_sum + root, total);
+        if (any_ns && !(__ldcg(c.isl_flags + root) & IF_NO_SLEEP)) atomicOr(c.isl_flags + root, IF_NO_SLEEP);
+    }
 }
 // per body: final label, island size, "moved between frames" test on the incoming velocities (physics.rs:722-731)
 __global__ void __launch_bounds__(256) k_isl_bodies_pre(IslandCtx c) {
@@ -125,9 +138,15 @@ __global__ void __launch_bounds__(256) k_isl_bodies_pre(IslandCtx c) {
     if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE)) { c.sl_valid[b] = 0u; return; }
     const uint32_t root = uf_find(c.parent, b);
     c.parent[b] = root;
-    atomicAdd(c.isl_count + root, 1u);
     const float4 v = c.V[b];
-    if (v.x * v.x + v.y * v.y + v.z * v.z >= c.sleep_vel_threshold) atomicOr(c.isl_flags + root, IF_MOVING);
+    const uint32_t moving = v.x * v.x + v.y * v.y + v.z * v.z >= c.sleep_vel_threshold ? 1u : 0u;
+    const uint32_t act = __activemask();
+    const uint32_t peers = __match_any_sync(act, root);
+    const uint32_t peers_moving = __ballot_sync(act, moving != 0u) & peers;
+    if (int(threadIdx.x & 31u) == __ffs(int(peers)) - 1) {
+        atomicAdd(c.isl_count + root, uint32_t(__popc(peers)));
+        if (peers_moving && !(__ldcg(c.isl_flags + root) & IF_MOVING)) atomicOr(c.isl_flags + root, IF_MOVING);
+    }
     if (root != b) c.sl_valid[b] = 0u;     // a record is only ever found through the island whose first_body it names
 }
 // per island root: the retain() of physics.rs:714-737 and the record clean-up of :739
@@ -163,7 +182,10 @@ __global__ void __launch_bounds__(256) k_isl_bodies_post(IslandCtx c) {
     const uint32_t fl = __float_as_uint(c.MI[b].z);
     if (!(fl & BF_ALIVE) || (fl & BF_ASLEEP)) return;
     const float4 v = c.V[b];
-    if (!(v.x * v.x + v.y * v.y + v.z * v.z < c.sleep_vel_threshold)) atomicOr(c.isl_flags + c.parent[b], IF_FAST);
+    if (!(v.x * v.x + v.y * v.y + v.z * v.z < c.sleep_vel_threshold)) {
+        const uint32_t root = c.parent[b];
+        if (!(__ldcg(c.isl_flags + root) & IF_FAST)) atomicOr(c.isl_flags + root, IF_FAST);
+    }
 }
 __global__ void __launch_bounds__(256) k_isl_fall_asleep(IslandCtx c) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
