@@ -196,14 +196,18 @@ def main():
     # ---------------- end-to-end arm: pinned host poses in -> tick -> poses out, through the C ABI.
     # This is Game::physics_tick (game.rs:297-303): sync_hecs_to_physics writes f32 poses into the world, tick,
     # sync_physics_to_hecs reads them back (hecs_sync.rs:121-227) -> sfg_set_poses / sfg_tick / sfg_get_poses.
+    # The scene is reloaded and warmed up again so that both arms time the SAME ticks of the scene (bodies land on the
+    # shelves as it runs: later ticks carry more contacts and cost more than earlier ones).
     host = torch.empty(nb * 16, dtype=torch.uint8).pin_memory()
     host_np = host.numpy().view(np.float32).reshape(nb, 4)
     lib, h = g.lib, g.h
+    assert lib.sfg_world_clear(h) == 0
+    g.load_scene(sc)
     assert lib.sfg_get_poses(h, 0, nb, abi.ptr(host_np)) == 0
-    for _ in range(3):
+    for _ in range(args.warmup):
         lib.sfg_set_poses(h, 0, nb, abi.ptr(host_np)); g.tick(FRAME_DT, None, ff); lib.sfg_get_poses(h, 0, nb, abi.ptr(host_np))
     barrier()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = args.steps
     per_step = []
     for _ in range(e2e_steps):
         t0 = time.perf_counter()
