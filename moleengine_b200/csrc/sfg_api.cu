@@ -115,7 +115,7 @@ struct SfgWorld {
     DBuf<SfgRay> d_rays;
     DBuf<SfgCastHit> d_hits;
     // islands + sleeping (sfg_islands.cuh)
-    DBuf<uint32_t> isl_parent, isl_flags, isl_count, sl_ticks, sl_valid, isl_counters;
+    DBuf<uint32_t> isl_parent, isl_first, isl_flags, isl_count, sl_ticks, sl_valid, isl_counters;
     DBuf<unsigned long long> isl_sum, sl_sum;
     DBuf<ContactRec> ct[2];       // contact list of the last tick (with retention for sleeping islands), double-buffered
     uint32_t ct_n = 0, ct_cur = 0;
@@ -474,7 +474,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : f2) b->release();
     DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->warp_counts, &w->scan_tmp, &w->U_prio,
                             &w->U_colour, &w->deg, &w->adj_start, &w->cursor, &w->jp_counters, &w->perm0, &w->perm1,
-                            &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour, &w->cell_cnt, &w->cell_off, &w->isl_parent, &w->isl_flags, &w->isl_count, &w->sl_ticks, &w->sl_valid,
+                            &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour, &w->cell_cnt, &w->cell_off, &w->isl_parent, &w->isl_first, &w->isl_flags, &w->isl_count, &w->sl_ticks, &w->sl_valid,
                             &w->isl_counters};
     for (auto* b : u1) b->release();
     DBuf<int>* i1[] = {&w->rope_next, &w->rope_prev, &w->rp_body, &w->rp_rope};
@@ -873,7 +873,7 @@ void fill_island_ctx(SfgWorld* w, IslandCtx& c) {
     memset(&c, 0, sizeof(c));
     c.n_bodies = w->n_bodies; c.n_units = w->n_units; c.n_constraints = w->n_constraints; c.n_links = w->n_rope_units;
     c.U_ids = w->U_ids.p; c.CI = w->CI.p; c.KI = w->KI.p; c.RU = w->RU.p; c.MI = w->MI.p; c.V = w->V.p;
-    c.parent = w->isl_parent.p; c.isl_sum = w->isl_sum.p; c.isl_flags = w->isl_flags.p; c.isl_count = w->isl_count.p;
+    c.parent = w->isl_parent.p; c.isl_first = w->isl_first.p; c.isl_sum = w->isl_sum.p; c.isl_flags = w->isl_flags.p; c.isl_count = w->isl_count.p;
     c.sl_sum = w->sl_sum.p; c.sl_ticks = w->sl_ticks.p; c.sl_valid = w->sl_valid.p; c.counters = w->isl_counters.p;
     c.sleep_vel_threshold = w->tuning.sleep_vel_threshold; c.fall_asleep_frames = w->tuning.fall_asleep_frames;
 }
@@ -882,7 +882,7 @@ int island_pass(SfgWorld* w) {
     cudaStream_t st = w->stream;
     const uint32_t nb = w->n_bodies;
     if (nb == 0) return SFG_OK;
-    CK(w->isl_parent.ensure(nb + 1)); CK(w->isl_flags.ensure(nb + 1)); CK(w->isl_count.ensure(nb + 1)); CK(w->isl_sum.ensure(nb + 1));
+    CK(w->isl_parent.ensure(nb + 1)); CK(w->isl_first.ensure(nb + 1)); CK(w->isl_flags.ensure(nb + 1)); CK(w->isl_count.ensure(nb + 1)); CK(w->isl_sum.ensure(nb + 1));
     CK(w->isl_counters.ensure(8));
     IslandCtx c;
     fill_island_ctx(w, c);
@@ -916,7 +916,7 @@ int island_post(SfgWorld* w) {
         CKL(w); w->launches++;
     }
     if (n_entries) {
-        k_contacts_append<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->LN.p, w->H.p, w->S.p, w->isl_parent.p, w->isl_sum.p, new_list.p, cursor);
+        k_contacts_append<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->LN.p, w->H.p, w->S.p, w->isl_parent.p, w->isl_first.p, w->isl_sum.p, new_list.p, cursor);
         CKL(w); w->launches++;
     }
     k_isl_bodies_post<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;

@@ -1,9 +1,11 @@
 // Islands and sleeping on the device (once per tick, between the broadphase and the colouring).
 //
 // Reference: /root/reference/src/physics.rs:598-741 (recursive DFS islands + sleeping filter), :1097-1144 (contact
-// retention, fall asleep), :178-202 (IslandId / SleepingIsland). The DFS is replaced by a lock-free union-find whose
-// roots are the smallest body slot of each component, which is exactly IslandId::first_body (DFS roots are taken in
-// ascending slot order, :674-677). IslandId::edge_sum is a wrapping sum over directed graph edges,
+// retention, fall asleep), :178-202 (IslandId / SleepingIsland). The DFS is replaced by a lock-free union-find; the
+// smallest body slot of each component (an atomicMin per body) is exactly IslandId::first_body (DFS roots are taken in
+// ascending slot order, :674-677). Roots are hooked by a HASH of the slot, not by the slot: bodies are usually numbered
+// along rows of the scene, and hooking by slot builds chains as long as a row before path halving catches up.
+// IslandId::edge_sum is a wrapping sum over directed graph edges,
 //      two-body edge (rope link, two-body constraint, body-body pair) seen from body a:  (a + 1) * (b + 1)
 //      one-body edge (body-world constraint, body-static pair):                           (a + 1)
 // (:634, :651, :662, :669) and does not depend on the visit order, so atomics reproduce it bit for bit; every two-body
@@ -12,6 +14,7 @@
 // Sleeping records live in a table indexed by first_body: the reference keeps at most one record per IslandId and drops
 // every record that no island matched in the current tick (:739), so two records can never share a first_body.
 #pragma once
+#include "../../include/sfg_hash.h"
 #include "sfg_state.cuh"
 
 namespace sfg {
@@ -26,7 +29,8 @@ struct IslandCtx {
     const int4* RU;               // rope links (curr, next, after, rope)
     float4* MI;
     const float4* V;
-    uint32_t* parent;             // union-find forest, then the island root (= first_body) of every body
+    uint32_t* parent;             // union-find forest, then the island's representative (root) for every body
+    uint32_t* isl_first;          // per root: smallest slot of the island = IslandId::first_body
     unsigned long long* isl_sum;  // per root: edge_sum
     uint32_t* isl_flags;          // per root: IF_*
     uint32_t* isl_count;          // per root: bodies
@@ -54,11 +58,11 @@ __device__ __forceinline__ uint32_t uf_find_halve(uint32_t* parent, uint32_t x) 
     }
     return x;
 }
-// hook the larger root under the smaller one: the final root of a component is its smallest slot
+// hook the root with the larger hash under the other one (sfg_fmix32 is a bijection, so this is a total order)
 __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t b) {
     uint32_t ra = uf_find_halve(parent, a), rb = uf_find_halve(parent, b);
     while (ra != rb) {
-        if (ra < rb) { const uint32_t t = ra; ra = rb; rb = t; }
+        if (sfg_fmix32(ra) < sfg_fmix32(rb)) { const uint32_t t = ra; ra = rb; rb = t; }
         const uint32_t old = atomicCAS(parent + ra, ra, rb);
         if (old == ra) return;
         ra = uf_find_halve(parent, old);
@@ -69,7 +73,7 @@ __device__ __forceinline__ void uf_union(uint32_t* parent, uint32_t a, uint32_t 
 __global__ void __launch_bounds__(256) k_isl_init(IslandCtx c) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= c.n_bodies) return;
-    c.parent[b] = b; c.isl_sum[b] = 0ull; c.isl_flags[b] = 0u; c.isl_count[b] = 0u;
+    c.parent[b] = b; c.isl_first[b] = 0xFFFFFFFFu; c.isl_sum[b] = 0ull; c.isl_flags[b] = 0u; c.isl_count[b] = 0u;
     float4 m = c.MI[b];
     const uint32_t fl = __float_as_uint(m.z);
     if (fl & BF_ASLEEP) { m.z = __uint_as_float(fl & ~BF_ASLEEP); c.MI[b] = m; }
@@ -143,11 +147,11 @@ __global__ void __launch_bounds__(256) k_isl_bodies_pre(IslandCtx c) {
     const uint32_t act = __activemask();
     const uint32_t peers = __match_any_sync(act, root);
     const uint32_t peers_moving = __ballot_sync(act, moving != 0u) & peers;
-    if (int(threadIdx.x & 31u) == __ffs(int(peers)) - 1) {
+    if (int(threadIdx.x & 31u) == __ffs(int(peers)) - 1) {   // lanes run in slot order: the group's leader holds its smallest slot
         atomicAdd(c.isl_count + root, uint32_t(__popc(peers)));
+        atomicMin(c.isl_first + root, b);
         if (peers_moving && !(__ldcg(c.isl_flags + root) & IF_MOVING)) atomicOr(c.isl_flags + root, IF_MOVING);
     }
-    if (root != b) c.sl_valid[b] = 0u;     // a record is only ever found through the island whose first_body it names
 }
 // per island root: the retain() of physics.rs:714-737 and the record clean-up of :739
 __global__ void __launch_bounds__(256) k_isl_decide(IslandCtx c) {
@@ -155,10 +159,11 @@ __global__ void __launch_bounds__(256) k_isl_decide(IslandCtx c) {
     if (b >= c.n_bodies) return;
     if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE) || c.parent[b] != b) return;
     uint32_t fl = c.isl_flags[b] | IF_ROOT;
-    const bool match = c.sl_valid[b] && c.sl_sum[b] == c.isl_sum[b];
+    const uint32_t first = c.isl_first[b];          // the record of this island, if any, sits at its first_body
+    const bool match = c.sl_valid[first] && c.sl_sum[first] == c.isl_sum[b];
     bool continues = false, keep = true;
-    if (match && !(fl & IF_MOVING)) { continues = true; keep = c.sl_ticks[b] < c.fall_asleep_frames; }
-    if (!continues) c.sl_valid[b] = 0u;
+    if (match && !(fl & IF_MOVING)) { continues = true; keep = c.sl_ticks[first] < c.fall_asleep_frames; }
+    if (!continues) c.sl_valid[first] = 0u;
     if (!keep) { fl |= IF_ASLEEP; atomicAdd(c.counters + 2, 1u); }
     c.isl_flags[b] = fl;
     atomicAdd(c.counters + 0, 1u);
@@ -169,7 +174,9 @@ __global__ void __launch_bounds__(256) k_isl_mark(IslandCtx c) {
     float4 m = c.MI[b];
     const uint32_t fl = __float_as_uint(m.z);
     if (!(fl & BF_ALIVE)) return;
-    if (c.isl_flags[c.parent[b]] & IF_ASLEEP) {
+    const uint32_t root = c.parent[b];
+    if (c.isl_first[root] != b) c.sl_valid[b] = 0u;   // a record is only ever found through the island whose first_body it names
+    if (c.isl_flags[root] & IF_ASLEEP) {
         m.z = __uint_as_float(fl | BF_ASLEEP);
         c.MI[b] = m;
         atomicAdd(c.counters + 1, 1u);
@@ -193,8 +200,9 @@ __global__ void __launch_bounds__(256) k_isl_fall_asleep(IslandCtx c) {
     if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE) || c.parent[b] != b) return;
     const uint32_t fl = c.isl_flags[b];
     if (fl & (IF_ASLEEP | IF_NO_SLEEP | IF_FAST)) return;
-    if (c.sl_valid[b] && c.sl_sum[b] == c.isl_sum[b]) c.sl_ticks[b] += 1u;
-    else { c.sl_valid[b] = 1u; c.sl_sum[b] = c.isl_sum[b]; c.sl_ticks[b] = 0u; }
+    const uint32_t first = c.isl_first[b];
+    if (c.sl_valid[first] && c.sl_sum[first] == c.isl_sum[b]) c.sl_ticks[first] += 1u;
+    else { c.sl_valid[first] = 1u; c.sl_sum[first] = c.isl_sum[b]; c.sl_ticks[first] = 0u; }
 }
 
 // ---- contact list with retention (physics.rs:1097-1122) ----
@@ -213,8 +221,9 @@ __global__ void __launch_bounds__(256) k_contacts_retain(uint32_t n_old, const C
 // this tick's latched contacts (solver.rs:318-320), tagged with the island they belong to
 __global__ void __launch_bounds__(256) k_contacts_append(uint32_t n_entries, uint32_t n_units, const float2* __restrict__ LN,
                                                          const float4* __restrict__ H, const float4* __restrict__ S,
-                                                         const uint32_t* __restrict__ parent, const unsigned long long* __restrict__ isl_sum,
-                                                         ContactRec* __restrict__ out, uint32_t* cursor) {
+                                                         const uint32_t* __restrict__ parent, const uint32_t* __restrict__ isl_first,
+                                                         const unsigned long long* __restrict__ isl_sum, ContactRec* __restrict__ out,
+                                                         uint32_t* cursor) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_entries) return;
     const float2 n = LN[e];
@@ -223,8 +232,9 @@ __global__ void __launch_bounds__(256) k_contacts_append(uint32_t n_entries, uin
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     ContactRec r;
     r.c0 = __float_as_uint(s.x); r.c1 = __float_as_uint(s.y); r.nx = n.x; r.ny = n.y; r.pad = 0u;
-    r.root = parent[b0 >= 0 ? b0 : b1];
-    r.sum = isl_sum[r.root];
+    const uint32_t rep = parent[b0 >= 0 ? b0 : b1];
+    r.root = isl_first[rep];          // IslandId::first_body: where the sleeping record of this island would sit
+    r.sum = isl_sum[rep];
     out[atomicAdd(cursor, 1u)] = r;
 }
 __global__ void __launch_bounds__(256) k_contacts_export(uint32_t n, const ContactRec* __restrict__ list, uint32_t* __restrict__ out4) {
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(256) k_isl_export(IslandCtx c, uint32_t cap, u
     if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE) || c.parent[b] != b) return;
     const uint32_t pos = atomicAdd(cursor, 1u);
     if (pos >= cap) return;
-    first_body[pos] = b; sums[pos] = c.isl_sum[b]; counts[pos] = c.isl_count[b]; flags[pos] = c.isl_flags[b];
+    first_body[pos] = c.isl_first[b]; sums[pos] = c.isl_sum[b]; counts[pos] = c.isl_count[b]; flags[pos] = c.isl_flags[b];
 }
 
 }  // namespace sfg
