@@ -1018,11 +1018,11 @@ int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
     }
     const uint32_t ns = uint32_t(w->h_stages.size());
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, 768, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_persistent, SFG_SOLVER_THREADS, 0));
     if (per_sm < 1) return fail(w, SFG_E_CUDA, "persistent solver kernel does not fit on an SM");
     uint32_t max_range = 0;
     for (const Stage& sg : w->h_stages) max_range = std::max(max_range, sg.end - sg.begin);
-    const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range, 768)));
+    const uint32_t grid = std::max(1u, std::min(uint32_t(per_sm * w->n_sms), nblk(max_range, SFG_SOLVER_THREADS)));
     const Stage* dst = w->d_stages.p;
     uint32_t n_stages = ns, sub_begin = first, sub_end = first + count, n_sub = substeps;
     unsigned int* bar = &w->hdr.p->barrier;
@@ -1033,7 +1033,7 @@ int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
     const size_t trace_n = size_t(2) * count * ns * grid;
     if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; }
     void* args[] = {(void*)&ctx, (void*)&dst, &n_stages, &sub_begin, &sub_end, &n_sub, (void*)&bar, (void*)&trace};
-    CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(768), args, 0, st));
+    CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(SFG_SOLVER_THREADS), args, 0, st));
     w->launches++;
     if (trace_path) {
         std::vector<unsigned long long> h(trace_n);

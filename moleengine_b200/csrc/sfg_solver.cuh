@@ -493,7 +493,7 @@ SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, unsigned l
 // The whole substep loop of one tick in ONE launch: every CTA walks the stage table, and the units of a stage are dealt
 // to warps round-robin ACROSS CTAs (chunk c of 32 units -> CTA c mod gridDim, warp slot c / gridDim), so a run of
 // expensive units (they are grouped by narrowphase path) is spread over all SMs; then all CTAs meet at a barrier.
-__global__ void __launch_bounds__(768, 1) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
+__global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
                                                              uint32_t n_stages, uint32_t sub_begin, uint32_t sub_end, uint32_t substeps,
                                                              unsigned int* barrier_counter, unsigned long long* trace) {
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;

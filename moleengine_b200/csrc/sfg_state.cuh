@@ -26,6 +26,9 @@
 namespace sfg {
 
 constexpr int MAX_LEVELS = 8;
+#ifndef SFG_SOLVER_THREADS
+#define SFG_SOLVER_THREADS 768      // threads per CTA of the persistent solver, one CTA per SM (80 registers per thread)
+#endif
 
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     uint32_t v;

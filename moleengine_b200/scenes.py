@@ -75,6 +75,21 @@ def c2_circles(nx=500, ny=200, seed=0xC2):
     return _scene(f"c2_circles_{n}", bodies, colliders, 4)
 
 
+def star(n_small=150, big_r=10.0, small_r=0.3):
+    """One large dynamic disc ringed by touching small ones: every pair shares the big body, so the colouring needs
+    n_small colours (more than the 64-colour window of the device kernel) and the big body's island holds everything."""
+    n = n_small + 1
+    bodies = np.zeros(n, abi.body_dtype)
+    colliders = np.zeros(n, abi.collider_dtype)
+    ang = np.arange(n_small) * (2.0 * np.pi / n_small)
+    x = np.concatenate([[0.0], (big_r + small_r * 0.9) * np.cos(ang)])
+    y = np.concatenate([[0.0], (big_r + small_r * 0.9) * np.sin(ang)])
+    circ = shapes.circle(np.concatenate([[big_r], np.full(n_small, small_r)]))
+    shapes.fill_bodies_dynamic(bodies, shapes.area(*circ), shapes.second_moment_of_area(*circ), 0.5, x, y)
+    shapes.fill_colliders(colliders, circ, body=np.arange(n))
+    return _scene(f"star_{n_small}", bodies, colliders, 4)
+
+
 # ---- mixed bodies (C3 / C5 body mix) -------------------------------------------------------------
 def _mixed_bodies(n, seed, x, y, domain=0, body_base=0):
     """25% Rect, 35% rounded Rect, 10% Hexagon, 10% Triangle (half of each rounded r = 0.1), 5% capsule,

@@ -16,7 +16,8 @@ def _pairset(p):
     return np.sort(p[:, 0] << np.uint64(32) | p[:, 1])
 
 
-@pytest.mark.parametrize("scene_fn", [scenes.c1_sandbox_stack, lambda: scenes.parity_mix(400, 7), lambda: scenes.c2_circles(60, 30)])
+@pytest.mark.parametrize("scene_fn", [scenes.c1_sandbox_stack, lambda: scenes.parity_mix(400, 7), lambda: scenes.c2_circles(60, 30),
+                                      lambda: scenes.star(150), lambda: scenes.c5_worlds(6, 16)])
 def test_pairs_and_colours_bit_exact(oracle, scene_fn):
     sc = scene_fn()
     tun = abi.default_tuning(substeps=1)
