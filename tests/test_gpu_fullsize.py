@@ -1,0 +1,110 @@
+"""BASELINE.json's full size (C3: 1 M mixed-collider bodies) through properties that need no oracle run:
+
+* the candidate-pair list has no duplicates, every pair's tick-time boxes strictly overlap, and a brute-force sweep over
+  a 20 m window of the world finds exactly the same pairs there (the oracle needs minutes at this size; numpy does not);
+* the colouring is proper (no two units of a colour share a body that sees forces) and uses few colours;
+* island ids equal scipy's connected components + the reference's edge_sum formula, in 64-bit wrapping arithmetic;
+* with gravity off and no static colliders, total linear momentum is conserved by the whole tick (every correction and
+  impulse is applied with opposite signs to the two bodies of a pair)."""
+import numpy as np
+import pytest
+
+from moleengine_b200 import GpuWorld, abi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c3():
+    return scenes.c3_mixed(1250, 800, seed=0xC3)
+
+
+def test_c3_pairs_colours_islands_at_full_size(c3):
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    sc = c3
+    g = GpuWorld(tuning=abi.default_tuning(substeps=4))
+    g.load_scene(sc)
+    for _ in range(3):
+        g.tick()
+    nb, nc = len(sc["bodies"]), len(sc["colliders"])
+    pairs = g.debug_pairs().astype(np.int64)
+    assert len(pairs) > nb
+    key = pairs[:, 0] << 32 | pairs[:, 1]
+    assert len(np.unique(key)) == len(key), "duplicate candidate pairs"
+    assert (pairs[:, 0] > pairs[:, 1]).all()
+    box = g.debug_aabbs(nc).astype(np.float64)
+    a, b = box[pairs[:, 0]], box[pairs[:, 1]]
+    assert ((np.maximum(a[:, 0], b[:, 0]) < np.minimum(a[:, 2], b[:, 2])) & (np.maximum(a[:, 1], b[:, 1]) < np.minimum(a[:, 3], b[:, 3]))).all()
+    # brute force in a window: all colliders whose box touches x in [100, 120], y anywhere
+    body = sc["colliders"]["body"].astype(np.int64)
+    alive = (sc["colliders"]["flags"] & abi.COLL_ALIVE) != 0
+    inwin = alive & np.isfinite(box[:, 0]) & (box[:, 2] > 100.0) & (box[:, 0] < 120.0)
+    idx = np.flatnonzero(inwin)
+    order = idx[np.argsort(box[idx, 1])]
+    want = set()
+    ymax = box[order, 3]
+    for k, i in enumerate(order):                      # sweep on y
+        j = order[k + 1: k + 1 + np.searchsorted(box[order[k + 1:], 1], ymax[k], side="left")]
+        hit = j[(np.maximum(box[i, 0], box[j, 0]) < np.minimum(box[i, 2], box[j, 2])) & (np.maximum(box[i, 1], box[j, 1]) < np.minimum(box[i, 3], box[j, 3]))]
+        for h in hit:
+            bi, bh = body[i], body[h]
+            if (bi >= 0 or bh >= 0) and not (bi >= 0 and bi == bh):
+                want.add((max(i, h), min(i, h)))
+    got = {(int(p[0]), int(p[1])) for p in pairs[inwin[pairs[:, 0]] & inwin[pairs[:, 1]]]}
+    assert len(want) > 1000 and got == want
+    # colouring: proper and small
+    hi, lo, mult, col = g.debug_contact_units()
+    sees = (sc["bodies"]["flags"] & (abi.BODY_MASS_FINITE | abi.BODY_INERTIA_FINITE)) != 0
+    b0, b1 = body[hi.astype(np.int64)], body[lo.astype(np.int64)]
+    for bb in (b0, b1):
+        m = (bb >= 0) & sees[np.maximum(bb, 0)]
+        k = bb[m] * 1024 + col[m].astype(np.int64)
+        assert len(np.unique(k)) == len(k), "two units of one colour share a dynamic body"
+    assert col.max() < 64
+    assert (mult == np.where((b0 >= 0) & (b1 >= 0), 2, 1)).all()
+    # islands: scipy components over the same edges, IslandId per physics.rs:634-673
+    pb0, pb1 = body[pairs[:, 0]], body[pairs[:, 1]]
+    two = (pb0 >= 0) & (pb1 >= 0)
+    n_comp, label = connected_components(coo_matrix((np.ones(int(two.sum()), np.int8), (pb0[two], pb1[two])), shape=(nb, nb)), directed=False)
+    first = np.full(n_comp, nb, np.int64)
+    np.minimum.at(first, label, np.arange(nb))
+    esum = np.zeros(n_comp, np.uint64)
+    with np.errstate(over="ignore"):
+        np.add.at(esum, label[pb0[two]], np.uint64(2) * (pb0[two].astype(np.uint64) + np.uint64(1)) * (pb1[two].astype(np.uint64) + np.uint64(1)))
+        one = ~two
+        ob = np.where(pb0 >= 0, pb0, pb1)[one]
+        np.add.at(esum, label[ob], ob.astype(np.uint64) + np.uint64(1))
+    count = np.bincount(label, minlength=n_comp)
+    fb, es, bc, fl = g.debug_islands()
+    o = np.argsort(fb)
+    o2 = np.argsort(first)
+    assert len(fb) == n_comp == int(g.stats()["n_islands"])
+    assert np.array_equal(fb[o].astype(np.int64), first[o2]) and np.array_equal(es[o], esum[o2]) and np.array_equal(bc[o].astype(np.int64), count[o2])
+    g.close()
+
+
+def test_c3_momentum_conserved_without_statics(c3):
+    sc = dict(c3)
+    coll = sc["colliders"].copy()
+    coll["flags"][coll["body"] < 0] = 0                       # no ground: nothing external touches the bodies
+    bodies = sc["bodies"].copy()
+    rng = np.random.default_rng(3)
+    n = len(bodies)
+    bodies["vx"] = rng.uniform(-3, 3, n).astype(np.float32); bodies["vy"] = rng.uniform(-3, 3, n).astype(np.float32)
+    bodies["flags"] |= abi.BODY_IGNORES_GRAVITY
+    sc["colliders"], sc["bodies"] = coll, bodies
+    g = GpuWorld(tuning=abi.default_tuning(substeps=4, flags=abi.TUNE_NO_SLEEPING))
+    g.load_scene(sc)
+    m = np.where(bodies["inv_mass"] > 0, 1.0 / np.maximum(bodies["inv_mass"].astype(np.float64), 1e-12), 0.0)
+    p0 = np.array([(m * bodies["vx"]).sum(), (m * bodies["vy"]).sum()])
+    scale = (m * np.hypot(bodies["vx"], bodies["vy"])).sum()
+    for _ in range(5):
+        g.tick()
+    b = g.get_bodies()
+    p1 = np.array([(m * b["vx"].astype(np.float64)).sum(), (m * b["vy"].astype(np.float64)).sum()])
+    moved = np.hypot(b["vx"] - bodies["vx"], b["vy"] - bodies["vy"]) > 1e-3
+    print({"p0": p0.tolist(), "p1": p1.tolist(), "scale": scale, "bodies_with_changed_velocity": int(moved.sum())})
+    assert moved.sum() > 1000, "no contacts happened: the check would be vacuous"
+    assert np.abs(p1 - p0).max() <= 2e-5 * scale
+    g.close()
