@@ -85,7 +85,7 @@ struct SfgWorld {
     GridParams grid{};
     uint32_t n_live = 0, n_entries = 0;
     DBuf<uint32_t> cell_cnt, cell_off;
-    DBuf<uint32_t> keys0, keys1, vals0, vals1, sort_tmp, cell_start, warp_counts, scan_tmp;
+    DBuf<uint32_t> keys0, keys1, vals0, vals1, sort_tmp, cell_start, scan_tmp;
     DBuf<float4> SA;
     DBuf<int4> SI;
     // pair units
@@ -472,7 +472,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : f4) b->release();
     DBuf<float2>* f2[] = {&w->EA, &w->PCD, &w->LAT, &w->LN};
     for (auto* b : f2) b->release();
-    DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->warp_counts, &w->scan_tmp, &w->U_prio,
+    DBuf<uint32_t>* u1[] = {&w->keys0, &w->keys1, &w->vals0, &w->vals1, &w->sort_tmp, &w->cell_start, &w->scan_tmp, &w->U_prio,
                             &w->U_colour, &w->deg, &w->adj_start, &w->cursor, &w->jp_counters, &w->perm0, &w->perm1,
                             &w->ckey0, &w->ckey1, &w->KU_prio, &w->KU_colour, &w->cell_cnt, &w->cell_off, &w->isl_parent, &w->isl_first, &w->isl_flags, &w->isl_count, &w->sl_ticks, &w->sl_valid,
                             &w->isl_counters};
@@ -722,7 +722,7 @@ int launch_stage_dyn(SfgWorld* w, const SolverCtx& ctx, const Stage& s, bool las
     case ST_CONSTRAINT_DAMP: return launch_stage<ST_CONSTRAINT_DAMP>(w, ctx, s, last, sub);
     case ST_ROPE_DAMP: return launch_stage<ST_ROPE_DAMP>(w, ctx, s, last, sub);
     case ST_ROPE_LATERAL: return launch_stage<ST_ROPE_LATERAL>(w, ctx, s, last, sub);
-    default: return launch_stage<ST_FOLD>(w, ctx, s, last, sub);
+    default: return fail(w, SFG_E_STATE, "unknown solver stage");
     }
 }
 

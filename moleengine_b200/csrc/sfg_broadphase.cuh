@@ -1,12 +1,13 @@
 // Spatial-hash broadphase and constraint-graph build (once per tick).
 //   k_aabb            tick-time AABB per collider (bit-exact f32 restatement of physics.rs:447-459) + world bounds
-//   k_cell_keys       hierarchical uniform grid: level by AABB extent, key = cell of the AABB centre
+//   k_cell_count / k_cell_emit   hierarchical uniform grid: level by AABB extent, key = cell of the AABB centre; large
+//                     colliders also get one proxy entry per level-0 cell they overlap (sfg_state.cuh GridParams)
 //   radix sort        sfg_sort.cuh
 //   k_gather_sorted / k_cell_starts
-//   k_pairs           one lane per collider, forward half of the 3x3 block on its own level + 3x3 on every coarser level; candidate
-//                     tests = strict AABB overlap + layer mask + same domain + ">=1 body, distinct
-//                     bodies" (physics.rs:461-474, 551-555, 579); hits compacted with warp ballots
-//   k_unit_setup / k_adj_fill / k_jp_colour / k_build_units   graph colouring (include/sfg_hash.h)
+//   k_pairs           one lane per collider: forward half of the 3x3 block on its own level, 3x3 of the proxy grid (large
+//                     partners), coarser levels only where populated; candidate tests = strict AABB overlap + layer mask +
+//                     same domain + ">=1 body, distinct bodies" (physics.rs:461-474, 551-555, 579); hits compacted with warp ballots
+//   k_pair_unit_setup / k_adj_fill / k_colour_dataflow / k_build_pair_units   graph colouring (include/sfg_hash.h)
 // The emitted SET equals the reference's BVH result; the order does not.
 #pragma once
 #include <cooperative_groups.h>
@@ -190,12 +191,6 @@ __global__ void __launch_bounds__(256) k_cell_starts(const uint32_t* __restrict_
         todo &= todo - 1u;
     }
 }
-// empty world: every start is 0
-__global__ void k_fill_u32(uint32_t* p, uint32_t n, uint32_t v) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
-
 // One lane per HOME entry (in cell-sorted order; home entries sort before the big-plain and proxy ranges). Same-level
 // partners are searched in the FORWARD half neighbourhood only (rest of the own cell + cell x+1, then cells x-1..x+1 of row
 // y+1): sorted order is a total order, so every unordered pair inside a 3x3 block is met exactly once. A small (level-0)

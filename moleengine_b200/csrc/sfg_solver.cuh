@@ -62,10 +62,6 @@ SFG_DI void stage_derive(const SolverCtx& c, uint32_t i, bool fold) {
     stb(c.V + i, v);
     if (fold) stb(c.P + i, make_float4(p.x + p.z, p.y + p.w, 0.f, 0.f));
 }
-SFG_DI void stage_fold(const SolverCtx& c, uint32_t i) {
-    float4 p = ldb(c.P + i);
-    stb(c.P + i, make_float4(p.x + p.z, p.y + p.w, 0.f, 0.f));
-}
 
 // ---------------------------------------------------------------- ropes (solver.rs:114-181)
 SFG_DI void stage_rope_step(const SolverCtx& c, uint32_t u) {
@@ -458,7 +454,6 @@ SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_s
     case ST_CONSTRAINT_DAMP: stage_constraint_damp(c, i); break;
     case ST_ROPE_DAMP: stage_rope_damp(c, i); break;
     case ST_ROPE_LATERAL: stage_rope_lateral(c, i); break;
-    case ST_FOLD: stage_fold(c, i); break;
     default: break;
     }
 }

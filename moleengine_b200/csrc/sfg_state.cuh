@@ -114,7 +114,7 @@ struct SolverCtx {
 // stage table of the persistent solver kernel
 enum StageKind : uint32_t {
     ST_INTEGRATE = 0, ST_ROPE_STEP, ST_CONSTRAINTS, ST_PRECONTACT, ST_CONTACTS, ST_DERIVE, ST_CONTACT_VEL,
-    ST_CONSTRAINT_DAMP, ST_ROPE_DAMP, ST_ROPE_LATERAL, ST_FOLD,
+    ST_CONSTRAINT_DAMP, ST_ROPE_DAMP, ST_ROPE_LATERAL,
 };
 struct Stage { uint32_t kind, begin, end, colour; };   // colour: index of the contact colour (contact stages only)
 constexpr uint32_t M0_COUNT_MASK = 0xFFu;
