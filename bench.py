@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--scale", default="full", choices=["full", "tenth", "tiny"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-slab", action="store_true", help="skip the slab-decomposed strong-scaling arm (N > 1 only)")
+    ap.add_argument("--island-arm", action="store_true", help="also time island sharding of the single world (N > 1 only; bit-exact partition)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -254,6 +255,28 @@ def main():
                      "active_colliders_rank0": int(gs.stats()["n_colliders"]), "transport": "torch.distributed NCCL send/recv between x-neighbours"}
         gs.close()
 
+    # ---------------- island-shard arm (N > 1, opt-in): the same single world, every rank solves the islands it owns and
+    # all-gathers the bodies it solved (exact parity with one GPU; the broadphase and the island pass are replicated)
+    island_info = None
+    if world_size > 1 and args.island_arm:
+        from moleengine_b200 import slab
+        sci = sc if rank == 0 else workload(args.scale, 0xC3)
+        gi = GpuWorld(tuning=abi.default_tuning(substeps=SUBSTEPS), device=local_rank)
+        gi.load_scene(sci)
+        drv = slab.IslandShardDriver(gi, rank, world_size, capacity=len(sci["bodies"]), device=torch.device("cuda", local_rank))
+        for _ in range(args.warmup):
+            drv.tick(FRAME_DT, ff)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            drv.tick(FRAME_DT, ff)
+        barrier()
+        isl_s = max_over_ranks(time.perf_counter() - t0) / args.steps
+        island_info = {"value": len(sci["bodies"]) * SUBSTEPS / isl_s, "unit": "body-substeps/s", "scaling": "strong", "ms_per_step": isl_s * 1e3,
+                       "ranks": world_size, "islands": int(gi.stats()["n_islands"]), "bodies_solved_rank0": drv.sent_records,
+                       "collective": "all_gather_into_tensor of (n_bodies + 1) x 64 B per rank (NCCL)"}
+        gi.close()
+
     if rank != 0:
         g.close()
         if world_size > 1:
@@ -307,6 +330,8 @@ def main():
     }
     if slab_info is not None:
         out["slab"] = slab_info
+    if island_info is not None:
+        out["island_shards"] = island_info
     print(json.dumps(out))
     g.close()
     if world_size > 1:

@@ -210,8 +210,13 @@ int sfg_tick_end(SfgWorld* w);
  * count), so the transport (NCCL send/recv, peer copies) stays outside the library. side 0 = towards lower x, 1 = higher x.
  * A slab world never sleeps (islands across a cut are not tracked). x_hi <= x_lo switches slab mode off. */
 int sfg_slab_configure(SfgWorld* w, float x_lo, float x_hi, float halo);
+/* Island sharding (the reference's own parallelism, physics.rs:895-947 / 1070-1082, one level up): every rank holds the whole
+ * world, solves only the islands with hash(first_body) % n_ranks == rank and skips the others for the tick; after sfg_tick
+ * the ranks exchange what they solved: sfg_slab_pack(mode 2, side 0) -> all-gather -> sfg_slab_unpack of every other rank's
+ * buffer. Bit-identical to one GPU (islands share nothing). n_ranks <= 1 switches it off. */
+int sfg_island_shard_configure(SfgWorld* w, uint32_t rank, uint32_t n_ranks);
 int sfg_slab_begin(SfgWorld* w);
-int sfg_slab_pack(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records, uint32_t* count_out);
+int sfg_slab_pack(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records, uint32_t* count_out);   /* mode 0 refresh, 1 substep sync, 2 island shard */
 int sfg_slab_unpack(SfgWorld* w, const void* device_in, uint32_t capacity_records);
 
 /* ---- results: bodies written back (physics.rs:1150-1157), contacts (:1097-1122, :1165) ---- */

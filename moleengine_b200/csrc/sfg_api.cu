@@ -129,6 +129,8 @@ struct SfgWorld {
     float slab_lo = 0.f, slab_hi = 0.f, slab_halo = 0.f;
     uint32_t slab_epoch = 0;
     DBuf<uint32_t> slab_stamp;
+    // island sharding (sfg_island_shard_configure)
+    uint32_t shard_rank = 0, shard_n = 1;
     // stats
     SfgStats stats{};
     uint32_t launches = 0;
@@ -177,7 +179,7 @@ __global__ void k_pack_bodies(SfgBody* out, uint32_t n, uint32_t first, const fl
     b.x = p.x + p.z; b.y = p.y + p.w; b.rot_s = q.x; b.rot_b = q.y;
     b.vx = v.x; b.vy = v.y; b.w = v.z;
     const uint32_t z = __float_as_uint(m.z);
-    b.flags = (z & 30u) | ((z & BF_EXISTS) ? SFG_BODY_ALIVE : 0u) | ((z & BF_GHOST) ? SFG_BODY_GHOST : 0u) |
+    b.flags = (z & ((z & BF_FOREIGN) ? 14u : 30u)) | ((z & BF_EXISTS) ? SFG_BODY_ALIVE : 0u) | ((z & BF_GHOST) ? SFG_BODY_GHOST : 0u) |
               (((z & BF_EXISTS) && !(z & BF_ALIVE)) ? SFG_BODY_INACTIVE : 0u);
     b.inv_mass = m.x; b.inv_inertia = m.y;
     b.reserved[0] = b.reserved[1] = 0;
@@ -315,7 +317,8 @@ __global__ void k_slab_classify(uint32_t nb, const float4* P, float4* MI, const 
     m.z = __uint_as_float(fl);
     MI[b] = m;
 }
-// mode 0: by position (the refresh that opens a tick, before the classification exists); mode 1: by this tick's flags
+// mode 0: by position (the refresh that opens a tick, before the classification exists); mode 1: by this tick's flags;
+// mode 2: the bodies of this rank's islands (island sharding)
 __global__ void k_slab_pack(uint32_t nb, int mode, int side, float lo, float hi, float halo, const float4* P, const float4* Q, const float4* V,
                             const float4* MI, HaloRec* out, uint32_t cap, uint32_t* cursor) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -326,7 +329,8 @@ __global__ void k_slab_pack(uint32_t nb, int mode, int side, float lo, float hi,
     if (mode == 0) {
         const float x = p.x + p.z;
         send = (fl & BF_EXISTS) && x >= lo && x < hi && (side == 0 ? x < lo + halo : x >= hi - halo);
-    } else send = (fl & BF_ALIVE) && !(fl & BF_GHOST) && (fl & (side == 0 ? BF_ZONE_L : BF_ZONE_R));
+    } else if (mode == 1) send = (fl & BF_ALIVE) && !(fl & BF_GHOST) && (fl & (side == 0 ? BF_ZONE_L : BF_ZONE_R));
+    else send = (fl & BF_ALIVE) && !(fl & BF_FOREIGN);     // mode 2, island sharding: every body this rank solved (or keeps asleep)
     if (!send) return;
     const uint32_t pos = atomicAdd(cursor, 1u);
     if (pos >= cap) return;
@@ -876,6 +880,7 @@ void fill_island_ctx(SfgWorld* w, IslandCtx& c) {
     c.parent = w->isl_parent.p; c.isl_first = w->isl_first.p; c.isl_sum = w->isl_sum.p; c.isl_flags = w->isl_flags.p; c.isl_count = w->isl_count.p;
     c.sl_sum = w->sl_sum.p; c.sl_ticks = w->sl_ticks.p; c.sl_valid = w->sl_valid.p; c.counters = w->isl_counters.p;
     c.sleep_vel_threshold = w->tuning.sleep_vel_threshold; c.fall_asleep_frames = w->tuning.fall_asleep_frames;
+    c.shard_rank = w->shard_rank; c.shard_n = w->shard_n; c.sleeping = sleeping_enabled(w) ? 1u : 0u;
 }
 // physics.rs:598-741: islands of the constraint graph, then which of them stay asleep this tick
 int island_pass(SfgWorld* w) {
@@ -975,7 +980,8 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     rc = broadphase(w, float(frame_dt));
     if (rc != SFG_OK) return rc;
     CK(cudaEventRecord(w->ev[1], st));
-    w->tick_sleeping = sleeping_enabled(w) && !w->slab_on;   // islands across a slab seam are not tracked: slabs never sleep
+    // islands across a slab seam are not tracked: slabs never sleep. Island sharding needs the islands even if nothing may sleep.
+    w->tick_sleeping = (sleeping_enabled(w) || w->shard_n > 1) && !w->slab_on;
     if (w->tick_sleeping) { rc = island_pass(w); if (rc != SFG_OK) return rc; }
     rc = build_graph(w);
     if (rc != SFG_OK) return rc;
@@ -1109,6 +1115,17 @@ int sfg_slab_configure(SfgWorld* w, float x_lo, float x_hi, float halo) {
     w->slab_epoch = 0;
     return SFG_OK;
 }
+// ---- island sharding (SURVEY.md §8e "independent islands of one world"): every rank holds the whole world and runs the
+// broadphase and the island pass on all of it, but colours and solves only the islands it owns; after the tick the ranks
+// exchange the bodies they solved (sfg_slab_pack mode 2 / sfg_slab_unpack), so all copies agree again. Islands share no
+// body, pair or constraint, so the result is bit-identical to one GPU.
+int sfg_island_shard_configure(SfgWorld* w, uint32_t rank, uint32_t n_ranks) {
+    if (!w) return SFG_E_INVALID;
+    if (n_ranks > 1 && rank >= n_ranks) return fail(w, SFG_E_INVALID, "island shard rank out of range");
+    if (n_ranks > 1 && w->slab_on) return fail(w, SFG_E_STATE, "island sharding and slab decomposition are exclusive");
+    w->shard_rank = n_ranks > 1 ? rank : 0; w->shard_n = n_ranks > 1 ? n_ranks : 1;
+    return SFG_OK;
+}
 int sfg_slab_begin(SfgWorld* w) {
     if (!w) return SFG_E_INVALID;
     if (!w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
@@ -1116,8 +1133,9 @@ int sfg_slab_begin(SfgWorld* w) {
     return SFG_OK;
 }
 int sfg_slab_pack(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records, uint32_t* count_out) {
-    if (!w || !device_out || !count_out || side < 0 || side > 1 || mode < 0 || mode > 1) return SFG_E_INVALID;
-    if (!w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
+    if (!w || !device_out || !count_out || side < 0 || side > 1 || mode < 0 || mode > 2) return SFG_E_INVALID;
+    if (mode < 2 && !w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
+    if (mode == 2 && w->shard_n < 2) return fail(w, SFG_E_STATE, "sfg_island_shard_configure first");
     cudaSetDevice(w->device);
     cudaStream_t st = w->stream;
     *count_out = 0;
@@ -1137,7 +1155,7 @@ int sfg_slab_pack(SfgWorld* w, int mode, int side, void* device_out, uint32_t ca
 }
 int sfg_slab_unpack(SfgWorld* w, const void* device_in, uint32_t capacity_records) {
     if (!w || !device_in) return SFG_E_INVALID;
-    if (!w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
+    if (!w->slab_on && w->shard_n < 2) return fail(w, SFG_E_STATE, "sfg_slab_configure or sfg_island_shard_configure first");
     if (capacity_records == 0 || w->n_bodies == 0) return SFG_OK;
     cudaSetDevice(w->device);
     CK(w->slab_stamp.ensure(size_t(w->n_bodies) + 1));

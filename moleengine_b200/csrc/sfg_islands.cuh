@@ -19,7 +19,7 @@
 
 namespace sfg {
 
-enum : uint32_t { IF_NO_SLEEP = 1u, IF_MOVING = 2u, IF_FAST = 4u, IF_ASLEEP = 8u, IF_ROOT = 16u };
+enum : uint32_t { IF_NO_SLEEP = 1u, IF_MOVING = 2u, IF_FAST = 4u, IF_ASLEEP = 8u, IF_ROOT = 16u, IF_FOREIGN = 32u /* solved by another rank */ };
 
 struct IslandCtx {
     uint32_t n_bodies, n_units, n_constraints, n_links;
@@ -40,6 +40,8 @@ struct IslandCtx {
     uint32_t* counters;           // [0] islands, [1] sleeping bodies, [2] asleep islands
     float sleep_vel_threshold;
     uint32_t fall_asleep_frames;
+    uint32_t shard_rank, shard_n;   // island sharding: this rank solves the islands with fmix32(first_body) % shard_n == shard_rank
+    uint32_t sleeping;              // 0: islands are only built for sharding, nothing falls asleep
 };
 
 __device__ __forceinline__ uint32_t uf_find(const uint32_t* parent, uint32_t x) {
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(256) k_isl_init(IslandCtx c) {
     c.parent[b] = b; c.isl_first[b] = 0xFFFFFFFFu; c.isl_sum[b] = 0ull; c.isl_flags[b] = 0u; c.isl_count[b] = 0u;
     float4 m = c.MI[b];
     const uint32_t fl = __float_as_uint(m.z);
-    if (fl & BF_ASLEEP) { m.z = __uint_as_float(fl & ~BF_ASLEEP); c.MI[b] = m; }
+    if (fl & (BF_ASLEEP | BF_FOREIGN)) { m.z = __uint_as_float(fl & ~(BF_ASLEEP | BF_FOREIGN)); c.MI[b] = m; }
     if (b < 4) c.counters[b] = 0u;
 }
 
@@ -162,9 +164,12 @@ __global__ void __launch_bounds__(256) k_isl_decide(IslandCtx c) {
     const uint32_t first = c.isl_first[b];          // the record of this island, if any, sits at its first_body
     const bool match = c.sl_valid[first] && c.sl_sum[first] == c.isl_sum[b];
     bool continues = false, keep = true;
-    if (match && !(fl & IF_MOVING)) { continues = true; keep = c.sl_ticks[first] < c.fall_asleep_frames; }
+    if (c.sleeping && match && !(fl & IF_MOVING)) { continues = true; keep = c.sl_ticks[first] < c.fall_asleep_frames; }
     if (!continues) c.sl_valid[first] = 0u;
     if (!keep) { fl |= IF_ASLEEP; atomicAdd(c.counters + 2, 1u); }
+    // islands are independent (physics.rs:155-172), so each rank can solve a subset of them and the results are exactly
+    // those of one GPU; the owner is a pure function of the island's identity
+    if (c.shard_n > 1u && sfg_fmix32(first) % c.shard_n != c.shard_rank) fl |= IF_FOREIGN;
     c.isl_flags[b] = fl;
     atomicAdd(c.counters + 0, 1u);
 }
@@ -176,10 +181,11 @@ __global__ void __launch_bounds__(256) k_isl_mark(IslandCtx c) {
     if (!(fl & BF_ALIVE)) return;
     const uint32_t root = c.parent[b];
     if (c.isl_first[root] != b) c.sl_valid[b] = 0u;   // a record is only ever found through the island whose first_body it names
-    if (c.isl_flags[root] & IF_ASLEEP) {
-        m.z = __uint_as_float(fl | BF_ASLEEP);
+    const uint32_t ifl = c.isl_flags[root];
+    if (ifl & (IF_ASLEEP | IF_FOREIGN)) {
+        m.z = __uint_as_float(fl | BF_ASLEEP | ((ifl & IF_FOREIGN) ? BF_FOREIGN : 0u));
         c.MI[b] = m;
-        atomicAdd(c.counters + 1, 1u);
+        if (ifl & IF_ASLEEP) atomicAdd(c.counters + 1, 1u);
     }
 }
 // after the solve: physics.rs:1128-1144
@@ -199,7 +205,7 @@ __global__ void __launch_bounds__(256) k_isl_fall_asleep(IslandCtx c) {
     if (b >= c.n_bodies) return;
     if (!(__float_as_uint(c.MI[b].z) & BF_ALIVE) || c.parent[b] != b) return;
     const uint32_t fl = c.isl_flags[b];
-    if (fl & (IF_ASLEEP | IF_NO_SLEEP | IF_FAST)) return;
+    if (!c.sleeping || (fl & (IF_ASLEEP | IF_NO_SLEEP | IF_FAST | IF_FOREIGN))) return;
     const uint32_t first = c.isl_first[b];
     if (c.sl_valid[first] && c.sl_sum[first] == c.isl_sum[b]) c.sl_ticks[first] += 1u;
     else { c.sl_valid[first] = 1u; c.sl_sum[first] = c.isl_sum[b]; c.sl_ticks[first] = 0u; }

@@ -74,7 +74,8 @@ enum : uint32_t {
 // BF_ALIVE means "takes part in this tick"; BF_EXISTS is what the host uploaded. They differ only in a slab-decomposed world,
 // where the per-tick classification (sfg_api.cu k_slab_classify) switches off bodies outside the slab and its halo.
 enum : uint32_t { BF_ALIVE = 1u, BF_NOGRAV = 2u, BF_MASS = 4u, BF_INERTIA = 8u, BF_ASLEEP = 16u /* set per tick by the island pass */,
-                  BF_EXISTS = 32u, BF_GHOST = 64u, BF_ZONE_L = 128u, BF_ZONE_R = 256u };
+                  BF_EXISTS = 32u, BF_GHOST = 64u, BF_ZONE_L = 128u, BF_ZONE_R = 256u,
+                  BF_FOREIGN = 512u /* island owned by another rank this tick (island sharding); always together with BF_ASLEEP */ };
 // collider flag bits kept in CM.w / CI.w (same values as SFG_COLL_*)
 enum : uint32_t { CF_ALIVE = 1u, CF_SENSOR = 2u, CF_HAS_SF = 4u, CF_HAS_DF = 8u };
 

@@ -144,3 +144,52 @@ def tick_local(drivers, transport, frame_dt=1.0 / 60.0, forcefield=None):
             exchange(1)
     for d in drivers:
         d.world.tick_end()
+
+
+# ---------------------------------------------------------------- island sharding (second row)
+class IslandShardDriver:
+    """One world replicated on every rank; each rank solves the islands it owns (sfg_island_shard_configure) and, after the
+    tick, all-gathers the bodies it solved so that every copy is whole again. Islands share no body, pair or constraint
+    (physics.rs:155-172), so the state after the exchange is bit-identical to a single-GPU tick. The exchange is the one
+    real collective of this partition: an all-gather of (capacity + 1) 64-byte records per rank."""
+
+    def __init__(self, world, rank, n_ranks, capacity, device=None, group=None):
+        import torch
+        self.world, self.rank, self.n_ranks, self.capacity, self.group = world, rank, n_ranks, capacity, group
+        world.island_shard_configure(rank, n_ranks)
+        words = (capacity + 1) * REC_WORDS
+        self.send = torch.zeros(words, dtype=torch.float32, device=device)
+        self.recv = torch.zeros(words * n_ranks, dtype=torch.float32, device=device)
+        self.sent_records = 0
+
+    def pack(self):
+        self.sent_records = self.world.slab_pack(2, 0, self.send.data_ptr(), self.capacity)
+
+    def unpack(self):
+        words = (self.capacity + 1) * REC_WORDS
+        for r in range(self.n_ranks):
+            if r != self.rank:
+                self.world.slab_unpack(self.recv[r * words:(r + 1) * words].data_ptr(), self.capacity)
+
+    def tick(self, frame_dt=1.0 / 60.0, forcefield=None):
+        import torch
+        import torch.distributed as dist
+        self.world.tick(frame_dt, None, forcefield)
+        self.pack()
+        dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        if self.send.is_cuda:
+            torch.cuda.current_stream().synchronize()
+        self.unpack()
+
+
+def tick_island_shards_local(drivers, frame_dt=1.0 / 60.0, forcefield=None):
+    """All shards in one process (tests): the all-gather is a copy of every driver's send buffer into every recv buffer."""
+    for d in drivers:
+        d.world.tick(frame_dt, None, forcefield)
+        d.pack()
+    words = (drivers[0].capacity + 1) * REC_WORDS
+    for d in drivers:
+        for src in drivers:
+            d.recv[src.rank * words:(src.rank + 1) * words].copy_(src.send)
+    for d in drivers:
+        d.unpack()

@@ -101,6 +101,9 @@ class GpuWorld:
     def slab_configure(self, x_lo, x_hi, halo):
         self._ck(self.lib.sfg_slab_configure(self.h, x_lo, x_hi, halo))
 
+    def island_shard_configure(self, rank, n_ranks):
+        self._ck(self.lib.sfg_island_shard_configure(self.h, rank, n_ranks))
+
     def slab_begin(self):
         self._ck(self.lib.sfg_slab_begin(self.h))
 

@@ -113,3 +113,48 @@ def test_two_ranks_gloo_exchange_and_call_order():
     assert got0 == [[1000.0 + 10.0 * m + i for i in range(4)] for m in (0, 1, 1)]
     assert got1 == [[100.0 + 10.0 * m + i for i in range(4)] for m in (0, 1, 1)]
     assert sent0 == 3 * 4 and sent1 == 3 * 4
+
+
+def _shard_worker(rank, world_size, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+
+    class W(FakeWorld):
+        def island_shard_configure(self, r, n):
+            self.calls.append(("shard", r, n))
+
+        def tick(self, frame_dt, time_scale, ff):
+            self.calls.append("tick")
+
+    w = W(rank)
+    d = slab.IslandShardDriver(w, rank, world_size, capacity=16, device="cpu")
+    w.bufs[d.send.data_ptr()] = d.send
+    words = (d.capacity + 1) * slab.REC_WORDS
+    for r in range(world_size):
+        w.bufs[d.recv[r * words:(r + 1) * words].data_ptr()] = d.recv[r * words:(r + 1) * words]
+    d.tick()
+    out.put((rank, w.calls, w.got, d.sent_records))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_island_shard_driver_all_gather_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r = out.get(timeout=120)
+        res[r[0]] = r
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        _, calls, got, sent = res[rank]
+        other = 1 - rank
+        assert calls == [("shard", rank, 2), "tick", ("pack", 2, 0), "unpack"]
+        assert sent == 3 + rank                                  # FakeWorld packs 3 + rank + side records
+        assert got == [[1000.0 * other + 10.0 * 2 + i for i in range(3 + other)]]   # exactly the other rank's buffer, once
