@@ -233,3 +233,32 @@ def test_pose_sync_roundtrip():
     assert np.array_equal(b1["x"], p2[:, 0]) and np.array_equal(b1["vx"], b0["vx"]) and np.array_equal(b1["w"], b0["w"])
     g.tick()
     g.close()
+
+
+def test_pair_buffer_overflow_reruns_the_search(oracle):
+    """The candidate-pair buffer is sized from the previous tick; a world that suddenly contracts (poses written from the host,
+    as user code may do between ticks) must overflow it once, re-run the search and still emit the exact pair set."""
+    sc = scenes.c3_mixed(100, 30, seed=9)
+    tun = abi.default_tuning(substeps=1)
+    g = GpuWorld(tuning=tun)
+    b0 = sc["bodies"].copy()
+    b0["x"] *= 4.0; b0["y"] = 1.0 + (b0["y"] - b0["y"].min()) * 4.0       # sparse start: hardly any candidate pair
+    sc0 = dict(sc); sc0["bodies"] = b0
+    g.load_scene(sc0)
+    g.tick()
+    n_before = int(g.stats()["n_pairs"])
+    b = sc["bodies"].copy()
+    b["x"] *= 0.3; b["y"] = 1.0 + (b["y"] - b["y"].min()) * 0.3            # 11x the design density: boxes overlap everywhere
+    g.set_bodies(b)
+    g.set_colliders(sc["colliders"])
+    g.tick()
+    n_after = int(g.stats()["n_pairs"])
+    # the buffer held max(1.25 * previous + 4096, 2 * colliders) pairs (+50 % allocation headroom)
+    assert n_after > 1.5 * max(1.25 * n_before + 4096, 2 * len(sc["colliders"])) + 64, (n_before, n_after)
+    sc2 = dict(sc); sc2["bodies"] = b
+    o32 = oracle.OracleWorld(use_f32=True, tuning=tun)
+    o32.load_scene(sc2)
+    o32.tick(mode=oracle.MODE_COLOURED)
+    key = lambda p: np.sort(np.asarray(p, np.uint64).reshape(-1, 2)[:, 0] << np.uint64(32) | np.asarray(p, np.uint64).reshape(-1, 2)[:, 1])  # noqa: E731
+    assert np.array_equal(key(g.debug_pairs()), key(o32.pairs()))
+    g.close()

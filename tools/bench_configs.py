@@ -34,12 +34,13 @@ def main():
     ap.add_argument("configs", nargs="*", default=["c1", "c2", "c4", "c5"])
     ap.add_argument("--ticks", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--cell-size", type=float, default=0.0, help="level-0 cell size override (SfgTuning.cell_size); 0 = automatic")
     args = ap.parse_args()
     for name in args.configs:
         t0 = time.perf_counter()
         sc, substeps, rays = build(name)
         t_build = time.perf_counter() - t0
-        g = GpuWorld(tuning=abi.default_tuning(substeps=substeps))
+        g = GpuWorld(tuning=abi.default_tuning(substeps=substeps, cell_size=args.cell_size))
         g.load_scene(sc)
         for _ in range(args.warmup):
             g.tick()
