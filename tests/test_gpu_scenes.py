@@ -262,3 +262,26 @@ def test_pair_buffer_overflow_reruns_the_search(oracle):
     key = lambda p: np.sort(np.asarray(p, np.uint64).reshape(-1, 2)[:, 0] << np.uint64(32) | np.asarray(p, np.uint64).reshape(-1, 2)[:, 1])  # noqa: E731
     assert np.array_equal(key(g.debug_pairs()), key(o32.pairs()))
     g.close()
+
+
+@pytest.mark.parametrize("offset", [(1000.0, -640.0), (-8000.0, 3000.0)])
+def test_far_from_the_origin(oracle, offset):
+    """SURVEY.md "hard parts" 1: f32 positions lose 1/16 mm per ulp at |x| = 1000 m and v = (x - x_old) / dt would amplify that
+    240x; the device keeps (x_old, dx) and pair-local frames, so a scene translated to the far corner of the 1 M-body world
+    (and well beyond it) still meets the one-substep gates against the f64 oracle replaying the same order."""
+    import parity
+    sc = scenes.parity_mix(300, 5, offset=offset)
+    tun = abi.default_tuning(substeps=1)
+    g = GpuWorld(tuning=tun)
+    g.load_scene(sc)
+    g.tick()
+    o = oracle.OracleWorld(tuning=tun)
+    o.load_scene(sc)
+    o.set_external_pairs(g.debug_pairs())
+    o.tick(mode=oracle.MODE_COLOURED)
+    r = parity.compare_tick(g, o, sc, tol_state=1e-4, hops=3)
+    print(offset, r)
+    assert r["non_tie_mismatches"] == 0 and r["bad_outside_influence"] == 0
+    assert r["manifold_err"] < 1e-5 and r["manifolds_compared"] > 50
+    assert r["vel_err_clean"] < 1e-4
+    g.close()
