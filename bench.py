@@ -33,16 +33,17 @@ def workload(scale, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region: the poller runs from before the warm-up (it takes
+    tens of milliseconds to start) and every row is stamped on arrival; only rows between mark_begin() and mark_end() count."""
 
     def __init__(self, device):
-        self.rows, self.proc, self.device = [], None, device
+        self.rows, self.proc, self.device, self.t0, self.t1 = [], None, device, None, None
 
     def start(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "10"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -50,16 +51,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.03)          # let the rows of the last milliseconds arrive
             self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        slack = 0.015                 # a row describes the ~10 ms before it was printed
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + slack]
+        rows = inside if inside else [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "samples_in_timed_region": len(inside)}
 
 
 def algorithmic_bytes_per_tick(st, n_bodies, substeps):
@@ -98,7 +110,8 @@ def run_reference(args, rank, world_size):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
     from moleengine_b200 import abi
-    sc = workload("tenth", 0xC3)
+    scale = "tenth" if args.scale == "full" else args.scale          # the bounded sample: 1/10 of the 1 M-body workload per step
+    sc = workload(scale, 0xC3)
     tun = abi.default_tuning(substeps=SUBSTEPS)
     cores = os.cpu_count() or 1
     w = O.OracleWorld(tuning=tun)
@@ -111,7 +124,7 @@ def run_reference(args, rank, world_size):
         w.tick(FRAME_DT, mode=O.MODE_REFERENCE, threads=cores)
     dt = time.perf_counter() - t0
     val = nb * SUBSTEPS * args.steps / dt
-    sample = f"c3_mixed at 1/10 scale ({nb} bodies), {args.steps} ticks of {SUBSTEPS} substeps, f64 oracle port of the reference tick"
+    sample = f"c3_mixed sample ({scale}: {nb} bodies), {args.steps} ticks of {SUBSTEPS} substeps, f64 oracle port of the reference tick"
     print(json.dumps({
         "impl": "reference", "metric": "body-substeps/sec", "value": val, "unit": "body-substeps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -174,13 +187,14 @@ def main():
     ff = abi.gravity_field()
 
     # ---------------- device-resident arm: `value`
-    for _ in range(args.warmup):
-        g.tick(FRAME_DT, None, ff)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        g.tick(FRAME_DT, None, ff)
+    barrier()
     solver_ms, total_ms, broad_ms, graph_ms, launches = 0.0, 0.0, 0.0, 0.0, 0
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         g.tick(FRAME_DT, None, ff)      # synchronous: returns after the tick's stream has drained
@@ -189,6 +203,7 @@ def main():
         launches += int(st["kernel_launches"])
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     step_s = max_over_ranks(wall) / args.steps
     value = world_size * nb * SUBSTEPS / step_s
