@@ -128,7 +128,7 @@ struct SfgWorld {
     bool slab_on = false, slab_was_on = false;
     float slab_lo = 0.f, slab_hi = 0.f, slab_halo = 0.f;
     uint32_t slab_epoch = 0;
-    DBuf<uint32_t> slab_stamp;
+    DBuf<uint32_t> slab_stamp, dbg;
     // island sharding (sfg_island_shard_configure)
     uint32_t shard_rank = 0, shard_n = 1;
     // stats
@@ -346,6 +346,15 @@ __global__ void k_slab_unpack(const HaloRec* in, uint32_t cap, uint32_t nb, floa
     if (r.slot >= nb) return;
     P[r.slot] = r.P; Q[r.slot] = r.Q; V[r.slot] = r.V;
     stamp[r.slot] = epoch;
+}
+
+// debug (SFG_DEBUG_NAN=1 with SFG_TUNE_SEPARATE_LAUNCHES): first body whose state is not finite after a stage
+__global__ void k_find_nonfinite(uint32_t nb, const float4* P, const float4* Q, const float4* V, const float4* MI, uint32_t* first) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb || !(__float_as_uint(MI[b].z) & BF_ALIVE)) return;
+    const float4 p = P[b], q = Q[b], v = V[b];
+    const float s = p.x + p.y + p.z + p.w + q.x + q.y + v.x + v.y + v.z;
+    if (!isfinite(s)) atomicMin(first, b);
 }
 
 int ensure_device(int device) {
@@ -1018,8 +1027,28 @@ int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
     const SolverCtx& ctx = w->tick_ctx;
     int rc;
     if (w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES) {
+        static const bool debug_nan = getenv("SFG_DEBUG_NAN") != nullptr;
+        bool reported = false;
         for (uint32_t s = first; s < first + count; ++s)
-            for (const Stage& sg : w->h_stages) { rc = launch_stage_dyn(w, ctx, sg, s + 1 == substeps, s); if (rc != SFG_OK) return rc; }
+            for (size_t k = 0; k < w->h_stages.size(); ++k) {
+                const Stage& sg = w->h_stages[k];
+                rc = launch_stage_dyn(w, ctx, sg, s + 1 == substeps, s);
+                if (rc != SFG_OK) return rc;
+                if (debug_nan && !reported) {
+                    uint32_t* flag = w->isl_counters.p ? w->isl_counters.p + 7 : nullptr;
+                    if (!flag) { CK(w->isl_counters.ensure(8)); flag = w->isl_counters.p + 7; }
+                    CK(cudaMemsetAsync(flag, 0xFF, 4, st));
+                    k_find_nonfinite<<<nblk(w->n_bodies), 256, 0, st>>>(w->n_bodies, w->P.p, w->Q.p, w->V.p, w->MI.p, flag);
+                    uint32_t fb = 0xFFFFFFFFu;
+                    CK(cudaMemcpyAsync(&fb, flag, 4, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    if (fb != 0xFFFFFFFFu) {
+                        fprintf(stderr, "SFG_DEBUG_NAN: first non-finite body %u after substep %u stage %zu (kind %u, colour %u, range [%u, %u))\n", fb, s, k,
+                                sg.kind, sg.colour, sg.begin, sg.end);
+                        reported = true;
+                    }
+                }
+            }
         return SFG_OK;
     }
     const uint32_t ns = uint32_t(w->h_stages.size());
@@ -1038,9 +1067,23 @@ int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
     unsigned long long* trace = nullptr;
     const size_t trace_n = size_t(2) * count * ns * grid;
     if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; }
-    void* args[] = {(void*)&ctx, (void*)&dst, &n_stages, &sub_begin, &sub_end, &n_sub, (void*)&bar, (void*)&trace};
+    static const bool debug_nan = getenv("SFG_DEBUG_NAN") != nullptr;
+    uint32_t* dbg = nullptr;
+    if (debug_nan) { CK(w->dbg.ensure(4096 + 8)); CK(cudaMemsetAsync(w->dbg.p, 0xFF, (4096 + 8) * 4, st)); dbg = w->dbg.p; }
+    void* args[] = {(void*)&ctx, (void*)&dst, &n_stages, &sub_begin, &sub_end, &n_sub, (void*)&bar, (void*)&trace, (void*)&dbg};
     CK(cudaLaunchCooperativeKernel((void*)k_solve_persistent, dim3(grid), dim3(SFG_SOLVER_THREADS), args, 0, st));
     w->launches++;
+    if (debug_nan) {
+        std::vector<uint32_t> h(4096 + 8);
+        CK(cudaMemcpyAsync(h.data(), dbg, h.size() * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h[0] != 0xFFFFFFFFu) {
+            const uint32_t idx = h[0], s = idx / ns, k = idx % ns;
+            const Stage& sg = w->h_stages[k];
+            fprintf(stderr, "SFG_DEBUG_NAN (persistent): first non-finite body %u after substep %u stage %u of %u (kind %u, colour %u, range [%u, %u))\n",
+                    h[1 + std::min(idx, 4000u)], s, k, ns, sg.kind, sg.colour, sg.begin, sg.end);
+        }
+    }
     if (trace_path) {
         std::vector<unsigned long long> h(trace_n);
         CK(cudaMemcpyAsync(h.data(), trace, trace_n * 8, cudaMemcpyDeviceToHost, st));

@@ -13,6 +13,10 @@
 namespace sfg {
 
 #define SFG_DI __device__ __forceinline__
+#ifndef SFG_GUARD_MASK
+#define SFG_GUARD_MASK 0xFFu            // zero-length guards (bisecting aid: build with -DSFG_GUARD_MASK=<bits> to switch some off)
+#endif
+#define SFG_GUARD(bit) ((SFG_GUARD_MASK >> (bit)) & 1u)
 
 struct V2 { float x, y; };
 SFG_DI V2 mk(float x, float y) { V2 v; v.x = x; v.y = y; return v; }
@@ -260,6 +264,11 @@ SFG_DI void circle_any(Iso pc, float rc, Iso po, const Shape& so, Manifold& m) {
     bool interior;
     V2 cp = closest_boundary_point(so, dist, &interior);
     V2 fc = dist - cp;
+    // Deviation (f32 robustness): where the reference normalises a vector that can be exactly zero it gets NaN and
+    // the NaN poisons every body the solver reaches in that tick. In f64 that takes an exact coincidence; in f32 it happens
+    // in crowded scenes (a rope pile lost 482 bodies at tick 256). A centre exactly on the boundary reports no contact for
+    // this visit; the next visit sees it a rounding error to one side.
+    if (SFG_GUARD(1) && fc.x == 0.f && fc.y == 0.f) { m.count = 0; return; }
     if (interior) {
         V2 dir = normalized(fc);
         m.count = 1; m.n = po.r * dir;
@@ -375,7 +384,7 @@ SFG_DI void any_any(Iso pose0, Iso pose1, const Shape& s0, const Shape& s1, Mani
     const V2 d = cl_other - cl_pen;
     const float dsq = mag_sq(d);
     if (dsq >= r_sum * r_sum) { m.count = 0; return; }
-    const V2 axis = d * (1.0f / sqrtf(dsq));
+    const V2 axis = (SFG_GUARD(2) && dsq == 0.f) ? pen.n : d * (1.0f / sqrtf(dsq));   // coincident corner points: push along the SAT axis
     m.count = 1; m.n = pose_own_r * axis;
     m.off[0][0] = cl_pen + r_own * axis;
     m.off[0][1] = rel_own * (cl_other - r_inc * axis);

@@ -71,6 +71,7 @@ SFG_DI void stage_rope_step(const SolverCtx& c, uint32_t u) {
     const float imc = ldb(c.MI + ru.x).x, imn = ldb(c.MI + ru.y).x;
     V2 dist = mk((pn.x - pc.x) + (pn.z - pc.z), (pn.y - pc.y) + (pn.w - pc.w));
     float dm = mag(dist);
+    if (SFG_GUARD(3) && dm == 0.f) return;          // coincident particles: no direction to correct along (the reference gets NaN, sfg_geom.cuh circle_any)
     V2 dir = mk(dist.x / dm, dist.y / dm);
     float error = pa.x - dm;
     float lambda = -error / (imc + imn + pa.y * c.inv_dt_sq);
@@ -124,6 +125,11 @@ SFG_DI void stage_rope_lateral(const SolverCtx& c, uint32_t p) {
     float4 v = ldb(c.V + b);
     const float im = ldb(c.MI + b).x;
     float cm = sqrtf(corr.x * corr.x + corr.y * corr.y);
+    // Deviation (f32): the reference divides by the correction's length unguarded (solver.rs:752-756). In f64 a bending
+    // correction is never exactly zero; in f32 a tiny rotation of the last segment can leave the particle's displacement
+    // bit-identical, and 0 / 0 would poison the whole pile within the tick. A zero correction created no velocity, so the
+    // clamp below is [0, 0] and the impulse is zero: skipping is the limit of the reference's formula.
+    if (SFG_GUARD(0) && cm == 0.f) return;
     float vfc = cm * c.inv_dt;
     V2 dir = mk(corr.x / cm, corr.y / cm);
     float vid = v.x * dir.x + v.y * dir.y;
@@ -315,7 +321,9 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
                     V2 no = i ? -mf.n : mf.n;
                     V2 to_prev = mk((pp.x - ps.x) + (dp.x - ds.x), (pp.y - ps.y) + (dp.y - ds.y));
                     V2 to_next = mk((pn.x - ps.x) + (dn.x - ds.x), (pn.y - ps.y) + (dn.y - ds.y));
-                    V2 nn = dot(no, to_prev) > dot(no, to_next) ? normalized(left_normal(to_prev)) : normalized(left_normal(to_next));
+                    const V2 seg = dot(no, to_prev) > dot(no, to_next) ? to_prev : to_next;
+                    if (SFG_GUARD(4) && seg.x == 0.f && seg.y == 0.f) continue;   // neighbour on top of the particle: keep the shape normal
+                    V2 nn = normalized(left_normal(seg));
                     mf.n = dot(mf.n, nn) > 0.f ? nn : -nn;
                 }
             }
@@ -490,7 +498,7 @@ SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, unsigned l
 // expensive units (they are grouped by narrowphase path) is spread over all SMs; then all CTAs meet at a barrier.
 __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
                                                              uint32_t n_stages, uint32_t sub_begin, uint32_t sub_end, uint32_t substeps,
-                                                             unsigned int* barrier_counter, unsigned long long* trace) {
+                                                             unsigned int* barrier_counter, unsigned long long* trace, uint32_t* dbg_nan) {
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
     const uint32_t first_chunk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, chunk_stride = gridDim.x * warps_per_cta;
     unsigned int target = 0;
@@ -504,6 +512,13 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
                 if (i < n) run_stage(c, st.kind, st.begin + i, last, s, st.colour, st.begin);
             }
             grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
+            if (dbg_nan) {   // debug (SFG_DEBUG_NAN): the first stage after which some body is not finite
+                for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < c.n_bodies; b += gridDim.x * blockDim.x) {
+                    if (!(__float_as_uint(ldb(c.MI + b).z) & BF_ALIVE)) continue;
+                    const float4 p = ldb(c.P + b), q = ldb(c.Q + b), v = ldb(c.V + b);
+                    if (!isfinite(p.x + p.y + p.z + p.w + q.x + q.y + v.x + v.y + v.z)) { atomicMin(dbg_nan, s * n_stages + k); atomicMin(dbg_nan + 1 + min(s * n_stages + k, 4000u), b); }
+                }
+            }
         }
     }
 }
