@@ -25,3 +25,6 @@ run("c1", scenes.c1_sandbox_stack(), 10, 1200, -6.0)
 run("c2", scenes.c2_circles(500, 200), 4, 900, -1.0)
 run("c4", scenes.c4_ropes(10000, 64, 30000), 4, 400, -8.0)
 run("c3_tenth", scenes.c3_mixed(400, 250), 4, 900, -1e9)
+if len(sys.argv) > 1 and sys.argv[1] == "big":
+    run("c5", scenes.c5_worlds(8192, 16), 4, 200, -6.0)
+    run("c3", scenes.c3_mixed(1250, 800), 4, 400, -1e9)
