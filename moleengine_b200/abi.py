@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libstarframe_gpu.so")
+LIB_PATH = os.environ.get("SFG_LIB") or os.path.join(HERE, "libstarframe_gpu.so")   # SFG_LIB: an experimental build of the same CUDA library (A/B timing)
 
 SFG_OK, SFG_E_INVALID, SFG_E_CUDA, SFG_E_CAPACITY, SFG_E_NO_DEVICE, SFG_E_STATE = 0, 1, 2, 3, 4, 5
 

@@ -98,7 +98,7 @@ struct SfgWorld {
     DBuf<float4> H, S, G0, G1, L0, L1, M0, M1, M2;
     DBuf<float2> LN;
     DBuf<float> RC;
-    DBuf<uint32_t> WL, wl_count;
+    DBuf<uint32_t> WL, wl_count, near_count;
     uint32_t last_substeps = 0;   // substeps of the last tick = tag of a manifold entry written in its last substep
     // constraint units
     uint32_t n_kunits = 0, n_k_colours = 0;
@@ -427,8 +427,14 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     colour_start[n_colours] = run;
     if (run != n_units) return fail(w, SFG_E_CAPACITY, "colouring left units uncoloured");
     // stable sort by colour: perm = unit indices in colour-major order
+    uint32_t* near_count = nullptr;
+    if (pair_units) {
+        CK(w->near_count.ensure(n_colours));
+        CK(cudaMemsetAsync(w->near_count.p, 0, size_t(n_colours) * 4, st));
+        near_count = w->near_count.p;
+    }
     k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p,
-                                                    w->frame_dt, w->ckey0.p); CKL(w); w->launches++;
+                                                    w->frame_dt, w->ckey0.p, near_count); CKL(w); w->launches++;
     k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
     int bits = 5;
     while ((1u << bits) < n_colours * 32u) ++bits;
@@ -494,7 +500,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -857,7 +863,7 @@ void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
     c.rope_next = w->rope_next.p; c.rope_prev = w->rope_prev.p; c.n_bodies = w->n_bodies;
     c.H = w->H.p; c.S = w->S.p; c.G0 = w->G0.p; c.G1 = w->G1.p; c.L0 = w->L0.p; c.L1 = w->L1.p;
     c.M0 = w->M0.p; c.M1 = w->M1.p; c.M2 = w->M2.p; c.LN = w->LN.p; c.n_units = w->n_units;
-    c.RC = w->RC.p; c.WL = w->WL.p; c.wl_count = w->wl_count.p; c.n_colours = w->n_unit_colours;
+    c.RC = w->RC.p; c.WL = w->WL.p; c.wl_count = w->wl_count.p; c.near_count = w->near_count.p; c.n_colours = w->n_unit_colours;
     c.K0 = w->K0.p; c.K1 = w->K1.p; c.K2 = w->K2.p; c.n_kunits = w->n_kunits;
     c.RU = w->RU.p; c.RD = w->RD.p; c.RPA = w->RPA.p; c.RPB = w->RPB.p; c.rp_body = w->rp_body.p; c.rp_rope = w->rp_rope.p;
     c.LAT = w->LAT.p; c.n_particles = w->n_particles;
@@ -1084,6 +1090,16 @@ int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
                     h[1 + std::min(idx, 4000u)], s, k, ns, sg.kind, sg.colour, sg.begin, sg.end);
         }
     }
+#ifdef SFG_PROBE
+    if (const char* pp = getenv("SFG_PROBE_OUT")) {
+        std::vector<unsigned long long> h(1 + 8 * 65536);
+        CK(cudaStreamSynchronize(st));
+        CK(cudaMemcpyFromSymbol(h.data(), g_probe, h.size() * 8));
+        if (FILE* f = fopen(pp, "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+        unsigned long long zero = 0;
+        CK(cudaMemcpyToSymbol(g_probe, &zero, 8));
+    }
+#endif
     if (trace_path) {
         std::vector<unsigned long long> h(trace_n);
         CK(cudaMemcpyAsync(h.data(), trace, trace_n * 8, cudaMemcpyDeviceToHost, st));

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const 
                                                         const float4* __restrict__ CS, const float4* __restrict__ CL,
                                                         const int4* __restrict__ CI, const float4* __restrict__ P,
                                                         const float4* __restrict__ Q, const float4* __restrict__ V, float frame_dt,
-                                                        uint32_t* __restrict__ keys) {
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ near_count) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     uint32_t cls = 0;
@@ -397,7 +397,14 @@ __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const 
         const float gap = mag(t1 - t0) - (bound_radius(mkshape(s0)) + bound_radius(mkshape(s1)));
         if (gap > 0.02f + 1.5f * frame_dt * mag(v1 - v0)) cls |= 16u;
     }
-    keys[u] = colour[u] * 32u + cls;
+    const uint32_t col = colour[u];
+    keys[u] = col * 32u + cls;
+    // how many units of each colour sort into its "may touch" head: the solver deals those out a few lanes per warp
+    // (sfg_solver.cuh k_solve_persistent). One atomic per group of lanes with the same colour.
+    if (near_count && !(cls & 16u)) {
+        const uint32_t peers = __match_any_sync(__activemask(), col);
+        if ((threadIdx.x & 31u) == uint32_t(__ffs(int(peers)) - 1)) atomicAdd(near_count + col, uint32_t(__popc(peers)));
+    }
 }
 
 constexpr uint32_t UNCOLOURED = 0xFFFFFFFFu;

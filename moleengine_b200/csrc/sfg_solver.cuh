@@ -237,37 +237,65 @@ SFG_DI void stage_constraint_damp(const SolverCtx& c, uint32_t u) {
     if (target >= 0 && (mi1.x != 0.f || mi1.y != 0.f)) stb(c.V + target, V1);
 }
 
+// Debug build only (-DSFG_PROBE): cycle stamps along the contact path of units that found a contact, to see where a lone
+// unit's latency goes. The stamp's predicate depends on a loaded / computed value, so it cannot issue before that value exists.
+#ifdef SFG_PROBE
+__device__ unsigned long long g_probe[1 + 8 * 65536];
+#define SFG_STAMP(i, bits) asm volatile("{ .reg .pred p; setp.ne.u32 p, %1, 0x7fc12345; @p mov.u64 %0, %%clock64; }" : "+l"(pt[i]) : "r"(uint32_t(bits)) : "memory")
+#else
+#define SFG_STAMP(i, bits)
+#endif
+
 // ---------------------------------------------------------------- contacts (solver.rs:275-490, narrowphase inline)
-SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint32_t colour_begin, uint32_t sub) {
+SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint32_t colour_begin, uint32_t sub, bool head) {
+#ifdef SFG_PROBE
+    unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    SFG_STAMP(0, u);
+#endif
     const float4 h = ldc(c.H + u);
+    // First reject, on body positions alone: colliders sit within |local offset| of their body, so bodies farther apart
+    // than RC = bounding radii + offsets (+ margin, and never below circle_circle's sqrt(0.001) rule) cannot produce a
+    // contact in any branch of intersection_check. Neither visit of the unit moves anything then, and the manifold
+    // entries keep an old tag = "no contact".
+    // A unit's latency is a chain of memory round trips followed by the arithmetic, so the loads go out in as few batches
+    // as their addresses allow: everything indexed by the unit itself together with the header, everything indexed by the
+    // two bodies right after it. Units in the head of a colour (they may touch) fetch all of it at once; the rest of the
+    // colour fetches only what the reject needs (one 16-byte gather per body) and nearly always stops there.
+    const float reach = __ldg(c.RC + u);
+    float4 l0, l1, g0, g1;
+    if (head) { l0 = ldc(c.L0 + u); l1 = ldc(c.L1 + u); g0 = ldc(c.G0 + u); g1 = ldc(c.G1 + u); }
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     const uint32_t fl = __float_as_uint(h.z);
     if (fl & UF_ASLEEP) return;
     const float mu_s = h.w;
-    // First reject, on body positions alone (one gather per body, nothing else of the unit is touched): colliders sit
-    // within |local offset| of their body, so bodies farther apart than RC = bounding radii + offsets (+ margin, and never
-    // below circle_circle's sqrt(0.001) rule) cannot produce a contact in any branch of intersection_check. Neither
-    // visit of the unit moves anything then, and the manifold entries keep an old tag = "no contact".
-    const float reach = __ldg(c.RC + u);
-    float4 P0 = make_float4(0, 0, 0, 0), P1 = P0;
-    float4 l0, l1;
-    if (b0 >= 0) P0 = ldb(c.P + b0); else l0 = ldc(c.L0 + u);
-    if (b1 >= 0) P1 = ldb(c.P + b1); else l1 = ldc(c.L1 + u);
+    const int i0 = max(b0, 0), i1 = max(b1, 0);     // a static side reads body 0's row and ignores it: no branch between the loads
+    float4 P0 = ldb(c.P + i0), P1 = ldb(c.P + i1);
+    float4 Q0, Q1, mi0, mi1;
+    if (head) { Q0 = ldb(c.Q + i0); Q1 = ldb(c.Q + i1); mi0 = ldb(c.MI + i0); mi1 = ldb(c.MI + i1); }
+    if (b0 < 0) P0 = make_float4(0, 0, 0, 0);
+    if (b1 < 0) P1 = make_float4(0, 0, 0, 0);
+    if (!head) {
+        if (b0 < 0) l0 = ldc(c.L0 + u);
+        if (b1 < 0) l1 = ldc(c.L1 + u);
+    }
     {
         const V2 a = b0 >= 0 ? mk(P0.x, P0.y) : mk(l0.x, l0.y), da = mk(P0.z, P0.w);
         const V2 b = b1 >= 0 ? mk(P1.x, P1.y) : mk(l1.x, l1.y), db = mk(P1.z, P1.w);
         const V2 d = mk((b.x - a.x) + (db.x - da.x), (b.y - a.y) + (db.y - da.y));
+        SFG_STAMP(2, __float_as_uint(d.x + d.y));
         if (mag_sq(d) > reach * reach) return;
     }
-    if (b0 >= 0) l0 = ldc(c.L0 + u);
-    if (b1 >= 0) l1 = ldc(c.L1 + u);
-    const Shape sh0 = mkshape(ldc(c.G0 + u)), sh1 = mkshape(ldc(c.G1 + u));
+    if (!head) {
+        if (b0 >= 0) l0 = ldc(c.L0 + u);
+        if (b1 >= 0) l1 = ldc(c.L1 + u);
+        g0 = ldc(c.G0 + u); g1 = ldc(c.G1 + u);
+        Q0 = ldb(c.Q + i0); Q1 = ldb(c.Q + i1); mi0 = ldb(c.MI + i0); mi1 = ldb(c.MI + i1);
+    }
+    const Shape sh0 = mkshape(g0), sh1 = mkshape(g1);
     const Iso loc0 = mkiso(mk(l0.x, l0.y), mkrot(l0.z, l0.w)), loc1 = mkiso(mk(l1.x, l1.y), mkrot(l1.z, l1.w));
-
-    float4 Q0 = make_float4(1, 0, 1, 0), Q1 = Q0;
-    float im0 = 0.f, ii0 = 0.f, im1 = 0.f, ii1 = 0.f;
-    if (b0 >= 0) { Q0 = ldb(c.Q + b0); float4 m = ldb(c.MI + b0); im0 = m.x; ii0 = m.y; }
-    if (b1 >= 0) { Q1 = ldb(c.Q + b1); float4 m = ldb(c.MI + b1); im1 = m.x; ii1 = m.y; }
+    if (b0 < 0) { Q0 = make_float4(1, 0, 1, 0); mi0 = make_float4(0, 0, 0, 0); }
+    if (b1 < 0) { Q1 = make_float4(1, 0, 1, 0); mi1 = make_float4(0, 0, 0, 0); }
+    const float im0 = mi0.x, ii0 = mi0.y, im1 = mi1.x, ii1 = mi1.y;
     // pair-local frame: origin at object 0's substep-start position (or its static translation)
     const V2 org = b0 >= 0 ? mk(P0.x, P0.y) : loc0.t;
     const V2 told0 = mk(0.f, 0.f);
@@ -287,6 +315,7 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
 
     const uint32_t tag = (sub + 1u) << 8;
     bool moved = false;
+    SFG_STAMP(3, __float_as_uint(far_sq + l0.x + l1.x + Q0.x + Q1.x + im0 + im1));
     for (int m = 0; m < mult; ++m) {
         const uint32_t e = u + uint32_t(m) * c.n_units;
         const Iso pw0 = b0 >= 0 ? mkiso(mk(P0.z, P0.w), r0) * loc0 : st0;
@@ -294,6 +323,9 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
         Manifold mf;
         mf.count = 0;
         if (!(mag_sq(pw1.t - pw0.t) > far_sq)) intersection_check(pw0, pw1, sh0, sh1, mf);
+#ifdef SFG_PROBE
+        if (m == 0) SFG_STAMP(1, __float_as_uint(mf.n.x + mf.off[0][0].x + mf.off[0][1].x + mf.off[1][0].x) + uint32_t(mf.count));
+#endif
         if (mf.count == 0) {
             // first visit found nothing: no pose changed, so the second visit finds the same nothing and the unit is done
             // without a single store. A second visit that finds nothing after a first that did must say so (fresh tag).
@@ -364,6 +396,7 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
                 }
             }
         }
+        SFG_STAMP(4 + m, __float_as_uint(lambda_n + P0.z + P1.z + r0.s + r1.s + mf.n.x));
         stb(c.M0 + e, make_float4(__int_as_float(mf.count | int(tag)), lambda_n, mf.n.x, mf.n.y));
         stb(c.M1 + e, make_float4(mf.off[0][0].x, mf.off[0][0].y, mf.off[0][1].x, mf.off[0][1].y));
         if (mf.count == 2) stb(c.M2 + e, make_float4(mf.off[1][0].x, mf.off[1][0].y, mf.off[1][1].x, mf.off[1][1].y));
@@ -381,44 +414,59 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
         if (int(lane) == leader) base = atomicAdd(c.wl_count + sub * c.n_colours + colour, uint32_t(__popc(act)));
         base = __shfl_sync(act, base, leader);
         __stcg(c.WL + colour_begin + base + uint32_t(__popc(act & ((1u << lane) - 1u))), u);
+        SFG_STAMP(6, base);
     }
+#ifdef SFG_PROBE
+    if (mult == 2 && pt[5] && c.n_colours && __popc(__activemask()) <= 2) {   // thinly dealt units only: their own latency, not a crowded warp's
+        const unsigned long long slot = atomicAdd(&g_probe[0], 1ull);
+        if (slot < 65536) for (int i = 0; i < 8; ++i) g_probe[1 + slot * 8 + i] = i == 7 ? (uint64_t(colour) << 32 | sub) : pt[i];
+    }
+#endif
 }
 
 // solver.rs:496-618
 SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u, uint32_t sub) {
+    // Only units queued by this substep's position sweep come here, so they have a contact: everything indexed by the unit
+    // (header, material, both manifold entries) is fetched in one batch, everything indexed by the bodies in a second one.
     const float4 h = ldc(c.H + u);
+    const float4 s = ldc(c.S + u);
+    const uint32_t e1 = u + c.n_units;
+    float4 m0[2], m1[2], m2[2];
+    m0[0] = ldb(c.M0 + u); m1[0] = ldb(c.M1 + u); m2[0] = ldb(c.M2 + u);
+    m0[1] = ldb(c.M0 + e1); m1[1] = ldb(c.M1 + e1); m2[1] = ldb(c.M2 + e1);      // entries [n_units, 2 n_units) exist for every unit
     const uint32_t fl = __float_as_uint(h.z);
     const int mult = (fl & UF_MULT2) ? 2 : 1;
     const uint32_t tag = sub + 1u;
-    float4 m0[2];
-    m0[0] = ldb(c.M0 + u);
-    m0[1] = mult == 2 ? ldb(c.M0 + u + c.n_units) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
+    const int i0 = max(b0, 0), i1 = max(b1, 0);
+    const float mu_d = s.z, rest_mat = s.w;
+    // old velocities and external accelerations only feed the restitution term (solver.rs:555-576): e = 0 never reads them
+    const bool bouncy = rest_mat != 0.f;
+    float4 q0 = ldb(c.Q + i0), q1 = ldb(c.Q + i1), V0 = ldb(c.V + i0), V1 = ldb(c.V + i1), mi0 = ldb(c.MI + i0), mi1 = ldb(c.MI + i1);
+    float4 OV0 = make_float4(0, 0, 0, 0), OV1 = OV0;
+    V2 ea = mk(0.f, 0.f);
+    if (bouncy) {
+        if (b0 >= 0) { OV0 = ldb(c.OV + b0); float2 a = ldb(c.EA + b0); ea = ea + mk(a.x, a.y); }
+        if (b1 >= 0) { OV1 = ldb(c.OV + b1); float2 a = ldb(c.EA + b1); ea = ea + mk(a.x, a.y); }
+    }
     int cnt[2];
 #pragma unroll
     for (int m = 0; m < 2; ++m) { const uint32_t bits = __float_as_uint(m0[m].x); cnt[m] = (bits >> 8) == tag ? int(bits & M0_COUNT_MASK) : 0; }
+    if (mult == 1) cnt[1] = 0;
     if (cnt[0] == 0 && cnt[1] == 0) return;
-    const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
-    const float4 s = ldc(c.S + u);
-    const float mu_d = s.z, rest_mat = s.w;
-    float4 V0 = make_float4(0, 0, 0, 0), V1 = V0, OV0 = V0, OV1 = V0;
-    Rot r0 = mkrot(1.f, 0.f), r1 = r0;
-    float im0 = 0.f, ii0 = 0.f, im1 = 0.f, ii1 = 0.f;
-    V2 ea = mk(0.f, 0.f);
-    // old velocities and external accelerations only feed the restitution term (solver.rs:555-576): e = 0 never reads them
-    const bool bouncy = rest_mat != 0.f;
-    if (b0 >= 0) { float4 q = ldb(c.Q + b0); r0 = mkrot(q.x, q.y); V0 = ldb(c.V + b0); float4 mi = ldb(c.MI + b0); im0 = mi.x; ii0 = mi.y;
-                   if (bouncy) { OV0 = ldb(c.OV + b0); float2 a = ldb(c.EA + b0); ea = ea + mk(a.x, a.y); } }
-    if (b1 >= 0) { float4 q = ldb(c.Q + b1); r1 = mkrot(q.x, q.y); V1 = ldb(c.V + b1); float4 mi = ldb(c.MI + b1); im1 = mi.x; ii1 = mi.y;
-                   if (bouncy) { OV1 = ldb(c.OV + b1); float2 a = ldb(c.EA + b1); ea = ea + mk(a.x, a.y); } }
+    if (b0 < 0) { q0 = make_float4(1, 0, 1, 0); V0 = make_float4(0, 0, 0, 0); mi0 = V0; }
+    if (b1 < 0) { q1 = make_float4(1, 0, 1, 0); V1 = make_float4(0, 0, 0, 0); mi1 = V1; }
+    const Rot r0 = mkrot(q0.x, q0.y), r1 = mkrot(q1.x, q1.y);
+    const float im0 = mi0.x, ii0 = mi0.y, im1 = mi1.x, ii1 = mi1.y;
     const float rest_gate = c.dt * c.dt * mag_sq(ea);
-    for (int m = 0; m < mult; ++m) {
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
         const int count = cnt[m];
         if (count == 0) continue;
-        const uint32_t e = u + uint32_t(m) * c.n_units;
         const float lambda_n = m0[m].y;
         const V2 n = mk(m0[m].z, m0[m].w), tan = left_normal(n);
         for (int k = 0; k < count; ++k) {
-            const float4 pt = k == 0 ? ldb(c.M1 + e) : ldb(c.M2 + e);
+            const float4 pt = k == 0 ? m1[m] : m2[m];
             const V2 or0 = b0 >= 0 ? r0 * mk(pt.x, pt.y) : mk(0.f, 0.f);
             const V2 or1 = b1 >= 0 ? r1 * mk(pt.z, pt.w) : mk(0.f, 0.f);
             V2 pv0 = mk(V0.x - or0.y * V0.z, V0.y + or0.x * V0.z), pv1 = mk(V1.x - or1.y * V1.z, V1.y + or1.x * V1.z);
@@ -439,8 +487,8 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u, uint32_t sub) {
             if (um < 0.0001f) continue;
             V2 dir = mk(upd.x / um, upd.y / um);
             float wd0 = wedge(or0, dir), wd1 = wedge(or1, dir);
-            float e0 = im0 + (wd0 * wd0 * ii0), e1 = im1 + (wd1 * wd1 * ii1);
-            float imp = um / (e0 + e1);
+            float e0 = im0 + (wd0 * wd0 * ii0), e1d = im1 + (wd1 * wd1 * ii1);
+            float imp = um / (e0 + e1d);
             V0.x += im0 * imp * dir.x; V0.y += im0 * imp * dir.y; V0.z += ii0 * imp * wd0;
             V1.x -= im1 * imp * dir.x; V1.y -= im1 * imp * dir.y; V1.z -= ii1 * imp * wd1;
         }
@@ -450,13 +498,13 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u, uint32_t sub) {
 }
 
 // ---------------------------------------------------------------- drivers
-SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_substep, uint32_t sub, uint32_t colour, uint32_t begin) {
+SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_substep, uint32_t sub, uint32_t colour, uint32_t begin, bool head) {
     switch (kind) {
     case ST_INTEGRATE: stage_integrate(c, i); break;
     case ST_ROPE_STEP: stage_rope_step(c, i); break;
     case ST_CONSTRAINTS: stage_constraints(c, i); break;
     case ST_PRECONTACT: stage_precontact(c, i); break;
-    case ST_CONTACTS: stage_contacts(c, i, colour, begin, sub); break;
+    case ST_CONTACTS: stage_contacts(c, i, colour, begin, sub, head); break;
     case ST_DERIVE: stage_derive(c, i, last_substep); break;
     case ST_CONTACT_VEL: stage_contact_vel(c, __ldcg(c.WL + i), sub); break;   // i indexes the colour's worklist
     case ST_CONSTRAINT_DAMP: stage_constraint_damp(c, i); break;
@@ -471,7 +519,7 @@ __global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx
                                                uint32_t colour) {
     if (KIND == ST_CONTACT_VEL) end = begin + __ldcg(c.wl_count + sub * c.n_colours + colour);   // only the units queued by the position sweep
     const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < end) run_stage(c, KIND, i, last_substep != 0, sub, colour, begin);
+    if (i < end) run_stage(c, KIND, i, last_substep != 0, sub, colour, begin, false);
 }
 
 // Grid-wide barrier of the persistent kernel: one release-atomic per CTA on a monotonically increasing counter, a
@@ -507,9 +555,19 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
         for (uint32_t k = 0; k < n_stages; ++k) {
             const Stage st = stages[k];
             const uint32_t n = st.kind == ST_CONTACT_VEL ? __ldcg(c.wl_count + s * c.n_colours + st.colour) : st.end - st.begin;
-            for (uint32_t chunk = first_chunk; chunk * 32u < n; chunk += chunk_stride) {
-                const uint32_t i = chunk * 32u + lane;
-                if (i < n) run_stage(c, st.kind, st.begin + i, last, s, st.colour, st.begin);
+            // Units that may really touch (the head of a contact colour, or a whole velocity worklist) run the long,
+            // branchy path; a stage lasts as long as its slowest warp, and a warp serialises the distinct paths of its lanes.
+            // So those units are dealt out as thinly as the machine allows — ceil(n / warps) lanes per warp — instead of 32
+            // to a warp; the cheap rest of the colour (one distance test per unit) follows in full warps.
+            uint32_t n_head = 0;
+            if (st.kind == ST_CONTACT_VEL) n_head = n;
+            else if (st.kind == ST_CONTACTS) n_head = min(__ldg(c.near_count + st.colour), n);
+            const uint32_t lanes = n_head ? min(32u, (n_head + chunk_stride - 1u) / chunk_stride) : 32u;
+            const uint32_t groups = (n_head + lanes - 1u) / lanes, items = groups + (n - n_head + 31u) / 32u;
+            for (uint32_t it = first_chunk; it < items; it += chunk_stride) {
+                const bool head = it < groups;
+                const uint32_t i = head ? it * lanes + lane : n_head + (it - groups) * 32u + lane;
+                if (head ? (lane < lanes && i < n_head) : i < n) run_stage(c, st.kind, st.begin + i, last, s, st.colour, st.begin, head);
             }
             grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
             if (dbg_nan) {   // debug (SFG_DEBUG_NAN): the first stage after which some body is not finite
