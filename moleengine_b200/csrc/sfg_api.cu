@@ -109,7 +109,9 @@ struct SfgWorld {
     DBuf<float4> K0, K1, K2;
     // persistent solver
     DBuf<Stage> d_stages;
-    DBuf<unsigned long long> trace;
+    DBuf<unsigned long long> trace, body_word;
+    DBuf<uint2> adj_slots;
+    DBuf<uint32_t> adj_rank;
     std::vector<Stage> h_stages;
     // casts
     DBuf<SfgRay> d_rays;
@@ -389,7 +391,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     while (bucket_bits < 24 && (size_t(n_units) >> bucket_bits) * 8 > size_t(grid) * 1024) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
-    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
+    CK(w->adj_slots.ensure(n_units)); CK(w->adj_rank.ensure(size_t(n_units) * 2 + 1));
+    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, w->adj_slots.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
     CKL(w); w->launches++;
     const uint32_t* order;
     {
@@ -400,11 +403,18 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     }
     CK(cudaMemsetAsync(colour.p, 0xFF, size_t(n_units) * 4, st));
     CK(cudaMemsetAsync(w->jp_counters.p, 0, (16 + HIST_CAP) * 4, st));
+    CK(w->body_word.ensure(nb + 1));
+    CK(cudaMemsetAsync(w->body_word.p, 0, size_t(nb + 1) * 8, st));
+    // list slots in use = sum of degrees <= 2 n_units; unused tail slots of the allocation are never read
+    k_adj_rank<<<nblk(n_units * 2), 256, 0, st>>>(n_units * 2, w->adj2.p, ub, w->adj_slots.p, ids, w->adj_start.p, w->adj_rank.p, w->jp_counters.p, nb);
+    CKL(w); w->launches++;
     {
         uint32_t hist_cap = HIST_CAP;
         const uint32_t* adj_start = w->adj_start.p; const uint2* adj = w->adj2.p;
         uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_counters.p + 16;
-        void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, &col, &ctrl, &hist, &hist_cap};
+        unsigned long long* words = w->body_word.p;
+        const uint2* slots = w->adj_slots.p; const uint32_t* rank = w->adj_rank.p;
+        void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, (void*)&slots, (void*)&rank, &col, &words, &ctrl, &hist, &hist_cap};
         CK(cudaLaunchCooperativeKernel((void*)k_colour_dataflow, dim3(grid), dim3(1024), args, 0, st));
         w->launches++;
     }
@@ -415,6 +425,7 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     const uint32_t n_colours = head[1];
     w->stats_jp_rounds = head[4];
     if (n_colours == 0 || n_colours > HIST_CAP) return fail(w, SFG_E_CAPACITY, "colouring did not converge or needs > 65536 colours");
+    if (head[5]) return fail(w, SFG_E_CAPACITY, "a body takes part in 2^24 or more pairs / constraints");
     std::vector<uint32_t> hist(n_colours);
     memcpy(hist.data(), head + 16, std::min<size_t>(n_colours, 64) * 4);
     if (n_colours > 64) {
@@ -500,7 +511,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->body_word.release(); w->trace.release(); w->adj_slots.release(); w->adj_rank.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);

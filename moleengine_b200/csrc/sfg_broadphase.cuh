@@ -347,14 +347,16 @@ __global__ void __launch_bounds__(256) k_constraint_unit_setup(uint32_t n_units,
 // adjacency lists body -> (unit, priority of the unit); also the bucket key of the colouring pass (descending priority)
 __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
                                                   const uint32_t* __restrict__ adj_start, uint32_t* __restrict__ cursor,
-                                                  uint2* __restrict__ adj, int bucket_shift, uint32_t* __restrict__ bucket_key,
-                                                  uint32_t* __restrict__ order) {
+                                                  uint2* __restrict__ adj, uint2* __restrict__ slots, int bucket_shift,
+                                                  uint32_t* __restrict__ bucket_key, uint32_t* __restrict__ order) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const int2 b = ub[u];
     const uint32_t p = prio[u];
-    if (b.x >= 0) adj[adj_start[b.x] + atomicAdd(cursor + b.x, 1u)] = make_uint2(u, p);
-    if (b.y >= 0) adj[adj_start[b.y] + atomicAdd(cursor + b.y, 1u)] = make_uint2(u, p);
+    uint2 sl = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);           // where the unit sits in its bodies' lists
+    if (b.x >= 0) { sl.x = adj_start[b.x] + atomicAdd(cursor + b.x, 1u); adj[sl.x] = make_uint2(u, p); }
+    if (b.y >= 0) { sl.y = adj_start[b.y] + atomicAdd(cursor + b.y, 1u); adj[sl.y] = make_uint2(u, p); }
+    slots[u] = sl;
     bucket_key[u] = (~p) >> bucket_shift;
     order[u] = u;
 }
@@ -375,54 +377,124 @@ __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const 
                                                         const int4* __restrict__ CI, const float4* __restrict__ P,
                                                         const float4* __restrict__ Q, const float4* __restrict__ V, float frame_dt,
                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ near_count) {
+    __shared__ uint32_t s_near[64];
+    if (threadIdx.x < 64) s_near[threadIdx.x] = 0u;
+    __syncthreads();
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_units) return;
-    uint32_t cls = 0;
-    if (CS) {
-        const uint2 id = ids[u];
-        const float4 s0 = CS[id.x], s1 = CS[id.y];
-        const int4 c0 = CI[id.x], c1 = CI[id.y];
-        const uint32_t k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w);
-        uint32_t path;
-        if (k0 == K_POINT && k1 == K_POINT) path = 0;
-        else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
-        else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
-        const uint32_t mult2 = (c0.x >= 0 && c1.x >= 0) ? 1u : 0u;
-        cls = path * 2 + mult2;
-        // apart now, and by more than the bodies can close in one frame at their current speed (a hint, not a proof)
-        V2 v0, v1;
-        const V2 t0 = collider_centre(c0, CL[id.x], P, Q, &v0), t1 = collider_centre(c1, CL[id.y], P, Q, &v1);
-        if (c0.x >= 0) { const float4 v = V[c0.x]; v0 = mk(v.x, v.y); }
-        if (c1.x >= 0) { const float4 v = V[c1.x]; v1 = mk(v.x, v.y); }
-        const float gap = mag(t1 - t0) - (bound_radius(mkshape(s0)) + bound_radius(mkshape(s1)));
-        if (gap > 0.02f + 1.5f * frame_dt * mag(v1 - v0)) cls |= 16u;
+    if (u < n_units) {
+        uint32_t cls = 0;
+        if (CS) {
+            const uint2 id = ids[u];
+            const float4 s0 = CS[id.x], s1 = CS[id.y];
+            const int4 c0 = CI[id.x], c1 = CI[id.y];
+            const uint32_t k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w);
+            uint32_t path;
+            if (k0 == K_POINT && k1 == K_POINT) path = 0;
+            else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
+            else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
+            const uint32_t mult2 = (c0.x >= 0 && c1.x >= 0) ? 1u : 0u;
+            cls = path * 2 + mult2;
+            // apart now, and by more than the bodies can close in one frame at their current speed (a hint, not a proof)
+            V2 v0, v1;
+            const V2 t0 = collider_centre(c0, CL[id.x], P, Q, &v0), t1 = collider_centre(c1, CL[id.y], P, Q, &v1);
+            if (c0.x >= 0) { const float4 v = V[c0.x]; v0 = mk(v.x, v.y); }
+            if (c1.x >= 0) { const float4 v = V[c1.x]; v1 = mk(v.x, v.y); }
+            const float gap = mag(t1 - t0) - (bound_radius(mkshape(s0)) + bound_radius(mkshape(s1)));
+            if (gap > 0.02f + 1.5f * frame_dt * mag(v1 - v0)) cls |= 16u;
+        }
+        const uint32_t col = colour[u];
+        keys[u] = col * 32u + cls;
+        // how many units of each colour sort into its "may touch" head: the solver deals those out a few lanes per warp
+        // (sfg_solver.cuh k_solve_persistent). Counted per block in shared memory, one global atomic per colour and block.
+        if (near_count && !(cls & 16u)) {
+            if (col < 64u) atomicAdd(&s_near[col], 1u);
+            else atomicAdd(near_count + col, 1u);
+        }
     }
-    const uint32_t col = colour[u];
-    keys[u] = col * 32u + cls;
-    // how many units of each colour sort into its "may touch" head: the solver deals those out a few lanes per warp
-    // (sfg_solver.cuh k_solve_persistent). One atomic per group of lanes with the same colour.
-    if (near_count && !(cls & 16u)) {
-        const uint32_t peers = __match_any_sync(__activemask(), col);
-        if ((threadIdx.x & 31u) == uint32_t(__ffs(int(peers)) - 1)) atomicAdd(near_count + col, uint32_t(__popc(peers)));
-    }
+    __syncthreads();
+    if (near_count && threadIdx.x < 64 && s_near[threadIdx.x]) atomicAdd(near_count + threadIdx.x, s_near[threadIdx.x]);
 }
 
 constexpr uint32_t UNCOLOURED = 0xFFFFFFFFu;
 
 // Greedy colouring in descending priority (include/sfg_hash.h): a unit takes the smallest colour unused by its
-// higher-priority neighbours. The definition is sequential; here it runs in ONE pass as a dataflow: units are
-// bucket-sorted by the top bits of the priority (k_adj_fill + one radix pass), warps take 32-unit chunks of that order
-// round-robin, and a unit simply polls the colour words of its higher-priority neighbours until all are set. The
-// result is the same fixed point Jones-Plassmann rounds converge to (bit-identical to the oracle's greedy loop),
-// without a grid barrier per round. No fences: the polled word IS the data.
-// Progress: the highest-priority uncoloured unit never waits, every unit of an earlier bucket is coloured by then, and
-// a bucket spans far fewer chunks than there are co-resident warps (checked on the host), so the warp that owns its
-// chunk has finished all its earlier chunks and is running it.
-// ctrl: [1] max colour + 1, [4] 1. hist = units per colour.
+// higher-priority neighbours (units that share a body with it). The definition is sequential; here it runs in ONE pass
+// as a dataflow with a ticket per body. Units are edges between bodies, so "the higher-priority neighbours of u" are the
+// units ahead of u in the priority order of its (at most) two bodies. Every body carries one 64-bit word
+//     ticket (24 bits: how many of its units are coloured) | mask (40 bits: which of colours 0..39 they took).
+// A unit knows its rank in each body's list (k_adj_rank) and polls the two words until both tickets equal its ranks: at that moment exactly its higher-priority neighbours are coloured, the masks ARE
+// their colours, and the unit takes the lowest free bit, ors it in and bumps both tickets — two loads and two stores per
+// unit instead of a colour word per neighbour. Only one unit at a time holds a body's current ticket, so the words need
+// no atomics, and the polled word is the data, so they need no fences. If colours 0..39 are all taken the unit falls
+// back to reading its neighbours' colour words (polled until set) for the exact smallest free colour.
+// The result is the fixed point Jones-Plassmann rounds converge to, bit-identical to the oracle's greedy loop.
+// Progress: the highest-priority uncoloured unit is never kept waiting; units are bucket-sorted by the top bits of the
+// priority (k_adj_fill + one radix pass) and dealt to warps in 32-unit chunks of that order, a bucket spans far fewer
+// chunks than there are co-resident warps (checked on the host), so the warp owning that unit's chunk is running it.
+// ctrl: [1] max colour + 1, [4] 1, [5] != 0: a body has 2^24 or more units (the host reports SFG_E_CAPACITY). hist = units per colour.
+constexpr int CM_BITS = 40;
+constexpr unsigned long long CM_MASK = (1ull << CM_BITS) - 1ull;
+SFG_DI unsigned long long ld_relaxed64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SFG_DI void st_relaxed64(unsigned long long* p, unsigned long long v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+SFG_DI bool unit_higher(uint2 vp, uint32_t pu, uint2 iu, const uint2* __restrict__ ids) {   // does neighbour vp = (unit, priority) come before (pu, iu)?
+    if (vp.y != pu) return vp.y > pu;
+    const uint2 iv = ids[vp.x];
+    return iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y);
+}
+// rank of every adjacency entry inside its body's list = how many of that body's other units come before it. One thread per
+// list slot: the lanes of a warp walk the same one to three lists, so the walk is broadcast loads (the same scan done by
+// each unit for itself touches 2 x degree scattered sectors and was most of the colouring time in crowded worlds).
+__global__ void __launch_bounds__(256) k_adj_rank(uint32_t n_slots, const uint2* __restrict__ adj, const int2* __restrict__ ub,
+                                                  const uint2* __restrict__ slots, const uint2* __restrict__ ids,
+                                                  const uint32_t* __restrict__ adj_start, uint32_t* __restrict__ rank, uint32_t* ctrl,
+                                                  uint32_t n_bodies) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_slots || q >= adj_start[n_bodies]) return;      // slots in use = sum of the degrees (static sides have no list)
+    const uint2 me = adj[q];
+    const int2 b = ub[me.x];
+    const int body = slots[me.x].x == q ? b.x : b.y;
+    const uint2 iu = ids[me.x];
+    const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
+    uint32_t r = 0;
+    for (uint32_t a = a0; a < a1; ++a) {
+        const uint2 vp = adj[a];
+        if (vp.x != me.x && unit_higher(vp, me.y, iu, ids)) ++r;
+    }
+    if (a1 - a0 >= (1u << (64 - CM_BITS))) ctrl[5] = 1u;
+    rank[q] = r;
+}
+// exact smallest colour unused by the higher-priority neighbours of u, by windows of 64 colours; every such neighbour is
+// coloured by the time this runs (its ticket came up), the poll only bridges the gap between its two stores
+SFG_DI uint32_t colour_scan_exact(uint32_t u, int2 b, uint32_t pu, uint2 iu, const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
+                                  const uint2* __restrict__ adj, const uint32_t* colour) {
+    for (uint32_t win = 0;; win += 64) {
+        unsigned long long w_used = 0ull;
+        bool w_beyond = false;
+        for (int sd = 0; sd < 2; ++sd) {
+            const int body = sd ? b.y : b.x;
+            if (body < 0 || (sd && b.y == b.x)) continue;
+            for (uint32_t q = adj_start[body], q1 = adj_start[body + 1]; q < q1; ++q) {
+                const uint2 vp = adj[q];
+                if (vp.x == u || !unit_higher(vp, pu, iu, ids)) continue;
+                uint32_t cv;
+                while ((cv = ld_relaxed(colour + vp.x)) == 0xFFFFFFFFu) __nanosleep(40);
+                if (cv >= win && cv < win + 64) w_used |= 1ull << (cv - win);
+                else if (cv >= win + 64) w_beyond = true;
+            }
+        }
+        if (w_used != ~0ull) return win + uint32_t(__ffsll((long long)~w_used) - 1);
+        if (!w_beyond) return win + 64;
+    }
+}
 __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, const uint32_t* __restrict__ order, const int2* __restrict__ ub,
                                                          const uint32_t* __restrict__ prio, const uint2* __restrict__ ids,
                                                          const uint32_t* __restrict__ adj_start, const uint2* __restrict__ adj,
-                                                         uint32_t* colour, uint32_t* ctrl, uint32_t* hist, uint32_t hist_cap) {
+                                                         const uint2* __restrict__ slots, const uint32_t* __restrict__ rank,
+                                                         uint32_t* colour, unsigned long long* body_word, uint32_t* ctrl, uint32_t* hist, uint32_t hist_cap) {
     __shared__ uint32_t s_hist[64];
     __shared__ uint32_t s_max;
     if (threadIdx.x < 64) s_hist[threadIdx.x] = 0;
@@ -437,63 +509,27 @@ __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, cons
         uint32_t u = 0, pu = 0;
         int2 b = make_int2(-1, -1);
         uint2 iu = make_uint2(0, 0);
-        if (!done) { u = order[idx]; b = ub[u]; pu = prio[u]; iu = ids[u]; }
-        // the scan keeps its place across retries: side, position in that body's list, colours 0..63 seen so far
-        int side = 0;
-        uint32_t a = 0, a1 = 0;
-        unsigned long long used = 0ull;
-        bool beyond = false, side_open = false;
+        unsigned long long want0 = 0, want1 = 0;        // ticket the body must show, already shifted
+        uint32_t step0 = 1;                            // a unit whose two sides are the same body sits twice in that list
+        if (!done) {
+            u = order[idx]; b = ub[u]; pu = prio[u]; iu = ids[u];
+            const uint2 sl = slots[u];
+            if (b.x >= 0) want0 = (unsigned long long)rank[sl.x] << CM_BITS;
+            if (b.y == b.x && b.x >= 0) { b.y = -1; step0 = 2; }
+            if (b.y >= 0) want1 = (unsigned long long)rank[sl.y] << CM_BITS;
+        }
         while (__any_sync(0xFFFFFFFFu, !done)) {
             if (!done) {
-                bool ready = true;
-                while (side < 2) {
-                    if (!side_open) {
-                        const int body = side ? b.y : b.x;
-                        if (body < 0) { ++side; continue; }
-                        a = adj_start[body]; a1 = adj_start[body + 1]; side_open = true;
-                    }
-                    for (; a < a1; ++a) {
-                        const uint2 vp = adj[a];
-                        if (vp.x == u) continue;
-                        bool higher = vp.y > pu;
-                        if (vp.y == pu) { const uint2 iv = ids[vp.x]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
-                        if (!higher) continue;
-                        const uint32_t cv = ld_relaxed(colour + vp.x);
-                        if (cv == UNCOLOURED) { ready = false; break; }
-                        if (cv < 64) used |= 1ull << cv; else beyond = true;
-                    }
-                    if (!ready) break;
-                    ++side; side_open = false;
-                }
-                if (ready) {
-                    uint32_t result;
-                    if (used != ~0ull) result = uint32_t(__ffsll((long long)~used) - 1);
-                    else if (!beyond) result = 64;
-                    else {
-                        // more than 64 colours around this unit (rare): every higher neighbour is coloured by now, rescan by windows
-                        result = 0;
-                        for (uint32_t win = 64;; win += 64) {
-                            unsigned long long w_used = 0ull;
-                            bool w_beyond = false;
-                            for (int sd = 0; sd < 2; ++sd) {
-                                const int body = sd ? b.y : b.x;
-                                if (body < 0) continue;
-                                for (uint32_t q = adj_start[body], q1 = adj_start[body + 1]; q < q1; ++q) {
-                                    const uint2 vp = adj[q];
-                                    if (vp.x == u) continue;
-                                    bool higher = vp.y > pu;
-                                    if (vp.y == pu) { const uint2 iv = ids[vp.x]; higher = iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y); }
-                                    if (!higher) continue;
-                                    const uint32_t cv = ld_relaxed(colour + vp.x);
-                                    if (cv >= win && cv < win + 64) w_used |= 1ull << (cv - win);
-                                    else if (cv >= win + 64) w_beyond = true;
-                                }
-                            }
-                            if (w_used != ~0ull) { result = win + uint32_t(__ffsll((long long)~w_used) - 1); break; }
-                            if (!w_beyond) { result = win + 64; break; }
-                        }
-                    }
+                const unsigned long long w0 = b.x >= 0 ? ld_relaxed64(body_word + b.x) : 0ull;
+                const unsigned long long w1 = b.y >= 0 ? ld_relaxed64(body_word + b.y) : 0ull;
+                if ((w0 & ~CM_MASK) == want0 && (w1 & ~CM_MASK) == want1) {
+                    const unsigned long long used = (w0 | w1) & CM_MASK;
+                    const int2 bb = step0 == 2 ? make_int2(b.x, b.x) : b;
+                    const uint32_t result = used != CM_MASK ? uint32_t(__ffsll((long long)~used) - 1) : colour_scan_exact(u, bb, pu, iu, ids, adj_start, adj, colour);
                     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(colour + u), "r"(result) : "memory");
+                    const unsigned long long bit = result < uint32_t(CM_BITS) ? 1ull << result : 0ull;
+                    if (b.x >= 0) st_relaxed64(body_word + b.x, (w0 | bit) + ((unsigned long long)step0 << CM_BITS));
+                    if (b.y >= 0) st_relaxed64(body_word + b.y, (w1 | bit) + (1ull << CM_BITS));
                     if (result < 64) atomicAdd(&s_hist[result], 1u);
                     else if (result < hist_cap) atomicAdd(hist + result, 1u);
                     atomicMax(&s_max, result + 1u);
