@@ -244,6 +244,9 @@ int sfg_query_shape_batch(SfgWorld* w, uint32_t n, const SfgShapeQuery* queries,
 /* ---- parity hooks (tests only; not part of the drop-in surface) ---- */
 /* candidate pairs of the last tick as [later, earlier] collider slots, unsorted */
 int sfg_debug_get_pairs(SfgWorld* w, uint32_t* out_pairs, size_t capacity_pairs, size_t* n_out);
+/* per pair, in the same order: 1 = the pair may touch during the tick. A scheduling hint computed at tick start that is the
+ * top bit of the pair's colouring priority (include/sfg_hash.h); the CPU oracle is fed these bits to replay the same order */
+int sfg_debug_get_pair_hints(SfgWorld* w, uint8_t* out_hints, size_t capacity_pairs, size_t* n_out);
 /* contact entries of the last tick: (collider_hi, collider_lo | copy<<31) and colour */
 int sfg_debug_get_contact_entries(SfgWorld* w, uint32_t* out_hi, uint32_t* out_lo_copy, uint32_t* out_colour,
                                   size_t capacity, size_t* n_out);

@@ -388,7 +388,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     // a bucket must span far fewer units than the co-resident threads (progress argument in k_colour_dataflow):
     // 2^bits buckets of ~n / 2^bits units each (priorities are hashes), kept under 1/8 of the resident threads
     int bucket_bits = 8;
-    while (bucket_bits < 24 && (size_t(n_units) >> bucket_bits) * 8 > size_t(grid) * 1024) bucket_bits += 8;
+    // (the `near` bit splits the priority space in two halves that need not be equally full: allow for buckets twice the mean)
+    while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * 8 > size_t(grid) * 1024) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
     CK(w->adj_slots.ensure(n_units)); CK(w->adj_rank.ensure(size_t(n_units) * 2 + 1));
@@ -444,8 +445,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         CK(cudaMemsetAsync(w->near_count.p, 0, size_t(n_colours) * 4, st));
         near_count = w->near_count.p;
     }
-    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p,
-                                                    w->frame_dt, w->ckey0.p, near_count); CKL(w); w->launches++;
+    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CI.p, prio, w->ckey0.p, near_count);
+    CKL(w); w->launches++;
     k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
     int bits = 5;
     while ((1u << bits) < n_colours * 32u) ++bits;
@@ -835,7 +836,7 @@ int build_graph(SfgWorld* w) {
         const uint32_t n = w->n_units;
         CK(w->U_ub.ensure(n)); CK(w->U_prio.ensure(n));
         CK(cudaMemsetAsync(w->deg.p, 0, size_t(nb + 2) * 4, st));
-        k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->U_ub.p, w->U_prio.p, w->deg.p);
+        k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->CS.p, w->CL.p, w->P.p, w->Q.p, w->V.p, w->frame_dt, w->U_ub.p, w->U_prio.p, w->deg.p);
         CKL(w); w->launches++;
         uint32_t* perm = nullptr;
         int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours, true);
@@ -1401,6 +1402,19 @@ int sfg_debug_get_pairs(SfgWorld* w, uint32_t* out_pairs, size_t capacity_pairs,
     const size_t n = std::min<size_t>(capacity_pairs, w->n_units);
     CK(cudaMemcpyAsync(out_pairs, w->U_ids.p, n * sizeof(uint2), cudaMemcpyDeviceToHost, w->stream));
     CK(cudaStreamSynchronize(w->stream));
+    return SFG_OK;
+}
+// the `near` bit of each pair's colouring priority, in the order of sfg_debug_get_pairs (include/sfg_hash.h)
+int sfg_debug_get_pair_hints(SfgWorld* w, uint8_t* out_hints, size_t capacity_pairs, size_t* n_out) {
+    if (!w || !n_out) return SFG_E_INVALID;
+    *n_out = w->n_units;
+    if (!out_hints || w->n_units == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    const size_t n = std::min<size_t>(capacity_pairs, w->n_units);
+    std::vector<uint32_t> prio(n);
+    CK(cudaMemcpyAsync(prio.data(), w->U_prio.p, n * 4, cudaMemcpyDeviceToHost, w->stream));
+    CK(cudaStreamSynchronize(w->stream));
+    for (size_t i = 0; i < n; ++i) out_hints[i] = uint8_t(prio[i] >> 31);
     return SFG_OK;
 }
 // pair units in the solver's colour-major order: hi, lo | mult2 << 31, colour

@@ -316,17 +316,34 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
 
 // ---------------------------------------------------------------- graph colouring
 // unit = one candidate pair (or one user constraint); ub = its dynamic bodies (or -1); prio = sfg_hash3
+SFG_DI V2 collider_centre(int4 ci, float4 l, const float4* __restrict__ P, const float4* __restrict__ Q) {
+    if (ci.x < 0) return mk(l.x, l.y);
+    const float4 p = P[ci.x], q = Q[ci.x];
+    return mkrot(q.x, q.y) * mk(l.x, l.y) + mk(p.x + p.z, p.y + p.w);
+}
+// per candidate pair: the bodies it couples (only bodies that see forces count for conflicts), its colouring priority
+// (include/sfg_hash.h) and the degree of its bodies. The priority's top bit is the `near` hint: the colliders' bounding
+// circles are closer than the bodies can come in one frame at their current relative speed (a hint, not a proof).
 __global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const uint2* __restrict__ ids, const int4* __restrict__ CI,
-                                                         const float4* __restrict__ MI, int2* __restrict__ ub, uint32_t* __restrict__ prio,
-                                                         uint32_t* __restrict__ deg) {
+                                                         const float4* __restrict__ MI, const float4* __restrict__ CS,
+                                                         const float4* __restrict__ CL, const float4* __restrict__ P,
+                                                         const float4* __restrict__ Q, const float4* __restrict__ V, float frame_dt,
+                                                         int2* __restrict__ ub, uint32_t* __restrict__ prio, uint32_t* __restrict__ deg) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const uint2 id = ids[u];
-    int b0 = CI[id.x].x, b1 = CI[id.y].x;
+    const int4 c0 = CI[id.x], c1 = CI[id.y];
+    int b0 = c0.x, b1 = c1.x;
+    V2 v0 = mk(0.f, 0.f), v1 = v0;
+    if (b0 >= 0) { const float4 v = V[b0]; v0 = mk(v.x, v.y); }
+    if (b1 >= 0) { const float4 v = V[b1]; v1 = mk(v.x, v.y); }
+    const V2 t0 = collider_centre(c0, CL[id.x], P, Q), t1 = collider_centre(c1, CL[id.y], P, Q);
+    const float gap = mag(t1 - t0) - (bound_radius(mkshape(CS[id.x])) + bound_radius(mkshape(CS[id.y])));
+    const bool near_hint = !(gap > 0.02f + 1.5f * frame_dt * mag(v1 - v0));
     if (b0 >= 0 && !(__float_as_uint(MI[b0].z) & (BF_MASS | BF_INERTIA))) b0 = -1;
     if (b1 >= 0 && !(__float_as_uint(MI[b1].z) & (BF_MASS | BF_INERTIA))) b1 = -1;
     ub[u] = make_int2(b0, b1);
-    prio[u] = sfg_hash3(id.x, id.y, 0u);
+    prio[u] = sfg_pair_priority(id.x, id.y, near_hint ? 1u : 0u);
     if (b0 >= 0) atomicAdd(deg + b0, 1u);
     if (b1 >= 0) atomicAdd(deg + b1, 1u);
 }
@@ -366,17 +383,10 @@ __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* 
 // rest are grouped by narrowphase path (circle-circle / circle-polygon by polygon kind / polygon-polygon by edge count)
 // and visit count, so the 32 lanes of a warp run the same branches. The order inside a colour cannot change results
 // (no shared dynamic body), only divergence.
-SFG_DI V2 collider_centre(int4 ci, float4 l, const float4* __restrict__ P, const float4* __restrict__ Q, V2* vel) {
-    *vel = mk(0.f, 0.f);
-    if (ci.x < 0) return mk(l.x, l.y);
-    const float4 p = P[ci.x], q = Q[ci.x];
-    return mkrot(q.x, q.y) * mk(l.x, l.y) + mk(p.x + p.z, p.y + p.w);
-}
 __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const uint32_t* __restrict__ colour, const uint2* __restrict__ ids,
-                                                        const float4* __restrict__ CS, const float4* __restrict__ CL,
-                                                        const int4* __restrict__ CI, const float4* __restrict__ P,
-                                                        const float4* __restrict__ Q, const float4* __restrict__ V, float frame_dt,
-                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ near_count) {
+                                                        const float4* __restrict__ CS, const int4* __restrict__ CI,
+                                                        const uint32_t* __restrict__ prio, uint32_t* __restrict__ keys,
+                                                        uint32_t* __restrict__ near_count) {
     __shared__ uint32_t s_near[64];
     if (threadIdx.x < 64) s_near[threadIdx.x] = 0u;
     __syncthreads();
@@ -385,22 +395,14 @@ __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const 
         uint32_t cls = 0;
         if (CS) {
             const uint2 id = ids[u];
-            const float4 s0 = CS[id.x], s1 = CS[id.y];
-            const int4 c0 = CI[id.x], c1 = CI[id.y];
-            const uint32_t k0 = __float_as_uint(s0.w), k1 = __float_as_uint(s1.w);
+            const uint32_t k0 = __float_as_uint(CS[id.x].w), k1 = __float_as_uint(CS[id.y].w);
             uint32_t path;
             if (k0 == K_POINT && k1 == K_POINT) path = 0;
             else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
             else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
-            const uint32_t mult2 = (c0.x >= 0 && c1.x >= 0) ? 1u : 0u;
+            const uint32_t mult2 = (CI[id.x].x >= 0 && CI[id.y].x >= 0) ? 1u : 0u;
             cls = path * 2 + mult2;
-            // apart now, and by more than the bodies can close in one frame at their current speed (a hint, not a proof)
-            V2 v0, v1;
-            const V2 t0 = collider_centre(c0, CL[id.x], P, Q, &v0), t1 = collider_centre(c1, CL[id.y], P, Q, &v1);
-            if (c0.x >= 0) { const float4 v = V[c0.x]; v0 = mk(v.x, v.y); }
-            if (c1.x >= 0) { const float4 v = V[c1.x]; v1 = mk(v.x, v.y); }
-            const float gap = mag(t1 - t0) - (bound_radius(mkshape(s0)) + bound_radius(mkshape(s1)));
-            if (gap > 0.02f + 1.5f * frame_dt * mag(v1 - v0)) cls |= 16u;
+            if (!(prio[u] >> 31)) cls |= 16u;                                                 // not `near` (k_pair_unit_setup): goes last
         }
         const uint32_t col = colour[u];
         keys[u] = col * 32u + cls;

@@ -555,6 +555,9 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
         for (uint32_t k = 0; k < n_stages; ++k) {
             const Stage st = stages[k];
             const uint32_t n = st.kind == ST_CONTACT_VEL ? __ldcg(c.wl_count + s * c.n_colours + st.colour) : st.end - st.begin;
+            // an empty velocity worklist (the high colours hold only pairs that did not touch): no work and no barrier. The count
+            // was final before the barrier of the derive stage, so every CTA takes the same branch.
+            if (st.kind == ST_CONTACT_VEL && n == 0u) continue;
             // Units that may really touch (the head of a contact colour, or a whole velocity worklist) run the long,
             // branchy path; a stage lasts as long as its slowest warp, and a warp serialises the distinct paths of its lanes.
             // So those units are dealt out as thinly as the machine allows — ceil(n / warps) lanes per warp — instead of 32

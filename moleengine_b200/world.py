@@ -175,6 +175,15 @@ class GpuWorld:
             self._ck(self.lib.sfg_debug_get_pairs(self.h, abi.ptr(out), n.value, C.byref(n)))
         return out
 
+    def debug_pair_hints(self):
+        """Per pair of debug_pairs(): 1 = `near` (top bit of the colouring priority, include/sfg_hash.h)."""
+        n = C.c_size_t()
+        self._ck(self.lib.sfg_debug_get_pair_hints(self.h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, np.uint8)
+        if n.value:
+            self._ck(self.lib.sfg_debug_get_pair_hints(self.h, abi.ptr(out), n.value, C.byref(n)))
+        return out
+
     def debug_contact_units(self):
         n = C.c_size_t()
         self._ck(self.lib.sfg_debug_get_contact_entries(self.h, None, None, None, 0, C.byref(n)))

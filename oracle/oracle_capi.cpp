@@ -19,6 +19,7 @@ void sfo_set_colliders(void* w, uint32_t n, const SfgCollider* c) { static_cast<
 void sfo_set_constraints(void* w, uint32_t n, const SfgConstraint* c) { static_cast<IWorld*>(w)->set_constraints(n, c); }
 void sfo_set_ropes(void* w, uint32_t nr, const SfgRope* r, uint32_t np, const int32_t* p) { static_cast<IWorld*>(w)->set_ropes(nr, r, np, p); }
 void sfo_set_external_pairs(void* w, const uint32_t* hl, size_t n) { static_cast<IWorld*>(w)->set_external_pairs(hl, n); }
+void sfo_set_external_pair_hints(void* w, const uint32_t* hl, const uint8_t* hints, size_t n) { static_cast<IWorld*>(w)->set_external_pair_hints(hl, hints, n); }
 void sfo_tick(void* w, double frame_dt, int has_scale, double scale, const SfgForceField* ff, int mode, int threads) {
     static_cast<IWorld*>(w)->tick(frame_dt, has_scale != 0, scale, *ff, mode, threads);
 }

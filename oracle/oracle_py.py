@@ -38,6 +38,7 @@ def load():
             "sfo_set_bodies": [vp, C.c_uint32, vp], "sfo_set_colliders": [vp, C.c_uint32, vp],
             "sfo_set_constraints": [vp, C.c_uint32, vp], "sfo_set_ropes": [vp, C.c_uint32, vp, C.c_uint32, vp],
             "sfo_set_external_pairs": [vp, vp, C.c_size_t],
+            "sfo_set_external_pair_hints": [vp, vp, vp, C.c_size_t],
             "sfo_tick": [vp, C.c_double, C.c_int, C.c_double, vp, C.c_int, C.c_int],
             "sfo_get_bodies": [vp, C.c_uint32, C.c_uint32, vp], "sfo_n_pairs": [vp], "sfo_get_pairs": [vp, vp],
             "sfo_n_pair_units": [vp], "sfo_get_pair_units": [vp, vp, vp, vp, vp], "sfo_n_constraint_units": [vp],
@@ -95,9 +96,20 @@ class OracleWorld:
         self.lib.sfo_set_bodies(self.h, len(b), _p(b))
         self.n_bodies = len(b)
 
-    def set_external_pairs(self, pairs):
+    def set_external_pairs(self, pairs, hints=None):
+        """Candidate pairs of the device's broadphase and, for MODE_COLOURED, the `near` bit the device put in front of each
+        pair's colouring priority (GpuWorld.debug_pair_hints; include/sfg_hash.h). Without hints every pair counts as near."""
         p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
         self.lib.sfo_set_external_pairs(self.h, _p(p), len(p))
+        if hints is not None:
+            self.set_pair_hints(p, hints)
+
+    def set_pair_hints(self, pairs, hints):
+        """Only the `near` bits, keyed by pair: the oracle keeps finding the pairs with its own BVH."""
+        p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        h = np.ascontiguousarray(hints, np.uint8)
+        assert len(h) == len(p)
+        self.lib.sfo_set_external_pair_hints(self.h, _p(p), _p(h), len(p))
 
     def tick(self, frame_dt=1.0 / 60.0, time_scale=None, forcefield=None, mode=MODE_REFERENCE, threads=1):
         from moleengine_b200 import abi  # record dtypes only (no device code is touched)

@@ -21,6 +21,7 @@
 #include <array>
 #include <cstring>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 #include "../include/sfg_hash.h"
 #include "../include/starframe_gpu.h"
@@ -72,7 +73,7 @@ struct RopeS {                       // rope.rs:16-50 (solver-visible part)
     std::vector<int32_t> particles;  // body slots
 };
 
-struct PairUnit { uint32_t hi, lo, mult, colour; };       // one candidate pair, solved `mult` times
+struct PairUnit { uint32_t hi, lo, mult, colour, near_hint; };   // one candidate pair, solved `mult` times; near_hint: include/sfg_hash.h
 struct ConstraintUnit { uint32_t idx, mult, colour; };
 
 template <class R>
@@ -87,6 +88,7 @@ struct IWorld {
     virtual void set_constraints(uint32_t n, const SfgConstraint* c) = 0;
     virtual void set_ropes(uint32_t nr, const SfgRope* r, uint32_t np, const int32_t* p) = 0;
     virtual void set_external_pairs(const uint32_t* hi_lo, size_t n) = 0;
+    virtual void set_external_pair_hints(const uint32_t* hi_lo, const uint8_t* hints, size_t n) = 0;
     virtual void tick(double frame_dt, bool has_scale, double scale, const SfgForceField& ff, int mode,
                       int threads) = 0;
     virtual void get_bodies(uint32_t first, uint32_t count, double* out7) const = 0;
@@ -186,6 +188,11 @@ public:
     void set_external_pairs(const uint32_t* hl, size_t n) override {
         ext_pairs_.assign(hl, hl + 2 * n);
         use_ext_pairs_ = true;
+    }
+    // the `near` bit of each pair's colouring priority as the device computed it (include/sfg_hash.h); pairs without a hint count as near
+    void set_external_pair_hints(const uint32_t* hl, const uint8_t* hints, size_t n) override {
+        ext_hints_.clear();
+        for (size_t i = 0; i < n; ++i) ext_hints_[(uint64_t(hl[2 * i]) << 32) | hl[2 * i + 1]] = hints[i];
     }
 
     // ------------------------------------------------------------------ helpers
@@ -595,14 +602,16 @@ public:
         pair_units.clear();
         for (size_t p = 0; p + 1 < kept_pairs.size(); p += 2) {
             uint32_t hi = kept_pairs[p], lo = kept_pairs[p + 1];
-            pair_units.push_back({hi, lo, (cbody(hi) >= 0 && cbody(lo) >= 0) ? 2u : 1u, 0});
+            uint32_t near_hint = 1u;
+            if (!ext_hints_.empty()) { auto it = ext_hints_.find((uint64_t(hi) << 32) | lo); if (it != ext_hints_.end()) near_hint = it->second ? 1u : 0u; }
+            pair_units.push_back({hi, lo, (cbody(hi) >= 0 && cbody(lo) >= 0) ? 2u : 1u, 0, near_hint});
         }
         constraint_units.clear();
         for (size_t i = 0; i < constraints.size(); ++i) constraint_units.push_back({uint32_t(i), constraints[i].target >= 0 ? 2u : 1u, 0});
         typedef std::array<uint32_t, 4> P4;
         stat_colours_pairs = colour_units(pair_units, bodies.size(),
             [&](const PairUnit& u, int32_t* bs) { bs[0] = dyn_body(cbody(u.hi)); bs[1] = dyn_body(cbody(u.lo)); },
-            [](const PairUnit& u) { return P4{{sfg_hash3(u.hi, u.lo, 0), u.hi, u.lo, 0}}; });
+            [](const PairUnit& u) { return P4{{sfg_pair_priority(u.hi, u.lo, u.near_hint), u.hi, u.lo, 0}}; });
         stat_colours_constr = colour_units(constraint_units, bodies.size(),
             [&](const ConstraintUnit& u, int32_t* bs) { bs[0] = dyn_body(constraints[u.idx].owner); bs[1] = dyn_body(constraints[u.idx].target); },
             [](const ConstraintUnit& u) { return P4{{sfg_hash3(u.idx, SFG_CONSTRAINT_TAG, 0), u.idx, 0, 0}}; });
@@ -1113,6 +1122,7 @@ public:
 private:
     std::vector<uint32_t> ext_pairs_;
     bool use_ext_pairs_ = false;
+    std::unordered_map<uint64_t, uint8_t> ext_hints_;
 };
 
 }  // namespace sfo

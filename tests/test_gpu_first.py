@@ -26,6 +26,7 @@ def test_pairs_and_colours_bit_exact(oracle, scene_fn):
     g.tick()
     o32 = oracle.OracleWorld(use_f32=True, tuning=tun)
     o32.load_scene(sc)
+    o32.set_pair_hints(g.debug_pairs(), g.debug_pair_hints())   # the `near` bit of the priorities (include/sfg_hash.h); pairs come from the oracle's own BVH
     o32.tick(mode=oracle.MODE_COLOURED)
     # AABBs bit-exact against the f32 oracle
     ga = g.debug_aabbs(len(sc["colliders"]))
@@ -57,7 +58,7 @@ def test_tick_matches_oracle_replay(oracle, substeps, separate):
     g.tick()
     o = oracle.OracleWorld(tuning=tun)
     o.load_scene(sc)
-    o.set_external_pairs(g.debug_pairs())
+    o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
     o.tick(mode=oracle.MODE_COLOURED)
     tol = 1e-4 if substeps == 1 else 1e-3
     r = parity.compare_tick(g, o, sc, tol_state=tol, hops=3 if substeps == 1 else 8)

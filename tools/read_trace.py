@@ -14,6 +14,8 @@ print(f"{'stage':16s} {'units':>8s} {'first_arr':>9s} {'last_arr':>9s} {'release
 for s in range(n_sub):
     for k in range(ns):
         arr, rel = t[s, k, :, 0], t[s, k, :, 1]
+        if arr.max() == 0:      # stage skipped (empty velocity worklist)
+            continue
         start = prev_release if prev_release is not None else t0
         first, last, release = (arr.min() - start) / 1e3, (arr.max() - start) / 1e3, (rel.max() - start) / 1e3
         prev_release = rel.max()
