@@ -90,6 +90,7 @@ struct SfgWorld {
     DBuf<int4> SI;
     // pair units
     uint32_t n_units = 0, n_unit_colours = 0, prev_pairs = 0, stats_jp_rounds = 0;
+    bool bouncy_seen = false;      // a collider with restitution != 0 was uploaded
     std::vector<uint32_t> unit_colour_start;   // n_unit_colours + 1
     DBuf<uint2> U_ids;
     DBuf<int2> U_ub;
@@ -584,6 +585,7 @@ static int upload_colliders(SfgWorld* w, uint32_t first, uint32_t count, const S
         if (c[i].kind > SFG_POLY_HEXAGON) return fail(w, SFG_E_INVALID, "unknown collider polygon kind");
         if (c[i].layer >= 64) return fail(w, SFG_E_INVALID, "collider layer must be < 64");
         if (c[i].body >= 0 && uint32_t(c[i].body) >= w->n_bodies) return fail(w, SFG_E_INVALID, "collider body slot out of range (set bodies first)");
+        if (c[i].restitution != 0.0f) w->bouncy_seen = true;     // sticky until the next full upload: old velocities are kept only for worlds that bounce
     }
     cudaStream_t st = w->stream;
     CK(w->stage.ensure(size_t(count) * sizeof(SfgCollider)));
@@ -599,6 +601,7 @@ int sfg_set_colliders(SfgWorld* w, uint32_t n, const SfgCollider* c) {
     CK(w->CS.ensure(n)); CK(w->CL.ensure(n)); CK(w->CM.ensure(n)); CK(w->CI.ensure(n)); CK(w->AABB.ensure(n));
     w->n_colls = n;
     w->ticked = false;
+    w->bouncy_seen = false;
     return upload_colliders(w, 0, n, c);
 }
 int sfg_update_colliders(SfgWorld* w, uint32_t first, uint32_t count, const SfgCollider* c) {
@@ -872,7 +875,7 @@ int build_graph(SfgWorld* w) {
 void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
     memset(&c, 0, sizeof(c));
     c.P = w->P.p; c.Q = w->Q.p; c.V = w->V.p; c.OV = w->OV.p; c.MI = w->MI.p; c.EA = w->EA.p; c.PCD = w->PCD.p;
-    c.rope_next = w->rope_next.p; c.rope_prev = w->rope_prev.p; c.n_bodies = w->n_bodies;
+    c.rope_next = w->rope_next.p; c.rope_prev = w->rope_prev.p; c.n_bodies = w->n_bodies; c.bouncy = w->bouncy_seen ? 1u : 0u;
     c.H = w->H.p; c.S = w->S.p; c.G0 = w->G0.p; c.G1 = w->G1.p; c.L0 = w->L0.p; c.L1 = w->L1.p;
     c.M0 = w->M0.p; c.M1 = w->M1.p; c.M2 = w->M2.p; c.LN = w->LN.p; c.n_units = w->n_units;
     c.RC = w->RC.p; c.WL = w->WL.p; c.wl_count = w->wl_count.p; c.near_count = w->near_count.p; c.n_colours = w->n_unit_colours;

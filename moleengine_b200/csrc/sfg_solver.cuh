@@ -32,36 +32,35 @@ SFG_DI V2 force_at(const ForceParams& ff, V2 pos) {
     return acc;
 }
 
-// solver.rs:57-74 + physics.rs:78-83
-SFG_DI void stage_integrate(const SolverCtx& c, uint32_t i) {
-    float4 mi = ldb(c.MI + i);
+// solver.rs:57-74 + physics.rs:78-83. The columns are passed in so that the persistent kernel can fetch several bodies'
+// worth of them before the first is used (a streaming stage is otherwise a chain of dependent round trips per warp).
+SFG_DI void integrate_body(const SolverCtx& c, uint32_t i, float4 mi, float4 p, float4 q, float4 v) {
     const uint32_t fl = __float_as_uint(mi.z);
     if ((fl & (BF_ALIVE | BF_ASLEEP)) != BF_ALIVE) return;   // sleeping islands are skipped entirely (physics.rs:798-803)
-    float4 p = ldb(c.P + i), q = ldb(c.Q + i), v = ldb(c.V + i);
     V2 pos = mk(p.x + p.z, p.y + p.w);
     if (!(fl & BF_NOGRAV) && (fl & BF_MASS)) {
         V2 a = force_at(c.ff, pos);
         v.x += a.x * c.dt; v.y += a.y * c.dt;
-        stb(c.EA + i, make_float2(a.x, a.y));
+        if (c.bouncy) stb(c.EA + i, make_float2(a.x, a.y));
     }
-    stb(c.OV + i, v);
+    if (c.bouncy) stb(c.OV + i, v);                          // restitution is the only reader (stage_contact_vel)
     stb(c.V + i, v);
     Rot r = rot_from_angle(v.z * c.dt) * mkrot(q.x, q.y);
     stb(c.P + i, make_float4(pos.x, pos.y, v.x * c.dt, v.y * c.dt));
     stb(c.Q + i, make_float4(r.s, r.b, q.x, q.y));
 }
+SFG_DI void stage_integrate(const SolverCtx& c, uint32_t i) { integrate_body(c, i, ldb(c.MI + i), ldb(c.P + i), ldb(c.Q + i), ldb(c.V + i)); }
 
 // solver.rs:91-97 (+ fold of the displacement into the position after the last substep)
-SFG_DI void stage_derive(const SolverCtx& c, uint32_t i, bool fold) {
-    float4 mi = ldb(c.MI + i);
+SFG_DI void derive_body(const SolverCtx& c, uint32_t i, bool fold, float4 mi, float4 p, float4 q, float4 v) {
     if ((__float_as_uint(mi.z) & (BF_ALIVE | BF_ASLEEP)) != BF_ALIVE) return;
-    float4 p = ldb(c.P + i), q = ldb(c.Q + i), v = ldb(c.V + i);
     v.x = p.z * c.inv_dt; v.y = p.w * c.inv_dt;
     Rot d = mkrot(q.x, q.y) * mkrot(q.z, -q.w);
     v.z = (-atan2f(d.b, d.s) * 2.0f) * c.inv_dt;
     stb(c.V + i, v);
     if (fold) stb(c.P + i, make_float4(p.x + p.z, p.y + p.w, 0.f, 0.f));
 }
+SFG_DI void stage_derive(const SolverCtx& c, uint32_t i, bool fold) { derive_body(c, i, fold, ldb(c.MI + i), ldb(c.P + i), ldb(c.Q + i), ldb(c.V + i)); }
 
 // ---------------------------------------------------------------- ropes (solver.rs:114-181)
 SFG_DI void stage_rope_step(const SolverCtx& c, uint32_t u) {
@@ -565,12 +564,34 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
             uint32_t n_head = 0;
             if (st.kind == ST_CONTACT_VEL) n_head = n;
             else if (st.kind == ST_CONTACTS) n_head = min(__ldg(c.near_count + st.colour), n);
+            if (st.kind == ST_INTEGRATE || st.kind == ST_DERIVE) {
+                // streaming stages: all four columns of BODY_ILP chunks are in flight before the first body is touched
+                constexpr uint32_t BODY_ILP = 2;
+                const uint32_t chunks = (n + 31u) / 32u, items = (chunks + BODY_ILP - 1u) / BODY_ILP;
+                for (uint32_t it = first_chunk; it < items; it += chunk_stride) {
+                    float4 mi[BODY_ILP], p[BODY_ILP], q[BODY_ILP], v[BODY_ILP];
+#pragma unroll
+                    for (uint32_t j = 0; j < BODY_ILP; ++j) {
+                        const uint32_t i = st.begin + min((it + j * items) * 32u + lane, n - 1u);   // out-of-range slots re-read the last body and are skipped below
+                        mi[j] = ldb(c.MI + i); p[j] = ldb(c.P + i); q[j] = ldb(c.Q + i); v[j] = ldb(c.V + i);
+                    }
+#pragma unroll
+                    for (uint32_t j = 0; j < BODY_ILP; ++j) {
+                        const uint32_t i = (it + j * items) * 32u + lane;
+                        if (i < n) {
+                            if (st.kind == ST_INTEGRATE) integrate_body(c, st.begin + i, mi[j], p[j], q[j], v[j]);
+                            else derive_body(c, st.begin + i, last, mi[j], p[j], q[j], v[j]);
+                        }
+                    }
+                }
+            } else {
             const uint32_t lanes = n_head ? min(32u, (n_head + chunk_stride - 1u) / chunk_stride) : 32u;
             const uint32_t groups = (n_head + lanes - 1u) / lanes, items = groups + (n - n_head + 31u) / 32u;
             for (uint32_t it = first_chunk; it < items; it += chunk_stride) {
                 const bool head = it < groups;
                 const uint32_t i = head ? it * lanes + lane : n_head + (it - groups) * 32u + lane;
                 if (head ? (lane < lanes && i < n_head) : i < n) run_stage(c, st.kind, st.begin + i, last, s, st.colour, st.begin, head);
+            }
             }
             grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
             if (dbg_nan) {   // debug (SFG_DEBUG_NAN): the first stage after which some body is not finite

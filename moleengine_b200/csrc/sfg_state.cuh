@@ -89,6 +89,7 @@ struct SolverCtx {
     float2 *EA, *PCD;
     const int *rope_next, *rope_prev;
     uint32_t n_bodies;
+    uint32_t bouncy;              // some collider has restitution != 0: only then are old velocities / external accelerations kept (solver.rs:555-576)
     // pair units
     const float4 *H, *S, *G0, *G1, *L0, *L1;
     const float* RC;

@@ -8,6 +8,14 @@ the first, where `depth <= 0` / `dist_sq >= r_sum^2` are decided by the last rou
 f32 and f64. compare_tick() therefore (a) requires every manifold-count mismatch to be a zero-depth tie (oracle
 lambda_n == 0 up to 1e-6 or GPU lambda_n == 0), (b) requires all bodies farther than `hops` contact-graph steps from a
 tied entry to meet the tolerance, and (c) reports how many ties there were.
+
+The narrowphase has a second kind of discontinuity: the choice between equally good features — two SAT axes of equal depth
+(shape_shape.rs:160-215, strict `<`, first wins), two boundary features equally close to a circle centre
+(collider.rs:796-892). A difference in the last bit of the inputs picks the other feature and the manifold changes by O(1)
+although both answers are right. Such an entry is a "flip": same contact count on both sides, manifold off by more than
+`flip_threshold`, and NOTHING upstream of it wrong — it is the first suspicious entry (in the solver's colour / copy order)
+on both of its bodies. Flips seed the influence set like ties do and are counted; callers cap the count (a bug shows up as
+many flips, or as mismatches that have no flip upstream of them).
 """
 import numpy as np
 
@@ -25,7 +33,7 @@ def match_manifolds(g, o):
     """Align GPU manifolds (entry = copy * n_units + unit) with oracle manifolds (unit-major, copies adjacent).
     Returns (gm, om, unit_hi, unit_lo, copy) aligned row by row."""
     gm = g.debug_manifolds().astype(np.float64)
-    hi, lo, mult, _ = g.debug_contact_units()
+    hi, lo, mult, colour = g.debug_contact_units()
     n = len(hi)
     om = o.manifolds()
     ohi, olo, omult, _ = o.pair_units()
@@ -39,19 +47,45 @@ def match_manifolds(g, o):
     for m in (0, 1):
         sel = np.nonzero(mult > m)[0].astype(np.int64)
         rows_g.append(gm[sel + m * n]); rows_o.append(om[start[pos[sel]] + m])
-        uh.append(hi[sel]); ul.append(lo[sel]); cp.append(np.full(len(sel), m))
+        uh.append(hi[sel]); ul.append(lo[sel]); cp.append(2 * colour[sel].astype(np.int64) + m)   # order of the visit inside the sweep
     return np.concatenate(rows_g), np.concatenate(rows_o), np.concatenate(uh), np.concatenate(ul), np.concatenate(cp)
 
 
-def compare_tick(g, o, scene, tol_manifold=1e-5, tol_state=1e-4, hops=3):
+def _manifold_diff(gmr, omr, cnt_o):
+    """relative difference of normals + offsets per entry (second point only where there is one); NaN on both sides = equal"""
+    with np.errstate(invalid="ignore"):
+        d = np.abs(gmr[:, 4:] - omr[:, 4:])
+    d[np.isnan(gmr[:, 4:]) & np.isnan(omr[:, 4:])] = 0.0
+    ref = np.maximum(1.0, np.abs(omr[:, 4:]))
+    two = (cnt_o == 2)[:, None]
+    colmask = np.concatenate([np.ones((len(cnt_o), 6), bool), np.repeat(two, 4, 1)], 1)
+    return np.where(colmask, d / ref, 0.0).max(1, initial=0.0) if len(cnt_o) else np.zeros(0)
+
+
+def compare_tick(g, o, scene, tol_manifold=1e-5, tol_state=1e-4, hops=3, flip_threshold=1e-3):
     """g: GpuWorld after a tick, o: OracleWorld after the replayed tick. Returns a dict of measured errors."""
-    gmr, omr, uh, ul, _ = match_manifolds(g, o)
+    gmr, omr, uh, ul, visit = match_manifolds(g, o)
     cnt_g, cnt_o = gmr[:, 2].astype(int), omr[:, 2].astype(int)
     mism = cnt_g != cnt_o
     # ties: the side that has the contact carries (numerically) zero normal correction
     lam = np.where(cnt_o > 0, np.abs(omr[:, 3]), np.abs(gmr[:, 3]))
     scale = np.maximum(np.nanmax(np.abs(omr[:, 3]), initial=0.0), 1e-3)
     tie = mism & ~(lam > 1e-4 * scale)
+    # flips: same count, manifold grossly different, first suspicious entry on both of its bodies (module docstring)
+    cb_ = scene["colliders"]["body"]
+    eb0, eb1 = cb_[uh], cb_[ul]
+    mdiff = _manifold_diff(gmr, omr, cnt_o)
+    with np.errstate(invalid="ignore"):
+        gross = ~mism & (cnt_o > 0) & ~(mdiff <= flip_threshold)
+    suspicious = gross | mism
+    first_bad = np.full(len(scene["bodies"]) + 1, np.iinfo(np.int64).max, np.int64)
+    for arr in (eb0, eb1):
+        sel = suspicious & (arr >= 0)
+        np.minimum.at(first_bad, arr[sel], visit[sel])
+    upstream0 = np.where(eb0 >= 0, first_bad[np.maximum(eb0, 0)] < visit, False)
+    upstream1 = np.where(eb1 >= 0, first_bad[np.maximum(eb1, 0)] < visit, False)
+    flip = gross & ~upstream0 & ~upstream1
+    tie = tie | flip          # from here on a flip is treated like a tie: it seeds the influence set
     # body states
     got, want = body_state(g.get_bodies()), o.get_bodies()
     with np.errstate(invalid="ignore"):
@@ -91,16 +125,12 @@ def compare_tick(g, o, scene, tol_manifold=1e-5, tol_state=1e-4, hops=3):
     e_infl = np.where(b0 >= 0, infl[np.maximum(b0, 0)], False) | np.where(b1 >= 0, infl[np.maximum(b1, 0)], False)
     # manifolds of entries outside the influence set: counts must match, normals + offsets to tol (count 2 compares both points)
     same = ~mism & (cnt_o > 0) & ~e_infl
-    with np.errstate(invalid="ignore"):
-        d = np.abs(gmr[same][:, 4:] - omr[same][:, 4:])
-    d[np.isnan(gmr[same][:, 4:]) & np.isnan(omr[same][:, 4:])] = 0.0
-    ref = np.maximum(1.0, np.abs(omr[same][:, 4:]))
-    two = (cnt_o[same] == 2)[:, None]
-    colmask = np.concatenate([np.ones((int(same.sum()), 6), bool), np.repeat(two, 4, 1)], 1)
-    man = np.where(colmask, d / ref, 0.0)
+    man = mdiff[same]
     man_err = float(man.max(initial=0.0)) if not np.isnan(man).any() else float("nan")
     return {
-        "entries": int(len(cnt_o)), "ties": int(tie.sum()), "non_tie_mismatches": int((mism & ~tie & ~e_infl).sum()),
+        "entries": int(len(cnt_o)), "ties": int((tie & ~flip).sum()), "flips": int(flip.sum()),
+        "flips_ok": bool(flip.sum() <= max(1, len(cnt_o) // 500)),       # equal-feature choices are rare: one, or 0.2 % of the entries
+        "non_tie_mismatches": int((mism & ~tie & ~e_infl).sum()),
         "mismatches_inside_influence": int((mism & ~tie & e_infl).sum()),
         "manifold_err": man_err, "manifolds_compared": int(same.sum()),
         "pos_err_clean": float(ep[~infl].max(initial=0.0)), "vel_err_clean": float(ev[~infl].max(initial=0.0)),

@@ -63,7 +63,7 @@ def test_tick_matches_oracle_replay(oracle, substeps, separate):
     tol = 1e-4 if substeps == 1 else 1e-3
     r = parity.compare_tick(g, o, sc, tol_state=tol, hops=3 if substeps == 1 else 8)
     print(r)
-    assert r["non_tie_mismatches"] == 0
+    assert r["flips_ok"] and r["non_tie_mismatches"] == 0
     assert r["ties"] <= 0.01 * r["entries"]
     if substeps == 1:
         assert r["manifold_err"] < 1e-5
