@@ -47,6 +47,9 @@ SFG_DI V2 operator*(Rot r, V2 v) {
 SFG_DI Rot rot_from_angle(float angle) {
     float h = 0.5f * angle;
     float h2 = h * h;
+    if (h2 < 1e-3f) {   // the usual case (a positional correction turns a body by milliradians): the next terms are below 2^-40 relative
+        return mkrot(1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f)), -(h * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f)))));
+    }
     if (h2 < 0.0625f) {
         float sn = h * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f + h2 * (-1.0f / 5040.0f + h2 * (1.0f / 362880.0f)))));
         float cs = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f + h2 * (-1.0f / 3628800.0f)))));
@@ -151,14 +154,18 @@ SFG_DI PEdge supporting_edge(const Shape& s, V2 d) {
     }
     // triangle / hexagon: Iterator::max_by keeps the LAST of equal maxima
     float best = 0.f;
+    int code = 0;
     const bool sym = symmetrical(s);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        PEdge e = get_edge(s, i);
-        if (sym && dot(e.n, d) < 0.f) e = mirrored(e);
-        float v = dot(e.n, d);
-        if (i == 0 || v >= best) { o = e; best = v; }
+        const V2 n = get_edge(s, i).n;
+        float v = dot(n, d);
+        const bool mir = sym && v < 0.f;
+        if (mir) v = -v;                          // dot(-n, d)
+        if (i == 0 || v >= best) { code = i * 2 + (mir ? 1 : 0); best = v; }
     }
+    o = get_edge(s, code >> 1);
+    if (code & 1) o = mirrored(o);
     if (!(dot(o.e.dir, d) < 0.f)) o.e = flipped(o.e);
     return o;
 }
@@ -301,41 +308,43 @@ SFG_DI int clip_edge(const Edge& target, const Edge& edge, float* enters, float*
 
 // shape_shape.rs:160-349. Everything is kept in named registers (no dynamically indexed arrays): the SAT loop is
 // unrolled over the two owners, and the winning owner's data is picked with selects afterwards.
-SFG_DI void sat_pass(const Shape& own, const Shape& oth, V2 dist, Rot rel_own_r, float r_sum, int pass, float& pen_depth, PEdge& pen,
-                     float& pen_ext, int& o0, bool& have, bool& separated) {
+SFG_DI void sat_pass(const Shape& own, const Shape& oth, V2 dist, Rot rel_own_r, float r_sum, int pass, float& pen_depth, int& pen_code, bool& separated) {
     const int n = edge_count(own);
     const bool sym = symmetrical(own);
     for (int ei = 0; ei < n; ++ei) {
         PEdge e = get_edge(own, ei);
+        bool mir = false;
         if (!(dot(e.n, dist) >= 0.f)) {
-            if (sym) e = mirrored(e);
+            if (sym) { e.n = -e.n; mir = true; }
             else continue;
         }
         const float ext = edge_extent(own, ei);
         const V2 axis_o = -(rel_own_r * e.n);
         const float depth = ext + projected_extent(oth, axis_o) + r_sum - dot(dist, e.n);
         if (depth <= 0.f) { separated = true; return; }
-        if (depth < pen_depth) { pen_depth = depth; pen = e; pen_ext = ext; have = true; o0 = pass; }
+        if (depth < pen_depth) { pen_depth = depth; pen_code = pass * 8 + ei * 2 + (mir ? 1 : 0); }   // the winner is rebuilt after the loop
     }
 }
 SFG_DI void any_any(Iso pose0, Iso pose1, const Shape& s0, const Shape& s1, Manifold& m) {
     const Iso rel1 = inversed(pose0) * pose1;     // object 1 in object 0's frame
     const Iso rel0 = inversed(rel1);              // object 0 in object 1's frame
-    float pen_depth = 3.402823466e+38f, pen_ext = 0.f;
-    PEdge pen;
-    pen.n = mk(0.f, 0.f); pen.e.start = mk(0.f, 0.f); pen.e.dir = mk(0.f, 0.f); pen.e.len = 0.f;
-    bool have = false, separated = false;
-    int o0 = 0;
+    float pen_depth = 3.402823466e+38f;
+    int pen_code = -1;                             // owner * 8 + edge * 2 + mirrored of the least-depth axis (strict <: the first wins)
+    bool separated = false;
     // depth = extent + shapes[0].circle_r + projected_extent + shapes[1].circle_r - dist.n  (reference order of the sum:
     // ((ext + r0) + proj) + r1; f32 rounding differences of the regrouping are far below the parity tolerance)
     const float r_sum = s0.r + s1.r;
-    sat_pass(s0, s1, rel1.t, rel0.r, r_sum, 0, pen_depth, pen, pen_ext, o0, have, separated);
+    sat_pass(s0, s1, rel1.t, rel0.r, r_sum, 0, pen_depth, pen_code, separated);
     if (separated) { m.count = 0; return; }
-    sat_pass(s1, s0, rel0.t, rel1.r, r_sum, 1, pen_depth, pen, pen_ext, o0, have, separated);
-    if (separated || !have) { m.count = 0; return; }
-    const bool f = o0 != 0;
+    sat_pass(s1, s0, rel0.t, rel1.r, r_sum, 1, pen_depth, pen_code, separated);
+    if (separated || pen_code < 0) { m.count = 0; return; }
+    const bool f = pen_code >= 8;
     const Shape& sown = f ? s1 : s0;
     const Shape& sinc = f ? s0 : s1;
+    const int pen_ei = (pen_code >> 1) & 3;
+    PEdge pen = get_edge(sown, pen_ei);
+    if (pen_code & 1) pen = mirrored(pen);
+    const float pen_ext = edge_extent(sown, pen_ei);
     const Iso rel_own = f ? rel1 : rel0;          // relative_poses[shape_order[0]]
     const Iso rel_inc = f ? rel0 : rel1;          // relative_poses[shape_order[1]]
     const Rot pose_own_r = f ? pose1.r : pose0.r;
