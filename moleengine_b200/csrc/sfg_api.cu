@@ -50,6 +50,9 @@ struct TickHeader {            // small device block read back once per tick pha
 struct SfgWorld {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // the island pass runs here, next to the colouring (both only read the pair list)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool islands_in_flight = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
     SfgTuning tuning{};
@@ -487,6 +490,8 @@ int sfg_world_create(const SfgTuning* tuning, const uint64_t mask_matrix[64], in
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) w->n_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return SFG_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(w->stream); delete w; return SFG_E_CUDA; }
+    cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming);
     for (auto& e : w->ev) cudaEventCreate(&e);
     if (w->d_mask.ensure(64) != cudaSuccess || w->hdr.ensure(1) != cudaSuccess) { delete w; return SFG_E_CUDA; }
     cudaMemcpyAsync(w->d_mask.p, w->mask, sizeof(w->mask), cudaMemcpyHostToDevice, w->stream);
@@ -499,6 +504,7 @@ void sfg_world_destroy(SfgWorld* w) {
     if (!w) return;
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
+    if (w->stream2) cudaStreamSynchronize(w->stream2);
     DBuf<float4>* f4[] = {&w->P, &w->Q, &w->V, &w->OV, &w->MI, &w->CS, &w->CL, &w->CM, &w->AABB, &w->KA, &w->KB, &w->RPA, &w->RPB, &w->SA,
                           &w->H, &w->S, &w->G0, &w->G1, &w->L0, &w->L1, &w->M0, &w->M1, &w->M2, &w->K0, &w->K1, &w->K2};
     for (auto* b : f4) b->release();
@@ -516,6 +522,9 @@ void sfg_world_destroy(SfgWorld* w) {
     w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->body_word.release(); w->trace.release(); w->adj_slots.release(); w->adj_rank.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    if (w->ev_fork) cudaEventDestroy(w->ev_fork);
+    if (w->ev_join) cudaEventDestroy(w->ev_join);
+    if (w->stream2) cudaStreamDestroy(w->stream2);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
 }
@@ -828,6 +837,7 @@ int broadphase(SfgWorld* w, float frame_dt) {
     return SFG_OK;
 }
 
+int join_islands(SfgWorld* w);
 int build_graph(SfgWorld* w) {
     cudaStream_t st = w->stream;
     const uint32_t nb = w->n_bodies;
@@ -847,6 +857,7 @@ int build_graph(SfgWorld* w) {
         CK(w->RC.ensure(n)); CK(w->WL.ensure(n));
         CK(w->H.ensure(n)); CK(w->S.ensure(n)); CK(w->G0.ensure(n)); CK(w->G1.ensure(n)); CK(w->L0.ensure(n)); CK(w->L1.ensure(n));
         CK(w->M0.ensure(size_t(n) * 2)); CK(w->M1.ensure(size_t(n) * 2)); CK(w->M2.ensure(size_t(n) * 2)); CK(w->LN.ensure(size_t(n) * 2));
+        { int jr = join_islands(w); if (jr != SFG_OK) return jr; }
         k_build_pair_units<<<nblk(n), 256, 0, st>>>(n, perm, w->U_ids.p, w->CS.p, w->CL.p, w->CM.p, w->CI.p, w->MI.p,
                                                     w->n_ropes ? w->rope_next.p : nullptr, w->n_ropes ? w->rope_prev.p : nullptr, w->H.p, w->S.p,
                                                     w->G0.p, w->G1.p, w->L0.p, w->L1.p, w->RC.p);
@@ -913,8 +924,7 @@ void fill_island_ctx(SfgWorld* w, IslandCtx& c) {
     c.shard_rank = w->shard_rank; c.shard_n = w->shard_n; c.sleeping = sleeping_enabled(w) ? 1u : 0u;
 }
 // physics.rs:598-741: islands of the constraint graph, then which of them stay asleep this tick
-int island_pass(SfgWorld* w) {
-    cudaStream_t st = w->stream;
+int island_pass(SfgWorld* w, cudaStream_t st) {
     const uint32_t nb = w->n_bodies;
     if (nb == 0) return SFG_OK;
     CK(w->isl_parent.ensure(nb + 1)); CK(w->isl_first.ensure(nb + 1)); CK(w->isl_flags.ensure(nb + 1)); CK(w->isl_count.ensure(nb + 1)); CK(w->isl_sum.ensure(nb + 1));
@@ -960,6 +970,14 @@ int island_post(SfgWorld* w) {
     return SFG_OK;
 }
 
+// the island pass was forked onto stream2 (sfg_tick_begin); everything that reads its per-tick body flags waits here
+int join_islands(SfgWorld* w) {
+    if (!w->islands_in_flight) return SFG_OK;
+    w->islands_in_flight = false;
+    CK(cudaStreamWaitEvent(w->stream, w->ev_join, 0));
+    return SFG_OK;
+}
+
 void build_stage_table(SfgWorld* w) {
     auto& s = w->h_stages;
     s.clear();
@@ -1002,6 +1020,7 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
         dt = time_scale * frame_dt / double(substeps);
     }
     w->launches = 0;
+    w->islands_in_flight = false;
     w->frame_dt = float(frame_dt);
     CK(cudaEventRecord(w->ev[0], st));
     if (w->n_bodies) CK(cudaMemsetAsync(w->EA.p, 0, size_t(w->n_bodies) * sizeof(float2), st));
@@ -1012,8 +1031,20 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     CK(cudaEventRecord(w->ev[1], st));
     // islands across a slab seam are not tracked: slabs never sleep. Island sharding needs the islands even if nothing may sleep.
     w->tick_sleeping = (sleeping_enabled(w) || w->shard_n > 1) && !w->slab_on;
-    if (w->tick_sleeping) { rc = island_pass(w); if (rc != SFG_OK) return rc; }
+    // islands and colouring both only read the pair list: the island pass runs on a second stream next to the colouring
+    // (union-find and the colouring dataflow are latency-bound and leave most of the machine idle on their own); the join is
+    // in front of k_build_pair_units, the first reader of the asleep / foreign flags the island pass leaves on the bodies
+    if (w->tick_sleeping) {
+        CK(cudaEventRecord(w->ev_fork, st));
+        CK(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));
+        rc = island_pass(w, w->stream2);
+        if (rc != SFG_OK) return rc;
+        CK(cudaEventRecord(w->ev_join, w->stream2));
+        w->islands_in_flight = true;
+    }
     rc = build_graph(w);
+    if (rc != SFG_OK) return rc;
+    rc = join_islands(w);
     if (rc != SFG_OK) return rc;
     CK(cudaEventRecord(w->ev[2], st));
     w->tick_substeps = substeps; w->tick_next_substep = 0;
