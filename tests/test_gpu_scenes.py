@@ -289,3 +289,54 @@ def test_far_from_the_origin(oracle, offset):
     assert r["manifold_err"] < 1e-5 and r["manifolds_compared"] > 50
     assert r["vel_err_clean"] < 1e-4
     g.close()
+
+
+def test_restitution_added_by_a_partial_update(oracle):
+    """Old velocities / external accelerations are only kept for worlds that have a collider with restitution (their one reader,
+    solver.rs:555-576). The flag must come up when restitution arrives through sfg_update_colliders, not only through a full upload."""
+    sc = scenes.parity_mix(300, 5)
+    plain = sc["colliders"].copy()
+    plain["restitution"] = 0.0
+    assert (sc["colliders"]["restitution"] != 0).any()
+    tun = abi.default_tuning(substeps=1)
+    g = GpuWorld(tuning=tun)
+    g.set_bodies(sc["bodies"])
+    g.set_colliders(plain)                       # nothing bounces: the world starts without old velocities
+    g.set_constraints(sc["constraints"])
+    g.set_ropes(sc["ropes"], sc["rope_particles"])
+    g.update_colliders(0, sc["colliders"])       # now some colliders do
+    g.tick()
+    o = oracle.OracleWorld(tuning=tun)
+    o.load_scene(sc)
+    o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+    o.tick(mode=oracle.MODE_COLOURED)
+    r = parity.compare_tick(g, o, sc)
+    _check(r)
+    g.close()
+
+
+def test_near_hint_orders_the_colours():
+    """The `near` bit in front of the colouring priority (include/sfg_hash.h): one hint per pair, every touching pair carries it in
+    a falling scene, and near pairs sit in lower colours than the rest (that is what makes the high colours cheap)."""
+    sc = scenes.c3_mixed(60, 40)
+    g = GpuWorld(tuning=abi.default_tuning(substeps=4))
+    g.load_scene(sc)
+    for _ in range(12):
+        g.tick()
+    p = g.debug_pairs().astype(np.uint64)
+    h = g.debug_pair_hints()
+    assert h.dtype == np.uint8 and len(h) == len(p) and set(np.unique(h).tolist()) <= {0, 1}
+    assert 0 < h.sum() < len(h)
+    hi, lo, mult, col = g.debug_contact_units()
+    key_p = p[:, 0] << np.uint64(32) | p[:, 1]
+    order = np.argsort(key_p)
+    key_u = hi.astype(np.uint64) << np.uint64(32) | lo.astype(np.uint64)
+    near = h[order][np.searchsorted(key_p[order], key_u)].astype(bool)
+    m = g.debug_manifolds()
+    n = len(hi)
+    touching = (m[:n, 2] > 0) | (m[n:2 * n, 2] > 0)
+    assert touching.sum() > 20
+    assert near[touching].all()                                  # the hint missed no contact
+    assert col[near].mean() < col[~near].mean()
+    assert col[near].max() < col.max()                           # the top colours hold far pairs only
+    g.close()
