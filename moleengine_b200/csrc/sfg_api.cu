@@ -431,6 +431,7 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     w->stats_jp_rounds = head[4];
     if (n_colours == 0 || n_colours > HIST_CAP) return fail(w, SFG_E_CAPACITY, "colouring did not converge or needs > 65536 colours");
     if (head[5]) return fail(w, SFG_E_CAPACITY, "a body takes part in 2^24 or more pairs / constraints");
+    if (head[6]) return fail(w, SFG_E_STATE, "colouring watchdog: a unit waited forever for its bodies' tickets");
     std::vector<uint32_t> hist(n_colours);
     memcpy(hist.data(), head + 16, std::min<size_t>(n_colours, 64) * 4);
     if (n_colours > 64) {

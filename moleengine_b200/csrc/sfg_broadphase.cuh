@@ -433,7 +433,8 @@ constexpr uint32_t UNCOLOURED = 0xFFFFFFFFu;
 // Progress: the highest-priority uncoloured unit is never kept waiting; units are bucket-sorted by the top bits of the
 // priority (k_adj_fill + one radix pass) and dealt to warps in 32-unit chunks of that order, a bucket spans far fewer
 // chunks than there are co-resident warps (checked on the host), so the warp owning that unit's chunk is running it.
-// ctrl: [1] max colour + 1, [4] 1, [5] != 0: a body has 2^24 or more units (the host reports SFG_E_CAPACITY). hist = units per colour.
+// ctrl: [1] max colour + 1, [4] 1, [5] != 0: a body has 2^24 or more units (the host reports SFG_E_CAPACITY), [6] != 0: the watchdog
+// fired. hist = units per colour.
 constexpr int CM_BITS = 40;
 constexpr unsigned long long CM_MASK = (1ull << CM_BITS) - 1ull;
 SFG_DI unsigned long long ld_relaxed64(const unsigned long long* p) {
@@ -482,8 +483,8 @@ SFG_DI uint32_t colour_scan_exact(uint32_t u, int2 b, uint32_t pu, uint2 iu, con
             for (uint32_t q = adj_start[body], q1 = adj_start[body + 1]; q < q1; ++q) {
                 const uint2 vp = adj[q];
                 if (vp.x == u || !unit_higher(vp, pu, iu, ids)) continue;
-                uint32_t cv;
-                while ((cv = ld_relaxed(colour + vp.x)) == 0xFFFFFFFFu) __nanosleep(40);
+                uint32_t cv, spins = 0;
+                while ((cv = ld_relaxed(colour + vp.x)) == 0xFFFFFFFFu && ++spins < (1u << 22)) __nanosleep(40);   // bounded: see the watchdog in k_colour_dataflow
                 if (cv >= win && cv < win + 64) w_used |= 1ull << (cv - win);
                 else if (cv >= win + 64) w_beyond = true;
             }
@@ -520,11 +521,14 @@ __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, cons
             if (b.y == b.x && b.x >= 0) { b.y = -1; step0 = 2; }
             if (b.y >= 0) want1 = (unsigned long long)rank[sl.y] << CM_BITS;
         }
+        uint32_t polls = 0;
         while (__any_sync(0xFFFFFFFFu, !done)) {
             if (!done) {
+                // watchdog: a ticket that never comes up (it cannot, by the progress argument above) must not hang the device
                 const unsigned long long w0 = b.x >= 0 ? ld_relaxed64(body_word + b.x) : 0ull;
                 const unsigned long long w1 = b.y >= 0 ? ld_relaxed64(body_word + b.y) : 0ull;
-                if ((w0 & ~CM_MASK) == want0 && (w1 & ~CM_MASK) == want1) {
+                if (++polls > (1u << 22)) { ctrl[6] = 1u; done = true; }
+                else if ((w0 & ~CM_MASK) == want0 && (w1 & ~CM_MASK) == want1) {
                     const unsigned long long used = (w0 | w1) & CM_MASK;
                     const int2 bb = step0 == 2 ? make_int2(b.x, b.x) : b;
                     const uint32_t result = used != CM_MASK ? uint32_t(__ffsll((long long)~used) - 1) : colour_scan_exact(u, bb, pu, iu, ids, adj_start, adj, colour);

@@ -526,6 +526,7 @@ __global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx
 // the end. All data that crosses SMs between stages is accessed with ld.cg / st.cg, so L1 never holds it.
 SFG_DI unsigned long long global_timer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, unsigned long long* trace = nullptr) {
+    if (gridDim.x == 1 && !trace) { __syncthreads(); return; }   // a small world runs in one CTA: bar.sync orders its global accesses (all through L2)
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
