@@ -42,6 +42,9 @@ SFG_DI V2 operator*(Rot r, V2 v) {
     float fy = r.s * v.y - r.b * v.x;
     return mk(r.s * fx + r.b * fy, r.s * fy - r.b * fx);
 }
+// The general case of from_angle lives out of line: sincosf's argument reduction is ~130 instructions, it was inlined at every
+// correction site (12 % of the solver kernel's code) and never runs there; the solver's lone warps are instruction-fetch bound.
+__device__ __noinline__ void sincos_general(float h, float* sn, float* cs) { sincosf(h, sn, cs); }
 // from_angle with a polynomial fast path: corrections inside the solver are tiny rotations, for
 // which the Taylor series to h^9 is exact to f32 rounding; larger angles take sincosf.
 SFG_DI Rot rot_from_angle(float angle) {
@@ -56,7 +59,7 @@ SFG_DI Rot rot_from_angle(float angle) {
         return mkrot(cs, -sn);
     }
     float sn, cs;
-    sincosf(h, &sn, &cs);
+    sincos_general(h, &sn, &cs);
     return mkrot(cs, -sn);
 }
 

@@ -18,8 +18,8 @@ SFG_DI void stb(float4* p, float4 v) { __stcg(p, v); }
 SFG_DI void stb(float2* p, float2 v) { __stcg(p, v); }
 SFG_DI float4 ldc(const float4* p) { return __ldg(p); }
 
-// forcefield.rs
-SFG_DI V2 force_at(const ForceParams& ff, V2 pos) {
+// forcefield.rs (out of line: one copy for the three places that integrate a body)
+__device__ __noinline__ V2 force_at(const ForceParams& ff, V2 pos) {
     V2 acc = mk(0.f, 0.f);
     for (uint32_t i = 0; i < ff.n; ++i) {
         if (ff.kind[i] == 1u) acc = acc + mk(ff.a[i], ff.b[i]);
