@@ -27,8 +27,9 @@ namespace sfg {
 
 constexpr int MAX_LEVELS = 8;
 #ifndef SFG_SOLVER_THREADS
-#define SFG_SOLVER_THREADS 640      // threads per CTA of the persistent solver, one CTA per SM: 96 registers per thread. Measured: 768 threads
-                                    // (80 registers, 286 B of spills) is 6-12 % slower on C3 and C5, 512 threads (117 registers, none) the same as 640
+#define SFG_SOLVER_THREADS 512      // threads per CTA of the persistent solver, one CTA per SM: 117 registers per thread, no spills.
+                                    // Measured on C3 / settled C3 / C5 (solver ms): 384: 0.89 / 4.76 / 16.9, 448: 0.86 / 4.65 / 16.5,
+                                    // 512: 0.85 / 4.48 / 15.7, 640 (96 registers, 64 B of spills): 0.87 / 4.59 / 16.5, 768 (80, 176 B): 0.90 / 4.77 / 16.9
 #endif
 
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
