@@ -42,24 +42,22 @@ SFG_DI V2 operator*(Rot r, V2 v) {
     float fy = r.s * v.y - r.b * v.x;
     return mk(r.s * fx + r.b * fy, r.s * fy - r.b * fx);
 }
-// The general case of from_angle lives out of line: sincosf's argument reduction is ~130 instructions, it was inlined at every
-// correction site (12 % of the solver kernel's code) and never runs there; the solver's lone warps are instruction-fetch bound.
-__device__ __noinline__ void sincos_general(float h, float* sn, float* cs) { sincosf(h, sn, cs); }
-// from_angle with a polynomial fast path: corrections inside the solver are tiny rotations, for
-// which the Taylor series to h^9 is exact to f32 rounding; larger angles take sincosf.
-SFG_DI Rot rot_from_angle(float angle) {
-    float h = 0.5f * angle;
-    float h2 = h * h;
-    if (h2 < 1e-3f) {   // the usual case (a positional correction turns a body by milliradians): the next terms are below 2^-40 relative
-        return mkrot(1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f)), -(h * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f)))));
-    }
+// from_angle: corrections inside the solver are rotations by milliradians, for which a three-term series is exact to f32
+// rounding (the next terms are below 2^-40 relative). Everything else lives out of line — the h^9 series up to a quarter
+// radian of half-angle, sincosf beyond (its argument reduction alone is ~130 instructions): inlined at every correction site
+// that was 15 % of the solver kernel's code and it never runs there; the solver's lone warps are instruction-fetch bound.
+__device__ __noinline__ void from_angle_general(float h, float* sn, float* cs) {
+    const float h2 = h * h;
     if (h2 < 0.0625f) {
-        float sn = h * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f + h2 * (-1.0f / 5040.0f + h2 * (1.0f / 362880.0f)))));
-        float cs = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f + h2 * (-1.0f / 3628800.0f)))));
-        return mkrot(cs, -sn);
-    }
+        *sn = h * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f + h2 * (-1.0f / 5040.0f + h2 * (1.0f / 362880.0f)))));
+        *cs = 1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f + h2 * (-1.0f / 720.0f + h2 * (1.0f / 40320.0f + h2 * (-1.0f / 3628800.0f)))));
+    } else sincosf(h, sn, cs);
+}
+SFG_DI Rot rot_from_angle(float angle) {
+    const float h = 0.5f * angle, h2 = h * h;
+    if (h2 < 1e-3f) return mkrot(1.0f + h2 * (-0.5f + h2 * (1.0f / 24.0f)), -(h * (1.0f + h2 * (-1.0f / 6.0f + h2 * (1.0f / 120.0f)))));
     float sn, cs;
-    sincos_general(h, &sn, &cs);
+    from_angle_general(h, &sn, &cs);
     return mkrot(cs, -sn);
 }
 
@@ -193,7 +191,7 @@ SFG_DI V2 closest_boundary_point(const Shape& s, V2 pt, bool* interior) {
         float min_d = 3.402823466e+38f;
         V2 cp = mk(0.f, 0.f);
         const bool sym = symmetrical(s);
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 3; ++i) {
             PEdge e = get_edge(s, i);
             if (sym && dot(e.n, pt) < 0.f) e = mirrored(e);
