@@ -115,7 +115,7 @@ struct SfgWorld {
     DBuf<Stage> d_stages;
     DBuf<unsigned long long> trace, body_word;
     DBuf<uint2> adj_slots;
-    DBuf<uint32_t> adj_rank;
+    DBuf<int4> adj_rank;              // per unit: (body 0, body 1, rank in body 0's list, rank in body 1's list)
     std::vector<Stage> h_stages;
     // casts
     DBuf<SfgRay> d_rays;
@@ -396,8 +396,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * 8 > size_t(grid) * 1024) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
-    CK(w->adj_slots.ensure(n_units)); CK(w->adj_rank.ensure(size_t(n_units) * 2 + 1));
-    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, w->adj_slots.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
+    CK(w->adj_slots.ensure(n_units)); CK(w->adj_rank.ensure(size_t(n_units) + 1));
+    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, w->adj_slots.p, w->adj_rank.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
     CKL(w); w->launches++;
     const uint32_t* order;
     {
@@ -418,8 +418,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         const uint32_t* adj_start = w->adj_start.p; const uint2* adj = w->adj2.p;
         uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_counters.p + 16;
         unsigned long long* words = w->body_word.p;
-        const uint2* slots = w->adj_slots.p; const uint32_t* rank = w->adj_rank.p;
-        void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, (void*)&slots, (void*)&rank, &col, &words, &ctrl, &hist, &hist_cap};
+        const int4* urec = w->adj_rank.p;
+        void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, (void*)&urec, &col, &words, &ctrl, &hist, &hist_cap};
         CK(cudaLaunchCooperativeKernel((void*)k_colour_dataflow, dim3(grid), dim3(1024), args, 0, st));
         w->launches++;
     }

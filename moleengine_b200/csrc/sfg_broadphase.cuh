@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(256) k_constraint_unit_setup(uint32_t n_units,
 // adjacency lists body -> (unit, priority of the unit); also the bucket key of the colouring pass (descending priority)
 __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
                                                   const uint32_t* __restrict__ adj_start, uint32_t* __restrict__ cursor,
-                                                  uint2* __restrict__ adj, uint2* __restrict__ slots, int bucket_shift,
-                                                  uint32_t* __restrict__ bucket_key, uint32_t* __restrict__ order) {
+                                                  uint2* __restrict__ adj, uint2* __restrict__ slots, int4* __restrict__ urec,
+                                                  int bucket_shift, uint32_t* __restrict__ bucket_key, uint32_t* __restrict__ order) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const int2 b = ub[u];
@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* 
     if (b.x >= 0) { sl.x = adj_start[b.x] + atomicAdd(cursor + b.x, 1u); adj[sl.x] = make_uint2(u, p); }
     if (b.y >= 0) { sl.y = adj_start[b.y] + atomicAdd(cursor + b.y, 1u); adj[sl.y] = make_uint2(u, p); }
     slots[u] = sl;
+    urec[u] = make_int4(b.x, b.y, 0, 0);       // k_adj_rank fills in the two ranks
     bucket_key[u] = (~p) >> bucket_shift;
     order[u] = u;
 }
@@ -453,13 +454,14 @@ SFG_DI bool unit_higher(uint2 vp, uint32_t pu, uint2 iu, const uint2* __restrict
 // each unit for itself touches 2 x degree scattered sectors and was most of the colouring time in crowded worlds).
 __global__ void __launch_bounds__(256) k_adj_rank(uint32_t n_slots, const uint2* __restrict__ adj, const int2* __restrict__ ub,
                                                   const uint2* __restrict__ slots, const uint2* __restrict__ ids,
-                                                  const uint32_t* __restrict__ adj_start, uint32_t* __restrict__ rank, uint32_t* ctrl,
+                                                  const uint32_t* __restrict__ adj_start, int4* __restrict__ urec, uint32_t* ctrl,
                                                   uint32_t n_bodies) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_slots || q >= adj_start[n_bodies]) return;      // slots in use = sum of the degrees (static sides have no list)
     const uint2 me = adj[q];
     const int2 b = ub[me.x];
-    const int body = slots[me.x].x == q ? b.x : b.y;
+    const bool side0 = slots[me.x].x == q;
+    const int body = side0 ? b.x : b.y;
     const uint2 iu = ids[me.x];
     const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
     uint32_t r = 0;
@@ -468,7 +470,8 @@ __global__ void __launch_bounds__(256) k_adj_rank(uint32_t n_slots, const uint2*
         if (vp.x != me.x && unit_higher(vp, me.y, iu, ids)) ++r;
     }
     if (a1 - a0 >= (1u << (64 - CM_BITS))) ctrl[5] = 1u;
-    rank[q] = r;
+    // the colouring pass reads ONE 16-byte record per unit: (body 0, body 1, rank in body 0's list, rank in body 1's list)
+    reinterpret_cast<int*>(urec + me.x)[side0 ? 2 : 3] = int(r);
 }
 // exact smallest colour unused by the higher-priority neighbours of u, by windows of 64 colours; every such neighbour is
 // coloured by the time this runs (its ticket came up), the poll only bridges the gap between its two stores
@@ -496,7 +499,7 @@ SFG_DI uint32_t colour_scan_exact(uint32_t u, int2 b, uint32_t pu, uint2 iu, con
 __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, const uint32_t* __restrict__ order, const int2* __restrict__ ub,
                                                          const uint32_t* __restrict__ prio, const uint2* __restrict__ ids,
                                                          const uint32_t* __restrict__ adj_start, const uint2* __restrict__ adj,
-                                                         const uint2* __restrict__ slots, const uint32_t* __restrict__ rank,
+                                                         const int4* __restrict__ urec,
                                                          uint32_t* colour, unsigned long long* body_word, uint32_t* ctrl, uint32_t* hist, uint32_t hist_cap) {
     __shared__ uint32_t s_hist[64];
     __shared__ uint32_t s_max;
@@ -515,11 +518,12 @@ __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, cons
         unsigned long long want0 = 0, want1 = 0;        // ticket the body must show, already shifted
         uint32_t step0 = 1;                            // a unit whose two sides are the same body sits twice in that list
         if (!done) {
-            u = order[idx]; b = ub[u]; pu = prio[u]; iu = ids[u];
-            const uint2 sl = slots[u];
-            if (b.x >= 0) want0 = (unsigned long long)rank[sl.x] << CM_BITS;
+            u = order[idx];
+            const int4 rec = urec[u];
+            b = make_int2(rec.x, rec.y);
+            if (b.x >= 0) want0 = (unsigned long long)uint32_t(rec.z) << CM_BITS;
             if (b.y == b.x && b.x >= 0) { b.y = -1; step0 = 2; }
-            if (b.y >= 0) want1 = (unsigned long long)rank[sl.y] << CM_BITS;
+            if (b.y >= 0) want1 = (unsigned long long)uint32_t(rec.w) << CM_BITS;
         }
         uint32_t polls = 0;
         while (__any_sync(0xFFFFFFFFu, !done)) {
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, cons
                 else if ((w0 & ~CM_MASK) == want0 && (w1 & ~CM_MASK) == want1) {
                     const unsigned long long used = (w0 | w1) & CM_MASK;
                     const int2 bb = step0 == 2 ? make_int2(b.x, b.x) : b;
-                    const uint32_t result = used != CM_MASK ? uint32_t(__ffsll((long long)~used) - 1) : colour_scan_exact(u, bb, pu, iu, ids, adj_start, adj, colour);
+                    const uint32_t result = used != CM_MASK ? uint32_t(__ffsll((long long)~used) - 1) : colour_scan_exact(u, bb, prio[u], ids[u], ids, adj_start, adj, colour);
                     asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(colour + u), "r"(result) : "memory");
                     const unsigned long long bit = result < uint32_t(CM_BITS) ? 1ull << result : 0ull;
                     if (b.x >= 0) st_relaxed64(body_word + b.x, (w0 | bit) + ((unsigned long long)step0 << CM_BITS));
