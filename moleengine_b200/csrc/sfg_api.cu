@@ -114,7 +114,8 @@ struct SfgWorld {
     // persistent solver
     DBuf<Stage> d_stages;
     DBuf<unsigned long long> trace, body_word;
-    DBuf<uint2> adj_slots;
+    DBuf<uint32_t> adj_body;          // per list slot: body | side << 31
+    DBuf<uint8_t> U_cls;              // per pair unit: order class inside a colour (k_pair_unit_setup)
     DBuf<int4> adj_rank;              // per unit: (body 0, body 1, rank in body 0's list, rank in body 1's list)
     std::vector<Stage> h_stages;
     // casts
@@ -396,8 +397,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * 8 > size_t(grid) * 1024) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
-    CK(w->adj_slots.ensure(n_units)); CK(w->adj_rank.ensure(size_t(n_units) + 1));
-    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, w->adj_slots.p, w->adj_rank.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
+    CK(w->adj_body.ensure(size_t(n_units) * 2 + 1)); CK(w->adj_rank.ensure(size_t(n_units) + 1));
+    k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, w->adj_body.p, w->adj_rank.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
     CKL(w); w->launches++;
     const uint32_t* order;
     {
@@ -411,7 +412,7 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     CK(w->body_word.ensure(nb + 1));
     CK(cudaMemsetAsync(w->body_word.p, 0, size_t(nb + 1) * 8, st));
     // list slots in use = sum of degrees <= 2 n_units; unused tail slots of the allocation are never read
-    k_adj_rank<<<nblk(n_units * 2), 256, 0, st>>>(n_units * 2, w->adj2.p, ub, w->adj_slots.p, ids, w->adj_start.p, w->adj_rank.p, w->jp_counters.p, nb);
+    k_adj_rank<<<nblk(n_units * 2), 256, 0, st>>>(n_units * 2, w->adj2.p, w->adj_body.p, ids, w->adj_start.p, w->adj_rank.p, w->jp_counters.p, nb);
     CKL(w); w->launches++;
     {
         uint32_t hist_cap = HIST_CAP;
@@ -450,7 +451,7 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         CK(cudaMemsetAsync(w->near_count.p, 0, size_t(n_colours) * 4, st));
         near_count = w->near_count.p;
     }
-    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, ids, pair_units ? w->CS.p : nullptr, w->CI.p, prio, w->ckey0.p, near_count);
+    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, pair_units ? w->U_cls.p : nullptr, w->ckey0.p, near_count);
     CKL(w); w->launches++;
     k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
     int bits = 5;
@@ -520,7 +521,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->body_word.release(); w->trace.release(); w->adj_slots.release(); w->adj_rank.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->body_word.release(); w->trace.release(); w->adj_body.release(); w->adj_rank.release(); w->U_cls.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
@@ -848,9 +849,9 @@ int build_graph(SfgWorld* w) {
     // ---- pair units
     if (w->n_units) {
         const uint32_t n = w->n_units;
-        CK(w->U_ub.ensure(n)); CK(w->U_prio.ensure(n));
+        CK(w->U_ub.ensure(n)); CK(w->U_prio.ensure(n)); CK(w->U_cls.ensure(n));
         CK(cudaMemsetAsync(w->deg.p, 0, size_t(nb + 2) * 4, st));
-        k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->CS.p, w->CL.p, w->P.p, w->Q.p, w->V.p, w->frame_dt, w->U_ub.p, w->U_prio.p, w->deg.p);
+        k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->CS.p, w->CL.p, w->P.p, w->Q.p, w->V.p, w->frame_dt, w->U_ub.p, w->U_prio.p, w->deg.p, w->U_cls.p);
         CKL(w); w->launches++;
         uint32_t* perm = nullptr;
         int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours, true);

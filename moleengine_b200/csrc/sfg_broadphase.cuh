@@ -328,7 +328,8 @@ __global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const
                                                          const float4* __restrict__ MI, const float4* __restrict__ CS,
                                                          const float4* __restrict__ CL, const float4* __restrict__ P,
                                                          const float4* __restrict__ Q, const float4* __restrict__ V, float frame_dt,
-                                                         int2* __restrict__ ub, uint32_t* __restrict__ prio, uint32_t* __restrict__ deg) {
+                                                         int2* __restrict__ ub, uint32_t* __restrict__ prio, uint32_t* __restrict__ deg,
+                                                         uint8_t* __restrict__ ucls) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const uint2 id = ids[u];
@@ -344,6 +345,15 @@ __global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const
     if (b1 >= 0 && !(__float_as_uint(MI[b1].z) & (BF_MASS | BF_INERTIA))) b1 = -1;
     ub[u] = make_int2(b0, b1);
     prio[u] = sfg_pair_priority(id.x, id.y, near_hint ? 1u : 0u);
+    {   // order inside a colour (k_unit_sort_keys): far units last, the rest grouped by narrowphase path and visit count
+        const uint32_t k0 = __float_as_uint(CS[id.x].w), k1 = __float_as_uint(CS[id.y].w);
+        uint32_t path;
+        if (k0 == K_POINT && k1 == K_POINT) path = 0;
+        else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
+        else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
+        const uint32_t mult2 = (c0.x >= 0 && c1.x >= 0) ? 1u : 0u;
+        ucls[u] = uint8_t(path * 2 + mult2 + (near_hint ? 0u : 16u));
+    }
     if (b0 >= 0) atomicAdd(deg + b0, 1u);
     if (b1 >= 0) atomicAdd(deg + b1, 1u);
 }
@@ -364,16 +374,15 @@ __global__ void __launch_bounds__(256) k_constraint_unit_setup(uint32_t n_units,
 // adjacency lists body -> (unit, priority of the unit); also the bucket key of the colouring pass (descending priority)
 __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* __restrict__ ub, const uint32_t* __restrict__ prio,
                                                   const uint32_t* __restrict__ adj_start, uint32_t* __restrict__ cursor,
-                                                  uint2* __restrict__ adj, uint2* __restrict__ slots, int4* __restrict__ urec,
+                                                  uint2* __restrict__ adj, uint32_t* __restrict__ adj_body, int4* __restrict__ urec,
                                                   int bucket_shift, uint32_t* __restrict__ bucket_key, uint32_t* __restrict__ order) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const int2 b = ub[u];
     const uint32_t p = prio[u];
-    uint2 sl = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);           // where the unit sits in its bodies' lists
-    if (b.x >= 0) { sl.x = adj_start[b.x] + atomicAdd(cursor + b.x, 1u); adj[sl.x] = make_uint2(u, p); }
-    if (b.y >= 0) { sl.y = adj_start[b.y] + atomicAdd(cursor + b.y, 1u); adj[sl.y] = make_uint2(u, p); }
-    slots[u] = sl;
+    // every list slot also remembers whose list it is and which side of the unit it stands for (top bit)
+    if (b.x >= 0) { const uint32_t q = adj_start[b.x] + atomicAdd(cursor + b.x, 1u); adj[q] = make_uint2(u, p); adj_body[q] = uint32_t(b.x); }
+    if (b.y >= 0) { const uint32_t q = adj_start[b.y] + atomicAdd(cursor + b.y, 1u); adj[q] = make_uint2(u, p); adj_body[q] = uint32_t(b.y) | 0x80000000u; }
     urec[u] = make_int4(b.x, b.y, 0, 0);       // k_adj_rank fills in the two ranks
     bucket_key[u] = (~p) >> bucket_shift;
     order[u] = u;
@@ -384,27 +393,14 @@ __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* 
 // rest are grouped by narrowphase path (circle-circle / circle-polygon by polygon kind / polygon-polygon by edge count)
 // and visit count, so the 32 lanes of a warp run the same branches. The order inside a colour cannot change results
 // (no shared dynamic body), only divergence.
-__global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const uint32_t* __restrict__ colour, const uint2* __restrict__ ids,
-                                                        const float4* __restrict__ CS, const int4* __restrict__ CI,
-                                                        const uint32_t* __restrict__ prio, uint32_t* __restrict__ keys,
-                                                        uint32_t* __restrict__ near_count) {
+__global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const uint32_t* __restrict__ colour, const uint8_t* __restrict__ ucls,
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ near_count) {
     __shared__ uint32_t s_near[64];
     if (threadIdx.x < 64) s_near[threadIdx.x] = 0u;
     __syncthreads();
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u < n_units) {
-        uint32_t cls = 0;
-        if (CS) {
-            const uint2 id = ids[u];
-            const uint32_t k0 = __float_as_uint(CS[id.x].w), k1 = __float_as_uint(CS[id.y].w);
-            uint32_t path;
-            if (k0 == K_POINT && k1 == K_POINT) path = 0;
-            else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
-            else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
-            const uint32_t mult2 = (CI[id.x].x >= 0 && CI[id.y].x >= 0) ? 1u : 0u;
-            cls = path * 2 + mult2;
-            if (!(prio[u] >> 31)) cls |= 16u;                                                 // not `near` (k_pair_unit_setup): goes last
-        }
+        const uint32_t cls = ucls ? ucls[u] : 0u;            // k_pair_unit_setup; constraints have no classes
         const uint32_t col = colour[u];
         keys[u] = col * 32u + cls;
         // how many units of each colour sort into its "may touch" head: the solver deals those out a few lanes per warp
@@ -452,26 +448,27 @@ SFG_DI bool unit_higher(uint2 vp, uint32_t pu, uint2 iu, const uint2* __restrict
 // rank of every adjacency entry inside its body's list = how many of that body's other units come before it. One thread per
 // list slot: the lanes of a warp walk the same one to three lists, so the walk is broadcast loads (the same scan done by
 // each unit for itself touches 2 x degree scattered sectors and was most of the colouring time in crowded worlds).
-__global__ void __launch_bounds__(256) k_adj_rank(uint32_t n_slots, const uint2* __restrict__ adj, const int2* __restrict__ ub,
-                                                  const uint2* __restrict__ slots, const uint2* __restrict__ ids,
-                                                  const uint32_t* __restrict__ adj_start, int4* __restrict__ urec, uint32_t* ctrl,
-                                                  uint32_t n_bodies) {
+__global__ void __launch_bounds__(256) k_adj_rank(uint32_t n_slots, const uint2* __restrict__ adj, const uint32_t* __restrict__ adj_body,
+                                                  const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
+                                                  int4* __restrict__ urec, uint32_t* ctrl, uint32_t n_bodies) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_slots || q >= adj_start[n_bodies]) return;      // slots in use = sum of the degrees (static sides have no list)
     const uint2 me = adj[q];
-    const int2 b = ub[me.x];
-    const bool side0 = slots[me.x].x == q;
-    const int body = side0 ? b.x : b.y;
-    const uint2 iu = ids[me.x];
+    const uint32_t ab = adj_body[q], body = ab & 0x7FFFFFFFu;
     const uint32_t a0 = adj_start[body], a1 = adj_start[body + 1];
     uint32_t r = 0;
     for (uint32_t a = a0; a < a1; ++a) {
         const uint2 vp = adj[a];
-        if (vp.x != me.x && unit_higher(vp, me.y, iu, ids)) ++r;
+        if (vp.x == me.x) continue;
+        if (vp.y != me.y) r += vp.y > me.y ? 1u : 0u;
+        else {                                                 // equal hashes (rare): the pair's collider slots decide
+            const uint2 iv = ids[vp.x], iu = ids[me.x];
+            r += (iv.x > iu.x || (iv.x == iu.x && iv.y > iu.y)) ? 1u : 0u;
+        }
     }
     if (a1 - a0 >= (1u << (64 - CM_BITS))) ctrl[5] = 1u;
     // the colouring pass reads ONE 16-byte record per unit: (body 0, body 1, rank in body 0's list, rank in body 1's list)
-    reinterpret_cast<int*>(urec + me.x)[side0 ? 2 : 3] = int(r);
+    reinterpret_cast<int*>(urec + me.x)[(ab >> 31) ? 3 : 2] = int(r);
 }
 // exact smallest colour unused by the higher-priority neighbours of u, by windows of 64 colours; every such neighbour is
 // coloured by the time this runs (its ticket came up), the poll only bridges the gap between its two stores
