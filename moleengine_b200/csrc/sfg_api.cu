@@ -1120,7 +1120,7 @@ int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
     const char* trace_path = getenv("SFG_TRACE");
     unsigned long long* trace = nullptr;
     const size_t trace_n = size_t(2) * count * ns * grid;
-    if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; }
+    if (trace_path) { CK(w->trace.ensure(trace_n)); trace = w->trace.p; CK(cudaMemsetAsync(trace, 0, trace_n * 8, st)); }   // skipped stages stay 0
     static const bool debug_nan = getenv("SFG_DEBUG_NAN") != nullptr;
     uint32_t* dbg = nullptr;
     if (debug_nan) { CK(w->dbg.ensure(4096 + 8)); CK(cudaMemsetAsync(w->dbg.p, 0xFF, (4096 + 8) * 4, st)); dbg = w->dbg.p; }
