@@ -813,7 +813,10 @@ int broadphase(SfgWorld* w, float frame_dt) {
     const uint32_t* keys = where ? w->keys1.p : w->keys0.p;
     const uint32_t* vals = where ? w->vals1.p : w->vals0.p;
     // 3. sorted copies + cell starts
-    CK(w->SA.ensure(ne)); CK(w->SI.ensure(ne)); CK(w->cell_start.ensure(size_t(g.n_keys) + 2));
+    // the key space is bounded by choose_grid's cap (cells of all levels <= cap / 2, repeated once for proxies and big-plain
+    // levels): sized for the bound once, so a world that spreads out never reallocates its cell table in the middle of a run
+    const size_t key_bound = size_t(std::min(double(1u << 26), 8.0 * double(w->n_live) + 4096.0)) + 2;
+    CK(w->SA.ensure(ne)); CK(w->SI.ensure(ne)); CK(w->cell_start.ensure(std::max(size_t(g.n_keys) + 2, key_bound)));
     k_gather_sorted<<<nblk(ne), 256, 0, st>>>(g, ne, keys, vals, w->AABB.p, w->CI.p, w->SA.p, w->SI.p);
     CKL(w); w->launches++;
     k_cell_starts<<<nblk(ne + 1), 256, 0, st>>>(keys, ne, g.n_keys, w->cell_start.p);
