@@ -102,7 +102,7 @@ struct SfgWorld {
     DBuf<float4> H, S, G0, G1, L0, L1, M0, M1, M2;
     DBuf<float2> LN;
     DBuf<float> RC;
-    DBuf<uint32_t> WL, wl_count, near_count;
+    DBuf<uint32_t> WL, wl_count, near_count, far_min;
     uint32_t last_substeps = 0;   // substeps of the last tick = tag of a manifold entry written in its last substep
     // constraint units
     uint32_t n_kunits = 0, n_k_colours = 0;
@@ -521,7 +521,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->body_word.release(); w->trace.release(); w->adj_body.release(); w->adj_rank.release(); w->U_cls.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->far_min.release(); w->body_word.release(); w->trace.release(); w->adj_body.release(); w->adj_rank.release(); w->U_cls.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
@@ -1060,6 +1060,9 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
             CK(w->wl_count.ensure(size_t(substeps) * w->n_unit_colours));
             CK(cudaMemsetAsync(w->wl_count.p, 0, size_t(substeps) * w->n_unit_colours * 4, st));
             w->tick_ctx.wl_count = w->wl_count.p;
+            CK(w->far_min.ensure(substeps));
+            CK(cudaMemsetAsync(w->far_min.p, 0xFF, size_t(substeps) * 4, st));
+            w->tick_ctx.far_min = w->far_min.p;
         }
         if (!(w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES)) {
             const uint32_t ns = uint32_t(w->h_stages.size());

@@ -496,6 +496,32 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u, uint32_t sub) {
     if (fl & UF_SEES1) stb(c.V + b1, V1);
 }
 
+// The two rejects of stage_contacts on their own: true = the unit cannot touch and stage_contacts would return from its first
+// visit without a store. First the body-level test (header, reach, one 16-byte gather per body or the static collider's
+// position); a unit that passes it (common for compounds: the body-level reach is loose) is tested on its collider centres
+// like every visit of stage_contacts does, with a 1e-4 margin on the squared bound so that rounding differences between
+// the two evaluations can only make this helper keep a unit, never drop one.
+SFG_DI bool contacts_rejects(const SolverCtx& c, uint32_t u) {
+    const float4 h = ldc(c.H + u);
+    const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
+    if (__float_as_uint(h.z) & UF_ASLEEP) return true;
+    const float reach = __ldg(c.RC + u);
+    const float4 l0 = ldc(c.L0 + u), l1 = ldc(c.L1 + u);
+    float4 A = make_float4(l0.x, l0.y, 0.f, 0.f), B = make_float4(l1.x, l1.y, 0.f, 0.f);
+    if (b0 >= 0) A = ldb(c.P + b0);
+    if (b1 >= 0) B = ldb(c.P + b1);
+    const V2 d = mk((B.x - A.x) + (B.z - A.z), (B.y - A.y) + (B.w - A.w));
+    if (mag_sq(d) > reach * reach) return true;
+    // collider centres in the pair-local frame (origin = object 0's substep-start position or static translation)
+    V2 t0 = mk(0.f, 0.f), t1 = d;
+    if (b0 >= 0) { const float4 q = ldb(c.Q + b0); t0 = mkrot(q.x, q.y) * mk(l0.x, l0.y) + mk(A.z, A.w); }
+    if (b1 >= 0) { const float4 q = ldb(c.Q + b1); t1 = mkrot(q.x, q.y) * mk(l1.x, l1.y) + mk((B.x - A.x) + B.z, (B.y - A.y) + B.w); }
+    else t1 = mk(l1.x - A.x, l1.y - A.y);
+    const float reach2 = (bound_radius(mkshape(ldc(c.G0 + u))) + bound_radius(mkshape(ldc(c.G1 + u)))) * 1.001f + 1e-3f;
+    const float far_sq = fmaxf(reach2 * reach2, 0.0011f);
+    return mag_sq(t1 - t0) > far_sq * 1.0001f;
+}
+
 // ---------------------------------------------------------------- drivers
 SFG_DI void run_stage(const SolverCtx& c, uint32_t kind, uint32_t i, bool last_substep, uint32_t sub, uint32_t colour, uint32_t begin, bool head) {
     switch (kind) {
@@ -552,8 +578,36 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
     unsigned int target = 0;
     for (uint32_t s = sub_begin; s < sub_end; ++s) {   // substeps [sub_begin, sub_end) of a tick of `substeps`
         const bool last = s + 1 == substeps;
+        uint32_t merged_until = 0;                      // contact stages below this index have been through the merged reject pass
         for (uint32_t k = 0; k < n_stages; ++k) {
             const Stage st = stages[k];
+            // The high colours hold only pairs that were clearly apart at tick start (near_count == 0), and nearly always every
+            // one of them is rejected by the distance test, stage after stage, each paying a barrier and two round trips for
+            // nothing. A reject changes no state, so a run of such stages is tested in ONE pass; if every unit is rejected the
+            // whole run is done. If some unit survives, the stages from the first survivor's on are run the ordinary way (the
+            // stages before it changed nothing, so the order of the sweep is exactly the sequential one).
+            if (st.kind == ST_CONTACTS && k >= merged_until && __ldg(c.near_count + st.colour) == 0u) {
+                uint32_t k2 = k + 1;
+                while (k2 < n_stages && stages[k2].kind == ST_CONTACTS && __ldg(c.near_count + stages[k2].colour) == 0u) ++k2;
+                if (k2 - k >= 2u) {
+                    const uint32_t lo = st.begin, hi = stages[k2 - 1u].end;
+                    bool survivor = false;
+                    uint32_t first = 0xFFFFFFFFu;
+                    for (uint32_t i = lo + first_chunk * 32u + lane; i < hi; i += chunk_stride * 32u)
+                        if (!contacts_rejects(c, i)) { survivor = true; first = min(first, i); }
+                    if (survivor) {                     // rare: which stage is that unit in?
+                        uint32_t ks = k;
+                        while (ks + 1u < k2 && first >= stages[ks].end) ++ks;
+                        atomicMin(c.far_min + s, ks);
+                    }
+                    grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
+                    const uint32_t fm = __ldcg(c.far_min + s);
+                    merged_until = k2;
+                    if (fm == 0xFFFFFFFFu) { k = k2 - 1u; continue; }       // every unit of the run rejected: all its stages are done
+                    k = fm - 1u;                                             // resume at the first survivor's stage
+                    continue;
+                }
+            }
             const uint32_t n = st.kind == ST_CONTACT_VEL ? __ldcg(c.wl_count + s * c.n_colours + st.colour) : st.end - st.begin;
             // an empty velocity worklist (the high colours hold only pairs that did not touch): no work and no barrier. The count
             // was final before the barrier of the derive stage, so every CTA takes the same branch.
