@@ -3,10 +3,12 @@
 // batched casts and the parity hooks. There is NO CPU fallback: every entry point that computes needs a
 // CUDA device and reports SFG_E_NO_DEVICE / SFG_E_CUDA otherwise.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,21 +23,47 @@ using namespace sfg;
 
 namespace {
 
+// Device buffers grow with 50 % headroom and NEVER call cudaFree while a world is in use: on this platform a cudaFree in the
+// middle of a run was measured at 90-270 ms (it synchronises the device and unmaps), i.e. a visible hitch every time a pile
+// grows past a buffer. The outgrown allocation goes to a graveyard that is emptied when the world is cleared or destroyed;
+// the dead memory is bounded by the geometric growth (less than twice the live size).
+struct Graveyard {
+    std::mutex mu;
+    std::vector<void*> dead;
+    void add(void* q) { std::lock_guard<std::mutex> l(mu); dead.push_back(q); }
+    bool empty() { std::lock_guard<std::mutex> l(mu); return dead.empty(); }
+    void bury_all() { std::lock_guard<std::mutex> l(mu); for (void* q : dead) cudaFree(q); dead.clear(); }   // cudaFree synchronises the device first
+};
+inline Graveyard& dbuf_graveyard() { static Graveyard g; return g; }
 template <class T>
 struct DBuf {
     T* p = nullptr;
     size_t cap = 0;
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        static const bool dbg = getenv("SFG_DEBUG_ALLOC") != nullptr;     // debug: report every (re)allocation and what it cost
+        const auto t0 = std::chrono::steady_clock::now();
+        if (p) dbuf_graveyard().add(p);
         p = nullptr; cap = 0;
-        size_t want = n + n / 2 + 64;   // 50 % headroom: cudaFree + cudaMalloc stall the tick, and pair counts creep up as piles form
+        size_t want = n + n / 2 + 64;   // 50 % headroom: pair counts creep up as piles form
         cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess && !dbuf_graveyard().empty()) {     // out of memory: now the graveyard has to go
+            cudaGetLastError();
+            dbuf_graveyard().bury_all();
+            e = cudaMalloc(&p, want * sizeof(T));
+        }
         if (e == cudaSuccess) cap = want;
+        if (dbg) fprintf(stderr, "SFG_DEBUG_ALLOC: %zu bytes, cudaMalloc %.2f ms\n", want * sizeof(T),
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+
+// Pair-sized buffers are reserved for 6 candidate pairs per live collider from the first tick on (2-8 pairs per
+// body; C3 peaks at 3.5, C5 at 7): a cudaMalloc in the middle of a run costs 100-700 ms on this platform when it has to map
+// fresh memory, which showed up as a hitch every time a growing pile outgrew its buffers. ~330 B per reserved pair.
+constexpr size_t RESERVE_PAIRS_PER_COLLIDER = 6;
 
 struct TickHeader {            // small device block read back once per tick phase
     Bounds bounds;
@@ -115,6 +143,8 @@ struct SfgWorld {
     DBuf<Stage> d_stages;
     DBuf<unsigned long long> trace, body_word;
     DBuf<uint32_t> adj_body;          // per list slot: body | side << 31
+    DBuf<uint32_t> adj_colour;        // per list slot of a crowded body: the colour of that unit
+    DBuf<uint2> U_slot;               // per unit: its slots in crowded lists
     DBuf<uint8_t> U_cls;              // per pair unit: order class inside a colour (k_pair_unit_setup)
     DBuf<int4> adj_rank;              // per unit: (body 0, body 1, rank in body 0's list, rank in body 1's list)
     std::vector<Stage> h_stages;
@@ -380,13 +410,14 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     *perm_out = nullptr;
     if (n_units == 0) { colour_start.push_back(0); return SFG_OK; }
     const uint32_t nb = w->n_bodies;
+    const size_t nr = pair_units ? std::max<size_t>(n_units, size_t(w->n_live) * RESERVE_PAIRS_PER_COLLIDER) : n_units;   // reserved size of pair-sized buffers
     // adjacency (deg was accumulated by the unit-setup kernel) + bucket keys of the colouring order
     constexpr uint32_t HIST_CAP = 65536;
-    CK(w->adj_start.ensure(nb + 2)); CK(w->cursor.ensure(nb + 1)); CK(w->adj2.ensure(size_t(n_units) * 2 + 1));
+    CK(w->adj_start.ensure(nb + 2)); CK(w->cursor.ensure(nb + 1)); CK(w->adj2.ensure(size_t(nr) * 2 + 1));
     CK(w->scan_tmp.ensure(scan_tmp_words(nb + 1)));
-    CK(colour.ensure(n_units)); CK(w->jp_counters.ensure(16 + HIST_CAP));   // [0, 16) control words, then units per colour
-    CK(w->ckey0.ensure(n_units)); CK(w->ckey1.ensure(n_units)); CK(w->perm0.ensure(n_units)); CK(w->perm1.ensure(n_units));
-    CK(w->sort_tmp.ensure(sort_tmp_words(n_units)));
+    CK(colour.ensure(nr)); CK(w->jp_counters.ensure(16 + HIST_CAP));   // [0, 16) control words, then units per colour
+    CK(w->ckey0.ensure(nr)); CK(w->ckey1.ensure(nr)); CK(w->perm0.ensure(nr)); CK(w->perm1.ensure(nr));
+    CK(w->sort_tmp.ensure(sort_tmp_words(nr)));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_dataflow, 1024, 0));
     const uint32_t grid = std::max(1u, std::min<uint32_t>(uint32_t(per_sm * w->n_sms), nblk(n_units, 1024)));
@@ -397,7 +428,9 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * 8 > size_t(grid) * 1024) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
-    CK(w->adj_body.ensure(size_t(n_units) * 2 + 1)); CK(w->adj_rank.ensure(size_t(n_units) + 1));
+    CK(w->adj_body.ensure(size_t(nr) * 2 + 1)); CK(w->adj_rank.ensure(size_t(nr) + 1));
+    CK(w->adj_colour.ensure(size_t(nr) * 2 + 1)); CK(w->U_slot.ensure(size_t(nr) + 1));
+    CK(cudaMemsetAsync(w->adj_colour.p, 0xFF, (size_t(n_units) * 2 + 1) * 4, st));
     k_adj_fill<<<nblk(n_units), 256, 0, st>>>(n_units, ub, prio, w->adj_start.p, w->cursor.p, w->adj2.p, w->adj_body.p, w->adj_rank.p, 32 - bucket_bits, w->ckey0.p, w->perm0.p);
     CKL(w); w->launches++;
     const uint32_t* order;
@@ -412,17 +445,25 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     CK(w->body_word.ensure(nb + 1));
     CK(cudaMemsetAsync(w->body_word.p, 0, size_t(nb + 1) * 8, st));
     // list slots in use = sum of degrees <= 2 n_units; unused tail slots of the allocation are never read
-    k_adj_rank<<<nblk(n_units * 2), 256, 0, st>>>(n_units * 2, w->adj2.p, w->adj_body.p, ids, w->adj_start.p, w->adj_rank.p, w->jp_counters.p, nb);
+    k_adj_rank<<<nblk(n_units * 2), 256, 0, st>>>(n_units * 2, w->adj2.p, w->adj_body.p, ids, w->adj_start.p, w->adj_rank.p, w->U_slot.p, w->jp_counters.p, nb);
     CKL(w); w->launches++;
     {
         uint32_t hist_cap = HIST_CAP;
         const uint32_t* adj_start = w->adj_start.p; const uint2* adj = w->adj2.p;
         uint32_t* col = colour.p; uint32_t* ctrl = w->jp_counters.p; uint32_t* hist = w->jp_counters.p + 16;
         unsigned long long* words = w->body_word.p;
-        const int4* urec = w->adj_rank.p;
-        void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, (void*)&urec, &col, &words, &ctrl, &hist, &hist_cap};
+        const int4* urec = w->adj_rank.p; const uint2* uslot = w->U_slot.p; uint32_t* adj_colour = w->adj_colour.p;
+        void* args[] = {&n_units, (void*)&order, (void*)&ub, (void*)&prio, (void*)&ids, (void*)&adj_start, (void*)&adj, (void*)&urec, (void*)&uslot, &adj_colour, &col, &words, &ctrl, &hist, &hist_cap};
+        static const bool dbg_slow = getenv("SFG_DEBUG_SLOW") != nullptr;   // debug: wall time of the colouring kernel alone
+        std::chrono::steady_clock::time_point t0;
+        if (dbg_slow) { CK(cudaStreamSynchronize(st)); t0 = std::chrono::steady_clock::now(); }
         CK(cudaLaunchCooperativeKernel((void*)k_colour_dataflow, dim3(grid), dim3(1024), args, 0, st));
         w->launches++;
+        if (dbg_slow) {
+            CK(cudaStreamSynchronize(st));
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (ms > 20.0) fprintf(stderr, "SFG_DEBUG_SLOW: k_colour_dataflow %.1f ms (%u units, grid %u)\n", ms, n_units, grid);
+        }
     }
     // one read-back for the control words and the first 64 colours (a second one only if there are more)
     uint32_t head[16 + 64];
@@ -507,6 +548,7 @@ void sfg_world_destroy(SfgWorld* w) {
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
     if (w->stream2) cudaStreamSynchronize(w->stream2);
+    dbuf_graveyard().bury_all();
     DBuf<float4>* f4[] = {&w->P, &w->Q, &w->V, &w->OV, &w->MI, &w->CS, &w->CL, &w->CM, &w->AABB, &w->KA, &w->KB, &w->RPA, &w->RPB, &w->SA,
                           &w->H, &w->S, &w->G0, &w->G1, &w->L0, &w->L1, &w->M0, &w->M1, &w->M2, &w->K0, &w->K1, &w->K2};
     for (auto* b : f4) b->release();
@@ -521,7 +563,7 @@ void sfg_world_destroy(SfgWorld* w) {
     for (auto* b : i1) b->release();
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
-    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->far_min.release(); w->body_word.release(); w->trace.release(); w->adj_body.release(); w->adj_rank.release(); w->U_cls.release(); w->U_ub.release(); w->KU_ub.release();
+    w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->far_min.release(); w->body_word.release(); w->trace.release(); w->adj_body.release(); w->adj_rank.release(); w->U_cls.release(); w->adj_colour.release(); w->U_slot.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
@@ -533,6 +575,9 @@ void sfg_world_destroy(SfgWorld* w) {
 
 int sfg_world_clear(SfgWorld* w) {   // physics.rs:386-393
     if (!w) return SFG_E_INVALID;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    dbuf_graveyard().bury_all();         // outgrown buffers of the run that ends here
     w->n_bodies = w->n_colls = w->n_constraints = w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0;
     w->n_units = w->n_kunits = 0;
     w->ct_n = 0; w->islands_valid = false;
@@ -823,7 +868,7 @@ int broadphase(SfgWorld* w, float frame_dt) {
     CKL(w); w->launches++;
     // 4. candidate pairs in one pass; capacity is last tick's count + 25 % (re-run once if it overflows)
     const uint32_t n_warps = (w->n_live + 31) / 32;
-    size_t want = std::max<size_t>(size_t(w->prev_pairs) + w->prev_pairs / 4 + 4096, size_t(w->n_live) * 2);
+    size_t want = std::max<size_t>(size_t(w->prev_pairs) + w->prev_pairs / 4 + 4096, size_t(w->n_live) * RESERVE_PAIRS_PER_COLLIDER);
     for (int attempt = 0; attempt < 2; ++attempt) {
         CK(w->U_ids.ensure(want));
         const uint32_t cap = uint32_t(std::min<size_t>(w->U_ids.cap, 0xFFFFFFFFu));
@@ -852,16 +897,17 @@ int build_graph(SfgWorld* w) {
     // ---- pair units
     if (w->n_units) {
         const uint32_t n = w->n_units;
-        CK(w->U_ub.ensure(n)); CK(w->U_prio.ensure(n)); CK(w->U_cls.ensure(n));
+        const size_t nr = std::max<size_t>(n, size_t(w->n_live) * RESERVE_PAIRS_PER_COLLIDER);
+        CK(w->U_ub.ensure(nr)); CK(w->U_prio.ensure(nr)); CK(w->U_cls.ensure(nr));
         CK(cudaMemsetAsync(w->deg.p, 0, size_t(nb + 2) * 4, st));
         k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->CS.p, w->CL.p, w->P.p, w->Q.p, w->V.p, w->frame_dt, w->U_ub.p, w->U_prio.p, w->deg.p, w->U_cls.p);
         CKL(w); w->launches++;
         uint32_t* perm = nullptr;
         int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours, true);
         if (rc != SFG_OK) return rc;
-        CK(w->RC.ensure(n)); CK(w->WL.ensure(n));
-        CK(w->H.ensure(n)); CK(w->S.ensure(n)); CK(w->G0.ensure(n)); CK(w->G1.ensure(n)); CK(w->L0.ensure(n)); CK(w->L1.ensure(n));
-        CK(w->M0.ensure(size_t(n) * 2)); CK(w->M1.ensure(size_t(n) * 2)); CK(w->M2.ensure(size_t(n) * 2)); CK(w->LN.ensure(size_t(n) * 2));
+        CK(w->RC.ensure(nr)); CK(w->WL.ensure(nr));
+        CK(w->H.ensure(nr)); CK(w->S.ensure(nr)); CK(w->G0.ensure(nr)); CK(w->G1.ensure(nr)); CK(w->L0.ensure(nr)); CK(w->L1.ensure(nr));
+        CK(w->M0.ensure(nr * 2)); CK(w->M1.ensure(nr * 2)); CK(w->M2.ensure(nr * 2)); CK(w->LN.ensure(nr * 2));
         { int jr = join_islands(w); if (jr != SFG_OK) return jr; }
         k_build_pair_units<<<nblk(n), 256, 0, st>>>(n, perm, w->U_ids.p, w->CS.p, w->CL.p, w->CM.p, w->CI.p, w->MI.p,
                                                     w->n_ropes ? w->rope_next.p : nullptr, w->n_ropes ? w->rope_prev.p : nullptr, w->H.p, w->S.p,
@@ -957,7 +1003,7 @@ int island_post(SfgWorld* w) {
     const uint32_t n_entries = w->n_units * 2;
     DBuf<ContactRec>& old_list = w->ct[w->ct_cur];
     DBuf<ContactRec>& new_list = w->ct[w->ct_cur ^ 1];
-    CK(new_list.ensure(size_t(w->ct_n) + n_entries + 1));
+    CK(new_list.ensure(std::max<size_t>(size_t(w->ct_n) + n_entries + 1, size_t(w->n_live) * RESERVE_PAIRS_PER_COLLIDER * 2)));
     uint32_t* cursor = w->isl_counters.p + 4;
     CK(cudaMemsetAsync(cursor, 0, 4, st));
     if (w->ct_n) {

@@ -450,7 +450,7 @@ SFG_DI bool unit_higher(uint2 vp, uint32_t pu, uint2 iu, const uint2* __restrict
 // each unit for itself touches 2 x degree scattered sectors and was most of the colouring time in crowded worlds).
 __global__ void __launch_bounds__(256) k_adj_rank(uint32_t n_slots, const uint2* __restrict__ adj, const uint32_t* __restrict__ adj_body,
                                                   const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
-                                                  int4* __restrict__ urec, uint32_t* ctrl, uint32_t n_bodies) {
+                                                  int4* __restrict__ urec, uint2* __restrict__ uslot, uint32_t* ctrl, uint32_t n_bodies) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_slots || q >= adj_start[n_bodies]) return;      // slots in use = sum of the degrees (static sides have no list)
     const uint2 me = adj[q];
@@ -467,36 +467,69 @@ __global__ void __launch_bounds__(256) k_adj_rank(uint32_t n_slots, const uint2*
         }
     }
     if (a1 - a0 >= (1u << (64 - CM_BITS))) ctrl[5] = 1u;
-    // the colouring pass reads ONE 16-byte record per unit: (body 0, body 1, rank in body 0's list, rank in body 1's list)
-    reinterpret_cast<int*>(urec + me.x)[(ab >> 31) ? 3 : 2] = int(r);
+    // the colouring pass reads ONE 16-byte record per unit: (body 0, body 1, rank in body 0's list, rank in body 1's list).
+    // A list longer than the 40 colours of the body word is "crowded" (top bit of the rank): its units also write their colour
+    // next to their list entry (adj_colour, k_colour_dataflow), so they have to know where that entry is.
+    const bool crowded = a1 - a0 > uint32_t(CM_BITS);
+    reinterpret_cast<int*>(urec + me.x)[(ab >> 31) ? 3 : 2] = int(r | (crowded ? 0x80000000u : 0u));
+    if (crowded) reinterpret_cast<uint32_t*>(uslot + me.x)[(ab >> 31) ? 1 : 0] = q;
 }
-// exact smallest colour unused by the higher-priority neighbours of u, by windows of 64 colours; every such neighbour is
-// coloured by the time this runs (its ticket came up), the poll only bridges the gap between its two stores
-SFG_DI uint32_t colour_scan_exact(uint32_t u, int2 b, uint32_t pu, uint2 iu, const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start,
-                                  const uint2* __restrict__ adj, const uint32_t* colour) {
-    for (uint32_t win = 0;; win += 64) {
-        unsigned long long w_used = 0ull;
-        bool w_beyond = false;
-        for (int sd = 0; sd < 2; ++sd) {
-            const int body = sd ? b.y : b.x;
-            if (body < 0 || (sd && b.y == b.x)) continue;
-            for (uint32_t q = adj_start[body], q1 = adj_start[body + 1]; q < q1; ++q) {
-                const uint2 vp = adj[q];
-                if (vp.x == u || !unit_higher(vp, pu, iu, ids)) continue;
-                uint32_t cv, spins = 0;
-                while ((cv = ld_relaxed(colour + vp.x)) == 0xFFFFFFFFu && ++spins < (1u << 22)) __nanosleep(40);   // bounded: see the watchdog in k_colour_dataflow
-                if (cv >= win && cv < win + 64) w_used |= 1ull << (cv - win);
-                else if (cv >= win + 64) w_beyond = true;
+// Exact smallest colour unused by the higher-priority neighbours of unit u, for a unit whose two body words show colours
+// 0..39 all taken. The WHOLE WARP does it for one of its lanes (all arguments are that lane's values, broadcast): the 32
+// lanes stride over the two lists and or their bit sets together. A lane doing this alone keeps its 31 neighbours from
+// polling for the 50 us a 300-entry list takes, and with them every unit queued behind their tickets — measured as ticks
+// of 0.2 to 1 s in a rope pile with 290 colours. Every higher-priority neighbour is coloured by the time this runs (its
+// ticket came up); a colour word still unset only means its store is in flight, then the pass is repeated. A crowded body's
+// colours sit next to its list (adj_colour): contiguous reads instead of a gather per neighbour. One pass collects colours
+// base..base+511 in a bit set; beyond that, the next 512.
+SFG_DI uint32_t colour_scan_warp(uint32_t lane, uint32_t u, int bx, int by, bool crowded0, bool crowded1, uint32_t pu, uint2 iu,
+                                 const uint2* __restrict__ ids, const uint32_t* __restrict__ adj_start, const uint2* __restrict__ adj,
+                                 const uint32_t* colour, const uint32_t* adj_colour, uint32_t* ctrl) {
+    for (uint32_t base = 0;; base += 512u) {
+        uint32_t m[16];
+        bool beyond, retry;
+        uint32_t spins = 0;
+        do {
+            retry = false; beyond = false;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) m[i] = 0u;
+            for (int sd = 0; sd < 2; ++sd) {
+                const int body = sd ? by : bx;
+                if (body < 0 || (sd && by == bx)) continue;
+                const bool crowded = sd ? crowded1 : crowded0;
+                const uint32_t q0 = adj_start[body], q1 = adj_start[body + 1];
+                for (uint32_t q = q0 + lane; q < q1; q += 32u) {
+                    const uint2 vp = adj[q];
+                    const uint32_t cv = crowded ? ld_relaxed(adj_colour + q) : ld_relaxed(colour + vp.x);
+                    if (vp.x == u || !unit_higher(vp, pu, iu, ids)) continue;
+                    if (cv == 0xFFFFFFFFu) { retry = true; continue; }
+                    if (cv < base) continue;
+                    const uint32_t rel = cv - base;
+                    if (rel < 512u) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) if (int(rel >> 5) == i) m[i] |= 1u << (rel & 31u);   // static indices: the set stays in registers
+                    } else beyond = true;
+                }
             }
+            retry = __any_sync(0xFFFFFFFFu, retry);
+            if (retry) __nanosleep(100);
+        } while (retry && ++spins < (1u << 20));              // bounded: see the watchdog in k_colour_dataflow
+        if (retry) ctrl[6] = 2u;                               // a neighbour's colour never arrived: reported like the watchdog
+        beyond = __any_sync(0xFFFFFFFFu, beyond);
+        uint32_t found = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t all = __reduce_or_sync(0xFFFFFFFFu, m[i]);
+            if (found == 0xFFFFFFFFu && all != 0xFFFFFFFFu) found = base + uint32_t(i) * 32u + uint32_t(__ffs(int(~all)) - 1);
         }
-        if (w_used != ~0ull) return win + uint32_t(__ffsll((long long)~w_used) - 1);
-        if (!w_beyond) return win + 64;
+        if (found != 0xFFFFFFFFu) return found;
+        if (!beyond) return base + 512u;
     }
 }
 __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, const uint32_t* __restrict__ order, const int2* __restrict__ ub,
                                                          const uint32_t* __restrict__ prio, const uint2* __restrict__ ids,
                                                          const uint32_t* __restrict__ adj_start, const uint2* __restrict__ adj,
-                                                         const int4* __restrict__ urec,
+                                                         const int4* __restrict__ urec, const uint2* __restrict__ uslot, uint32_t* adj_colour,
                                                          uint32_t* colour, unsigned long long* body_word, uint32_t* ctrl, uint32_t* hist, uint32_t hist_cap) {
     __shared__ uint32_t s_hist[64];
     __shared__ uint32_t s_max;
@@ -514,35 +547,59 @@ __global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, cons
         uint2 iu = make_uint2(0, 0);
         unsigned long long want0 = 0, want1 = 0;        // ticket the body must show, already shifted
         uint32_t step0 = 1;                            // a unit whose two sides are the same body sits twice in that list
+        bool crowded0 = false, crowded1 = false;       // that body's list is longer than the 40 colours of its word
         if (!done) {
             u = order[idx];
             const int4 rec = urec[u];
             b = make_int2(rec.x, rec.y);
-            if (b.x >= 0) want0 = (unsigned long long)uint32_t(rec.z) << CM_BITS;
+            crowded0 = rec.z < 0; crowded1 = rec.w < 0;
+            if (b.x >= 0) want0 = (unsigned long long)(uint32_t(rec.z) & 0x7FFFFFFFu) << CM_BITS;
             if (b.y == b.x && b.x >= 0) { b.y = -1; step0 = 2; }
-            if (b.y >= 0) want1 = (unsigned long long)uint32_t(rec.w) << CM_BITS;
+            if (b.y >= 0) want1 = (unsigned long long)(uint32_t(rec.w) & 0x7FFFFFFFu) << CM_BITS;
         }
         uint32_t polls = 0;
         while (__any_sync(0xFFFFFFFFu, !done)) {
+            bool ready = false;
+            unsigned long long w0 = 0ull, w1 = 0ull;
             if (!done) {
+                w0 = b.x >= 0 ? ld_relaxed64(body_word + b.x) : 0ull;
+                w1 = b.y >= 0 ? ld_relaxed64(body_word + b.y) : 0ull;
                 // watchdog: a ticket that never comes up (it cannot, by the progress argument above) must not hang the device
-                const unsigned long long w0 = b.x >= 0 ? ld_relaxed64(body_word + b.x) : 0ull;
-                const unsigned long long w1 = b.y >= 0 ? ld_relaxed64(body_word + b.y) : 0ull;
                 if (++polls > (1u << 22)) { ctrl[6] = 1u; done = true; }
-                else if ((w0 & ~CM_MASK) == want0 && (w1 & ~CM_MASK) == want1) {
-                    const unsigned long long used = (w0 | w1) & CM_MASK;
-                    const int2 bb = step0 == 2 ? make_int2(b.x, b.x) : b;
-                    const uint32_t result = used != CM_MASK ? uint32_t(__ffsll((long long)~used) - 1) : colour_scan_exact(u, bb, prio[u], ids[u], ids, adj_start, adj, colour);
-                    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(colour + u), "r"(result) : "memory");
-                    const unsigned long long bit = result < uint32_t(CM_BITS) ? 1ull << result : 0ull;
-                    if (b.x >= 0) st_relaxed64(body_word + b.x, (w0 | bit) + ((unsigned long long)step0 << CM_BITS));
-                    if (b.y >= 0) st_relaxed64(body_word + b.y, (w1 | bit) + (1ull << CM_BITS));
-                    if (result < 64) atomicAdd(&s_hist[result], 1u);
-                    else if (result < hist_cap) atomicAdd(hist + result, 1u);
-                    atomicMax(&s_max, result + 1u);
-                    done = true;
-                } else __nanosleep(100);
+                else ready = (w0 & ~CM_MASK) == want0 && (w1 & ~CM_MASK) == want1;
             }
+            const unsigned long long used = (w0 | w1) & CM_MASK;
+            uint32_t result = used != CM_MASK ? uint32_t(__ffsll((long long)~used) - 1) : 0u;
+            // lanes whose 40 mask bits are all taken: the warp scans their lists together, one lane's unit at a time
+            uint32_t scan = __ballot_sync(0xFFFFFFFFu, ready && used == CM_MASK);
+            while (scan) {
+                const int L = __ffs(int(scan)) - 1;
+                scan &= scan - 1u;
+                const uint32_t Lu = __shfl_sync(0xFFFFFFFFu, u, L);
+                const int Lbx = __shfl_sync(0xFFFFFFFFu, b.x, L);
+                const int Lby = __shfl_sync(0xFFFFFFFFu, step0 == 2 ? b.x : b.y, L);
+                const bool Lc0 = __shfl_sync(0xFFFFFFFFu, crowded0 ? 1 : 0, L) != 0, Lc1 = __shfl_sync(0xFFFFFFFFu, (step0 == 2 ? crowded0 : crowded1) ? 1 : 0, L) != 0;
+                uint32_t Lpu = 0; uint2 Liu = make_uint2(0, 0);
+                if (int(lane) == L) { Lpu = prio[u]; Liu = ids[u]; }
+                Lpu = __shfl_sync(0xFFFFFFFFu, Lpu, L); Liu.x = __shfl_sync(0xFFFFFFFFu, Liu.x, L); Liu.y = __shfl_sync(0xFFFFFFFFu, Liu.y, L);
+                const uint32_t r = colour_scan_warp(lane, Lu, Lbx, Lby, Lc0, Lc1, Lpu, Liu, ids, adj_start, adj, colour, adj_colour, ctrl);
+                if (int(lane) == L) result = r;
+            }
+            if (ready) {
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(colour + u), "r"(result) : "memory");
+                if (crowded0 || crowded1) {             // the colour also goes next to the unit's entries in crowded lists
+                    const uint2 sl = uslot[u];
+                    if (crowded0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(adj_colour + sl.x), "r"(result) : "memory");
+                    if (crowded1) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(adj_colour + sl.y), "r"(result) : "memory");
+                }
+                const unsigned long long bit = result < uint32_t(CM_BITS) ? 1ull << result : 0ull;
+                if (b.x >= 0) st_relaxed64(body_word + b.x, (w0 | bit) + ((unsigned long long)step0 << CM_BITS));
+                if (b.y >= 0) st_relaxed64(body_word + b.y, (w1 | bit) + (1ull << CM_BITS));
+                if (result < 64) atomicAdd(&s_hist[result], 1u);
+                else if (result < hist_cap) atomicAdd(hist + result, 1u);
+                atomicMax(&s_max, result + 1u);
+                done = true;
+            } else if (!done) __nanosleep(100);
         }
     }
     __syncthreads();
