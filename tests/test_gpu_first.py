@@ -17,7 +17,7 @@ def _pairset(p):
 
 
 @pytest.mark.parametrize("scene_fn", [scenes.c1_sandbox_stack, lambda: scenes.parity_mix(400, 7), lambda: scenes.c2_circles(60, 30),
-                                      lambda: scenes.star(150), lambda: scenes.c5_worlds(6, 16)])
+                                      lambda: scenes.star(150), lambda: scenes.star(700, big_r=40.0, small_r=0.2), lambda: scenes.c5_worlds(6, 16)])
 def test_pairs_and_colours_bit_exact(oracle, scene_fn):
     sc = scene_fn()
     tun = abi.default_tuning(substeps=1)
