@@ -5,7 +5,7 @@ A "step" is one physics tick (frame_dt = 1/60, 4 XPBD substeps) of the C3 worklo
 in one large world. With --gpus N > 1 every rank steps its own independent 1 M-body world
 (different seed, no data-path collective): weak scaling over independent worlds, the partition north_star
 names first. `value` is device-resident throughput (state already in HBM); `e2e` goes through the C ABI with
-pinned HOST buffers: poses in (sfg_update_bodies) -> sfg_tick -> poses out (sfg_get_bodies) every step, which is
+pinned HOST buffers: poses in -> tick -> poses out every step in one sfg_tick_poses call, which is
 what the reference's Game::physics_tick does around PhysicsWorld::tick (game.rs:297-303).
 
 --impl reference times the CPU restatement of the reference tick (oracle/, MODE_REFERENCE, all host threads) on a
@@ -225,19 +225,23 @@ def main():
     assert lib.sfg_world_clear(h) == 0
     g.load_scene(sc)
     assert lib.sfg_get_poses(h, 0, nb, abi.ptr(host_np)) == 0
+    # sfg_tick_poses = sfg_set_poses + sfg_tick + sfg_get_poses in one call (the upload queued in front of the tick, the download
+    # overlapping its last kernels); both host buffers are pinned
+    host_out = torch.empty(nb * 16, dtype=torch.uint8).pin_memory()
+    host_out_np = host_out.numpy().view(np.float32).reshape(nb, 4)
+    ffp = abi.ptr(ff)
     for _ in range(args.warmup):
-        lib.sfg_set_poses(h, 0, nb, abi.ptr(host_np)); g.tick(FRAME_DT, None, ff); lib.sfg_get_poses(h, 0, nb, abi.ptr(host_np))
+        assert lib.sfg_tick_poses(h, abi.ptr(host_np), FRAME_DT, 0, 0.0, ffp, abi.ptr(host_out_np)) == 0
+        host_np, host_out_np = host_out_np, host_np
     barrier()
     e2e_steps = args.steps
     per_step = []
     for _ in range(e2e_steps):
         t0 = time.perf_counter()
-        rc = lib.sfg_set_poses(h, 0, nb, abi.ptr(host_np))     # H2D from pinned memory + unpack, synchronous
-        assert rc == 0
-        g.tick(FRAME_DT, None, ff)
-        rc = lib.sfg_get_poses(h, 0, nb, abi.ptr(host_np))     # pack + D2H into pinned memory, synchronous
+        rc = lib.sfg_tick_poses(h, abi.ptr(host_np), FRAME_DT, 0, 0.0, ffp, abi.ptr(host_out_np))   # H2D from pinned memory, tick, D2H into pinned memory, synchronous
         assert rc == 0
         per_step.append(time.perf_counter() - t0)
+        host_np, host_out_np = host_out_np, host_np      # the poses read back are the ones written in next step
     barrier()
     # every call above returns only after its stream has drained, so the wall clock of one step is its end-to-end time;
     # the median keeps one host hiccup (a fresh box paging in) from deciding the number, the worst step is reported too

@@ -228,6 +228,12 @@ int sfg_get_contacts(SfgWorld* w, SfgContactInfo* out, size_t capacity, size_t* 
  *      poses: `count` rows of (x, y, rot_s, rot_b); velocities and masses are untouched. ---- */
 int sfg_set_poses(SfgWorld* w, uint32_t first_slot, uint32_t count, const float* poses_xysb);
 int sfg_get_poses(SfgWorld* w, uint32_t first_slot, uint32_t count, float* poses_xysb);
+/* Game::physics_tick in one call (game.rs:297-303): poses of ALL body slots in (NULL = keep the device's), sfg_tick, poses of
+ * all body slots out (NULL = none). Same results as sfg_set_poses + sfg_tick + sfg_get_poses; the upload is queued in front of
+ * the tick instead of being waited for and the download overlaps the end of the tick. Pinned host buffers make both copies
+ * run at PCIe rate. */
+int sfg_tick_poses(SfgWorld* w, const float* poses_in_xysb, double frame_dt, int has_time_scale, double time_scale,
+                   const SfgForceField* forcefield, float* poses_out_xysb);
 int sfg_get_stats(SfgWorld* w, SfgStats* out);
 
 /* ---- PhysicsWorld::raycast / spherecast (physics.rs:1255-1311), batched ---- */

@@ -61,7 +61,7 @@ EXPORTS = [
     "sfg_abi_version", "sfg_world_create", "sfg_world_destroy", "sfg_world_clear", "sfg_last_error", "sfg_set_tuning",
     "sfg_set_mask_matrix", "sfg_default_tuning", "sfg_default_mask_matrix", "sfg_set_bodies", "sfg_update_bodies",
     "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_tick", "sfg_tick_begin", "sfg_tick_substeps", "sfg_tick_end", "sfg_slab_configure", "sfg_island_shard_configure", "sfg_slab_begin", "sfg_slab_pack", "sfg_slab_unpack", "sfg_get_bodies",
-    "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_query_point_batch", "sfg_query_shape_batch", "sfg_debug_get_pairs", "sfg_debug_get_pair_hints",
+    "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_tick_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_query_point_batch", "sfg_query_shape_batch", "sfg_debug_get_pairs", "sfg_debug_get_pair_hints",
     "sfg_debug_get_contact_entries", "sfg_debug_get_constraint_entries", "sfg_debug_get_manifolds", "sfg_debug_get_aabbs", "sfg_debug_get_islands",
     "sfg_debug_intersection_check", "sfg_debug_spherecast_collider", "sfg_debug_geometry",
 ]
@@ -112,6 +112,7 @@ def load():
     lib.sfg_get_contacts.argtypes = [vp, vp, sz, C.POINTER(sz)]
     lib.sfg_set_poses.argtypes = [vp, u32, u32, vp]
     lib.sfg_get_poses.argtypes = [vp, u32, u32, vp]
+    lib.sfg_tick_poses.argtypes = [vp, vp, C.c_double, i32, C.c_double, vp, vp]
     lib.sfg_get_stats.argtypes = [vp, vp]
     lib.sfg_cast_batch.argtypes = [vp, u32, vp, vp]
     lib.sfg_query_point_batch.argtypes = [vp, u32, vp, vp, u32, vp, vp]

@@ -109,7 +109,7 @@ struct SfgWorld {
     DBuf<float4> RPA, RPB;
     DBuf<int> rp_body, rp_rope;
     // staging
-    DBuf<unsigned char> stage;
+    DBuf<unsigned char> stage, stage2;   // stage2: pose read-back on the second stream (sfg_tick_poses)
     DBuf<unsigned long long> d_mask;
     DBuf<TickHeader> hdr;
     // broadphase scratch
@@ -1215,7 +1215,11 @@ int sfg_tick_substeps(SfgWorld* w, uint32_t count) {
     return SFG_OK;
 }
 
-int sfg_tick_end(SfgWorld* w) {
+static int tick_end_impl(SfgWorld* w, float* poses_out);
+int sfg_tick_end(SfgWorld* w) { return tick_end_impl(w, nullptr); }
+// poses_out != nullptr: the poses of all bodies are packed and copied to the host on the second stream while the contact
+// list and the sleeping bookkeeping run on the first (they only read what the solver left behind)
+static int tick_end_impl(SfgWorld* w, float* poses_out) {
     if (!w) return SFG_E_INVALID;
     if (!w->in_tick) return fail(w, SFG_E_STATE, "sfg_tick_end without sfg_tick_begin");
     if (w->tick_next_substep != w->tick_substeps) return fail(w, SFG_E_STATE, "sfg_tick_end before all substeps ran");
@@ -1226,11 +1230,19 @@ int sfg_tick_end(SfgWorld* w) {
     const uint32_t substeps = w->tick_substeps;
     int rc;
     CK(cudaEventRecord(w->ev[3], st));
+    if (poses_out && w->n_bodies) {
+        CK(w->stage2.ensure(size_t(w->n_bodies) * 16));
+        CK(cudaStreamWaitEvent(w->stream2, w->ev[3], 0));
+        k_get_poses<<<nblk(w->n_bodies), 256, 0, w->stream2>>>((float4*)w->stage2.p, w->n_bodies, 0, w->P.p, w->Q.p);
+        CKL(w); w->launches++;
+        CK(cudaMemcpyAsync(poses_out, w->stage2.p, size_t(w->n_bodies) * 16, cudaMemcpyDeviceToHost, w->stream2));
+    }
     if (sleeping) { rc = island_post(w); if (rc != SFG_OK) return rc; }
     uint32_t isl_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (sleeping && w->n_bodies) CK(cudaMemcpyAsync(isl_counts, w->isl_counters.p, sizeof(isl_counts), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(w->ev[4], st));
     CK(cudaStreamSynchronize(st));
+    if (poses_out) CK(cudaStreamSynchronize(w->stream2));
     w->islands_valid = sleeping;
     if (sleeping) w->ct_n = isl_counts[4];
     w->ticked = true;
@@ -1260,6 +1272,26 @@ int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale
     rc = sfg_tick_substeps(w, w->tick_substeps);
     if (rc != SFG_OK) return rc;
     return sfg_tick_end(w);
+}
+
+// Game::physics_tick in one call (game.rs:297-303): poses in (sync_hecs_to_physics), tick, poses out (sync_physics_to_hecs).
+// The upload is queued in front of the tick instead of being waited for, and the download overlaps the end of the tick.
+int sfg_tick_poses(SfgWorld* w, const float* poses_in, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff,
+                   float* poses_out) {
+    if (!w) return SFG_E_INVALID;
+    if (poses_in && w->n_bodies) {
+        cudaSetDevice(w->device);
+        cudaStream_t st = w->stream;
+        CK(w->stage.ensure(size_t(w->n_bodies) * 16));
+        CK(cudaMemcpyAsync(w->stage.p, poses_in, size_t(w->n_bodies) * 16, cudaMemcpyHostToDevice, st));
+        k_set_poses<<<nblk(w->n_bodies), 256, 0, st>>>((const float4*)w->stage.p, w->n_bodies, 0, w->P.p, w->Q.p);
+        CKL(w);
+    }
+    int rc = sfg_tick_begin(w, frame_dt, has_time_scale, time_scale, ff);
+    if (rc != SFG_OK) return rc;
+    rc = sfg_tick_substeps(w, w->tick_substeps);
+    if (rc != SFG_OK) return rc;
+    return tick_end_impl(w, poses_out);
 }
 
 // ---- slab decomposition (north_star "spatial slabs with boundary-body halo exchange")

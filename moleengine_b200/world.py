@@ -132,6 +132,18 @@ class GpuWorld:
         self._ck(self.lib.sfg_get_poses(self.h, first, count, abi.ptr(out)))
         return out
 
+    def tick_poses(self, poses_in=None, frame_dt=1.0 / 60.0, time_scale=None, forcefield=None, out=None):
+        """Game::physics_tick in one call: poses of all bodies in (or None), tick, poses of all bodies out (sfg_tick_poses)."""
+        ff = abi.gravity_field() if forcefield is None else forcefield
+        out = np.zeros((self.n_bodies, 4), np.float32) if out is None else out
+        pin = None
+        if poses_in is not None:
+            pin = np.ascontiguousarray(poses_in, np.float32)
+            assert pin.shape == (self.n_bodies, 4)
+        self._ck(self.lib.sfg_tick_poses(self.h, None if pin is None else abi.ptr(pin), frame_dt, 0 if time_scale is None else 1,
+                                         0.0 if time_scale is None else time_scale, abi.ptr(ff), abi.ptr(out)))
+        return out
+
     def get_contacts(self, capacity=1 << 20):
         out = np.zeros(capacity, abi.contact_dtype)
         n = C.c_size_t()

@@ -341,3 +341,25 @@ def test_near_hint_orders_the_colours():
     assert col[near].mean() < col[~near].mean()
     assert col[near].max() < col.max()                           # the top colours hold far pairs only
     g.close()
+
+
+def test_tick_poses_equals_set_tick_get():
+    """sfg_tick_poses (Game::physics_tick in one call, game.rs:297-303) = sfg_set_poses + sfg_tick + sfg_get_poses, bit for bit,
+    including the pose read-back that runs on the second stream next to the end of the tick."""
+    sc = scenes.parity_mix(300, 3)
+    tun = abi.default_tuning(substeps=4)
+    a, b = GpuWorld(tuning=tun), GpuWorld(tuning=tun)
+    a.load_scene(sc); b.load_scene(sc)
+    poses = a.get_poses()
+    for t in range(6):
+        nudged = poses.copy()
+        nudged[::17, 0] += 0.01 * (t + 1)                 # the game moves some entities between ticks
+        a.set_poses(nudged); a.tick(); want = a.get_poses()
+        got = b.tick_poses(nudged)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), t
+        assert np.array_equal(b.get_bodies().view(np.uint8), a.get_bodies().view(np.uint8))
+        poses = want
+    keep = b.tick_poses(None)                              # no upload: the device's own poses are stepped
+    a.tick()
+    assert np.array_equal(keep.view(np.uint32), a.get_poses().view(np.uint32))
+    a.close(); b.close()
