@@ -1106,8 +1106,8 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
             CK(w->wl_count.ensure(size_t(substeps) * w->n_unit_colours));
             CK(cudaMemsetAsync(w->wl_count.p, 0, size_t(substeps) * w->n_unit_colours * 4, st));
             w->tick_ctx.wl_count = w->wl_count.p;
-            CK(w->far_min.ensure(substeps));
-            CK(cudaMemsetAsync(w->far_min.p, 0xFF, size_t(substeps) * 4, st));
+            CK(w->far_min.ensure(size_t(substeps) * w->h_stages.size()));
+            CK(cudaMemsetAsync(w->far_min.p, 0xFF, size_t(substeps) * w->h_stages.size() * 4, st));
             w->tick_ctx.far_min = w->far_min.p;
         }
         if (!(w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES)) {

@@ -598,10 +598,10 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
                     if (survivor) {                     // rare: which stage is that unit in?
                         uint32_t ks = k;
                         while (ks + 1u < k2 && first >= stages[ks].end) ++ks;
-                        atomicMin(c.far_min + s, ks);
+                        atomicMin(c.far_min + size_t(s) * n_stages + k, ks);   // one word per run: a substep can hold several runs
                     }
                     grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
-                    const uint32_t fm = __ldcg(c.far_min + s);
+                    const uint32_t fm = __ldcg(c.far_min + size_t(s) * n_stages + k);
                     merged_until = k2;
                     if (fm == 0xFFFFFFFFu) { k = k2 - 1u; continue; }       // every unit of the run rejected: all its stages are done
                     k = fm - 1u;                                             // resume at the first survivor's stage

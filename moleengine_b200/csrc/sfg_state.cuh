@@ -98,7 +98,7 @@ struct SolverCtx {
     float2* LN;
     uint32_t* WL;
     uint32_t* wl_count;
-    uint32_t* far_min;            // per substep: first stage of the merged far-only run that had a surviving unit (0xFFFFFFFF = none)
+    uint32_t* far_min;            // [substep * n_stages + first stage of a merged far-only run]: the first stage of that run with a surviving unit (0xFFFFFFFF = none)
     const uint32_t* near_count;   // per contact colour: units sorted first inside the colour because they may touch this tick
     uint32_t n_units, n_colours;
     // constraint units (sorted colour-major)
