@@ -39,6 +39,10 @@ template <class T>
 struct DBuf {
     T* p = nullptr;
     size_t cap = 0;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }              // sfg_world_destroy deletes the world on its own device: nothing a release list forgot can leak
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
         static const bool dbg = getenv("SFG_DEBUG_ALLOC") != nullptr;     // debug: report every (re)allocation and what it cost
@@ -564,7 +568,7 @@ void sfg_world_destroy(SfgWorld* w) {
     DBuf<int4>* i4[] = {&w->CI, &w->KI, &w->RU, &w->RD, &w->SI};
     for (auto* b : i4) b->release();
     w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->far_min.release(); w->body_word.release(); w->trace.release(); w->adj_body.release(); w->adj_rank.release(); w->U_cls.release(); w->adj_colour.release(); w->U_slot.release(); w->U_ub.release(); w->KU_ub.release();
-    w->stage.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
+    w->stage.release(); w->stage2.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
     if (w->ev_join) cudaEventDestroy(w->ev_join);

@@ -39,7 +39,7 @@ def test_reference_scene_one_substep_parity(oracle, path):
     r = parity.compare_tick(g, o, sc, hops=3)
     print(os.path.basename(path), r)
     assert r["flips_ok"] and r["non_tie_mismatches"] == 0 and r["bad_outside_influence"] == 0
-    assert r["manifold_err"] < 1e-5 and r["pos_err_clean"] < 1e-4 and r["vel_err_clean"] < 1e-4
+    assert r["manifolds_ok"] and r["pos_err_clean"] < 1e-4 and r["vel_err_clean"] < 1e-4
     g.close()
 
 

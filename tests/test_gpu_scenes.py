@@ -25,7 +25,7 @@ def _check(r, ties_frac=0.02):
     print(r)
     assert r["flips_ok"] and r["non_tie_mismatches"] == 0
     assert r["ties"] <= ties_frac * max(r["entries"], 50)
-    assert r["manifold_err"] < 1e-5 and r["manifolds_compared"] > 0
+    assert r["manifolds_ok"] and r["manifolds_compared"] > 0
     assert r["bad_outside_influence"] == 0
     assert r["influenced"] < r["bodies"]
 
@@ -287,7 +287,7 @@ def test_far_from_the_origin(oracle, offset):
     r = parity.compare_tick(g, o, sc, tol_state=1e-4, hops=3)
     print(offset, r)
     assert r["flips_ok"] and r["non_tie_mismatches"] == 0 and r["bad_outside_influence"] == 0
-    assert r["manifold_err"] < 1e-5 and r["manifolds_compared"] > 50
+    assert r["manifolds_ok"] and r["manifolds_compared"] > 50
     assert r["vel_err_clean"] < 1e-4
     g.close()
 
