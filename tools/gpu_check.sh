@@ -3,6 +3,7 @@
 # the library) the contact-path latency probe. Usage: gpurun -- 'bash tools/gpu_check.sh [tag]'
 tag=${1:-chk}
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$tag.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 python bench.py --no-cpu-baseline > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"
 python -c "
 import json; d=json.load(open('gpurun_out/bench_$tag.json')); print('$tag', d['ms_per_step'], d['phases_ms'], d['e2e']['ms_per_step'], d['roofline']['frac'])"
