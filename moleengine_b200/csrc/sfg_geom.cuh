@@ -94,13 +94,13 @@ SFG_DI int edge_count(const Shape& s) { return s.kind == K_POINT ? 0 : (s.kind =
 SFG_DI bool symmetrical(const Shape& s) { return s.kind != K_TRIANGLE; }                                                             // :528
 
 // collider.rs:572-665
-SFG_DI PEdge get_edge(const Shape& s, int i) {
+SFG_DI PEdge get_edge(const Shape& s, int i) {      // the kinds are tested most common first (rectangles and their rounded variants)
     PEdge o;
-    if (s.kind == K_SEGMENT) {
-        o.n = mk(0.f, 1.f); o.e.start = mk(s.p0, 0.f); o.e.dir = mk(-1.f, 0.f); o.e.len = 2.f * s.p0;
-    } else if (s.kind == K_RECT) {
+    if (s.kind == K_RECT) {
         if (i == 0) { o.n = mk(1.f, 0.f); o.e.start = mk(s.p0, -s.p1); o.e.dir = mk(0.f, 1.f); o.e.len = 2.f * s.p1; }
         else { o.n = mk(0.f, 1.f); o.e.start = mk(s.p0, s.p1); o.e.dir = mk(-1.f, 0.f); o.e.len = 2.f * s.p0; }
+    } else if (s.kind == K_SEGMENT) {
+        o.n = mk(0.f, 1.f); o.e.start = mk(s.p0, 0.f); o.e.dir = mk(-1.f, 0.f); o.e.len = 2.f * s.p0;
     } else if (s.kind == K_TRIANGLE) {
         const float len = s.p0 / SFG_PI6_TAN;
         if (i == 0) { o.n = mk(0.f, -1.f); o.e.start = (-s.p0) * mk(SFG_PI6_COS, SFG_PI6_SIN); o.e.dir = mk(1.f, 0.f); }
@@ -120,26 +120,22 @@ SFG_DI Edge flipped(Edge e) { Edge o; o.start = e.start + e.len * e.dir; o.dir =
 
 // collider.rs:668-686
 SFG_DI float edge_extent(const Shape& s, int i) {
-    if (s.kind == K_SEGMENT) return 0.f;
     if (s.kind == K_RECT) return i == 0 ? s.p0 : s.p1;
+    if (s.kind == K_SEGMENT) return 0.f;
     if (s.kind == K_TRIANGLE) return s.p0 / 2.f;
     return SFG_PI6_COS * s.p0;
 }
 // collider.rs:692-714
 SFG_DI float projected_extent(const Shape& s, V2 d) {
-    switch (s.kind) {
-    case K_POINT: return 0.f;
-    case K_SEGMENT: return fabsf(d.x) * s.p0;
-    case K_RECT: return fabsf(d.x) * s.p0 + fabsf(d.y) * s.p1;
-    case K_TRIANGLE: {
+    if (s.kind == K_RECT) return fabsf(d.x) * s.p0 + fabsf(d.y) * s.p1;
+    if (s.kind == K_SEGMENT) return fabsf(d.x) * s.p0;
+    if (s.kind == K_POINT) return 0.f;
+    if (s.kind == K_TRIANGLE) {
         float a = d.y, b = -(SFG_PI6_COS * d.x + SFG_PI6_SIN * d.y), c = -(-SFG_PI6_COS * d.x + SFG_PI6_SIN * d.y);
         return fmaxf(a, fmaxf(b, c)) * s.p0;
     }
-    default: {
-        float a = fabsf(d.x), b = fabsf(SFG_PI6_SIN * d.x + SFG_PI6_COS * d.y), c = fabsf(-SFG_PI6_SIN * d.x + SFG_PI6_COS * d.y);
-        return fmaxf(a, fmaxf(b, c)) * s.p0;
-    }
-    }
+    float a = fabsf(d.x), b = fabsf(SFG_PI6_SIN * d.x + SFG_PI6_COS * d.y), c = fabsf(-SFG_PI6_SIN * d.x + SFG_PI6_COS * d.y);
+    return fmaxf(a, fmaxf(b, c)) * s.p0;
 }
 // collider.rs:722-790
 SFG_DI PEdge supporting_edge(const Shape& s, V2 d) {
