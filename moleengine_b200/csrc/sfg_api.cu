@@ -423,13 +423,13 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     CK(w->ckey0.ensure(nr)); CK(w->ckey1.ensure(nr)); CK(w->perm0.ensure(nr)); CK(w->perm1.ensure(nr));
     CK(w->sort_tmp.ensure(sort_tmp_words(nr)));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_dataflow, 1024, 0));
-    const uint32_t grid = std::max(1u, std::min<uint32_t>(uint32_t(per_sm * w->n_sms), nblk(n_units, 1024)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_dataflow, SFG_COLOUR_THREADS, 0));
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(uint32_t(per_sm * w->n_sms), nblk(n_units, SFG_COLOUR_THREADS)));
     // a bucket must span far fewer units than the co-resident threads (progress argument in k_colour_dataflow):
     // 2^bits buckets of ~n / 2^bits units each (priorities are hashes), kept under 1/8 of the resident threads
     int bucket_bits = 8;
     // (the `near` bit splits the priority space in two halves that need not be equally full: allow for buckets twice the mean)
-    while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * 8 > size_t(grid) * 1024) bucket_bits += 8;
+    while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * 8 > size_t(grid) * SFG_COLOUR_THREADS) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
     CK(w->adj_body.ensure(size_t(nr) * 2 + 1)); CK(w->adj_rank.ensure(size_t(nr) + 1));
@@ -461,7 +461,7 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         static const bool dbg_slow = getenv("SFG_DEBUG_SLOW") != nullptr;   // debug: wall time of the colouring kernel alone
         std::chrono::steady_clock::time_point t0;
         if (dbg_slow) { CK(cudaStreamSynchronize(st)); t0 = std::chrono::steady_clock::now(); }
-        CK(cudaLaunchCooperativeKernel((void*)k_colour_dataflow, dim3(grid), dim3(1024), args, 0, st));
+        CK(cudaLaunchCooperativeKernel((void*)k_colour_dataflow, dim3(grid), dim3(SFG_COLOUR_THREADS), args, 0, st));
         w->launches++;
         if (dbg_slow) {
             CK(cudaStreamSynchronize(st));

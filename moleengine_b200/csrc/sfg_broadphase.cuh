@@ -526,7 +526,11 @@ SFG_DI uint32_t colour_scan_warp(uint32_t lane, uint32_t u, int bx, int by, bool
         if (!beyond) return base + 512u;
     }
 }
-__global__ void __launch_bounds__(1024) k_colour_dataflow(uint32_t n_units, const uint32_t* __restrict__ order, const int2* __restrict__ ub,
+#ifndef SFG_COLOUR_THREADS
+#define SFG_COLOUR_THREADS 1024   // one 1024-thread CTA per SM (56 registers). Measured: 512 x 3 (40 registers) and 512 x 4 (32, spilling)
+#define SFG_COLOUR_BLOCKS 1       // resident CTAs per SM are 2-5 % slower on the graph phase of C3, C2 and C5: the pass is not short of warps
+#endif
+__global__ void __launch_bounds__(SFG_COLOUR_THREADS, SFG_COLOUR_BLOCKS) k_colour_dataflow(uint32_t n_units, const uint32_t* __restrict__ order, const int2* __restrict__ ub,
                                                          const uint32_t* __restrict__ prio, const uint2* __restrict__ ids,
                                                          const uint32_t* __restrict__ adj_start, const uint2* __restrict__ adj,
                                                          const int4* __restrict__ urec, const uint2* __restrict__ uslot, uint32_t* adj_colour,
