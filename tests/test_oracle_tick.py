@@ -139,3 +139,50 @@ def test_sleeping_matches_reference_rules(oracle):
     for _ in range(60):
         w2.tick(mode=oracle.MODE_REFERENCE)
     assert w2.stats()["islands"] >= 1
+
+
+def test_near_hint_is_a_priority_not_a_filter(oracle):
+    """include/sfg_hash.h: the `near` bit goes in front of the colouring priority. So (a) the colouring stays a proper colouring
+    of ALL pairs whatever the hints are, (b) near pairs outrank the rest: their colours are exactly the ones they would get if the
+    other pairs did not exist, and (c) without hints every pair counts as near."""
+    sc = scenes.parity_mix(300, 9)
+    w = _world(oracle, sc, 1)
+    w.tick(mode=oracle.MODE_COLOURED)
+    pairs = w.pairs()
+    hi0, lo0, _, col0 = w.pair_units()
+    assert len(pairs) > 300
+    rng = np.random.default_rng(5)
+    hints = (rng.random(len(pairs)) < 0.4).astype(np.uint8)
+    # (c): all-ones hints change nothing
+    w1 = _world(oracle, sc, 1)
+    w1.set_pair_hints(pairs, np.ones(len(pairs), np.uint8))
+    w1.tick(mode=oracle.MODE_COLOURED)
+    hi1, lo1, _, col1 = w1.pair_units()
+    key = lambda h, l: h.astype(np.uint64) << np.uint64(32) | l.astype(np.uint64)   # noqa: E731
+    assert dict(zip(key(hi0, lo0).tolist(), col0.tolist())) == dict(zip(key(hi1, lo1).tolist(), col1.tolist()))
+    # mixed hints
+    w2 = _world(oracle, sc, 1)
+    w2.set_pair_hints(pairs, hints)
+    w2.tick(mode=oracle.MODE_COLOURED)
+    hi2, lo2, _, col2 = w2.pair_units()
+    assert sorted(key(hi2, lo2).tolist()) == sorted(key(hi0, lo0).tolist())          # (a) every pair is still there ...
+    cb = sc["colliders"]["body"]
+    sees = (sc["bodies"]["flags"] & (abi.BODY_MASS_FINITE | abi.BODY_INERTIA_FINITE)) != 0
+    for c in np.unique(col2):                                                         # ... and no colour touches a dynamic body twice
+        sel = col2 == c
+        bs = np.concatenate([cb[hi2[sel]], cb[lo2[sel]]])
+        bs = bs[bs >= 0]
+        bs = bs[sees[bs]]
+        assert len(bs) == len(np.unique(bs))
+    # (b): the near pairs alone, as an external pair list
+    near = dict(zip(key(pairs[:, 0], pairs[:, 1]).tolist(), hints.tolist()))
+    near_pairs = pairs[hints == 1]
+    w3 = _world(oracle, sc, 1)
+    w3.set_external_pairs(near_pairs)
+    w3.tick(mode=oracle.MODE_COLOURED)
+    hi3, lo3, _, col3 = w3.pair_units()
+    alone = dict(zip(key(hi3, lo3).tolist(), col3.tolist()))
+    mixed = dict(zip(key(hi2, lo2).tolist(), col2.tolist()))
+    assert len(alone) > 50
+    for k, c in alone.items():
+        assert near[k] == 1 and mixed[k] == c
