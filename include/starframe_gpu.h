@@ -49,6 +49,7 @@ typedef struct SfgTuning {
 } SfgTuning;
 #define SFG_TUNE_NO_SLEEPING 1u      /* skip island / sleeping bookkeeping entirely */
 #define SFG_TUNE_SEPARATE_LAUNCHES 2u /* debug: one launch per colour instead of the persistent kernel */
+#define SFG_MAX_SUBSTEPS 4096u       /* substeps of one tick (after time scaling) are capped: per-substep tables are sized by it */
 
 /* body.rs:7-13 Body. flags carry the Mass enum discriminants (body.rs:105-129). */
 typedef struct SfgBody {
@@ -205,7 +206,8 @@ int sfg_tick_end(SfgWorld* w);
  * Every rank uploads the WHOLE world (same slots everywhere) and then owns the bodies whose x lies in [x_lo, x_hi); bodies
  * outside the slab and its halo sit the tick out on this rank. Per tick the caller runs
  *   sfg_slab_begin; pack(mode 0, side) -> send to that neighbour / receive -> unpack      (refresh: who is near the cut)
- *   sfg_tick_begin; then per substep: sfg_tick_substeps(1); pack(mode 1) -> exchange -> unpack (not after the last); sfg_tick_end
+ *   sfg_tick_begin; then per substep: sfg_tick_substeps(1); pack(mode 1) -> exchange -> unpack (after EVERY substep: ownership follows position, so both
+ *   copies of a body near a cut must be bitwise equal when the next refresh decides who owns it); sfg_tick_end
  * The buffers are DEVICE memory owned by the caller ((capacity_records + 1) * 64 bytes; record 0 is a header carrying the
  * count), so the transport (NCCL send/recv, peer copies) stays outside the library. side 0 = towards lower x, 1 = higher x.
  * A slab world never sleeps (islands across a cut are not tracked). x_hi <= x_lo switches slab mode off. */

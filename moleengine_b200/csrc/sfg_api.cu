@@ -8,7 +8,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,17 +27,22 @@ namespace {
 // grows past a buffer. The outgrown allocation goes to a graveyard that is emptied when the world is cleared or destroyed;
 // the dead memory is bounded by the geometric growth (less than twice the live size).
 struct Graveyard {
-    std::mutex mu;
     std::vector<void*> dead;
-    void add(void* q) { std::lock_guard<std::mutex> l(mu); dead.push_back(q); }
-    bool empty() { std::lock_guard<std::mutex> l(mu); return dead.empty(); }
-    void bury_all() { std::lock_guard<std::mutex> l(mu); for (void* q : dead) cudaFree(q); dead.clear(); }   // cudaFree synchronises the device first
+    void add(void* q) { dead.push_back(q); }
+    bool empty() const { return dead.empty(); }
+    void bury_all() { for (void* q : dead) cudaFree(q); dead.clear(); }   // cudaFree synchronises the device first
 };
-inline Graveyard& dbuf_graveyard() { static Graveyard g; return g; }
+// The graveyard belongs to the world whose buffers it holds (SfgWorld::graveyard): clearing or destroying one world frees only
+// what that world retired, on its own device — never another world's buffers (a cudaFree is a device-wide synchronisation of
+// 90-270 ms here, exactly the hitch the graveyard exists to avoid; batched worlds and several GPUs in one process would all pay
+// it). A DBuf picks up its world's graveyard when it is constructed as a member of that world (sfg_world_create sets the
+// thread-local pointer around `new SfgWorld`).
+thread_local Graveyard* tl_ctor_yard = nullptr;
 template <class T>
 struct DBuf {
     T* p = nullptr;
     size_t cap = 0;
+    Graveyard* yard = tl_ctor_yard;
     DBuf() = default;
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
@@ -47,13 +51,13 @@ struct DBuf {
         if (n <= cap) return cudaSuccess;
         static const bool dbg = getenv("SFG_DEBUG_ALLOC") != nullptr;     // debug: report every (re)allocation and what it cost
         const auto t0 = std::chrono::steady_clock::now();
-        if (p) dbuf_graveyard().add(p);
+        if (p) { if (yard) yard->add(p); else cudaFree(p); }
         p = nullptr; cap = 0;
         size_t want = n + n / 2 + 64;   // 50 % headroom: pair counts creep up as piles form
         cudaError_t e = cudaMalloc(&p, want * sizeof(T));
-        if (e != cudaSuccess && !dbuf_graveyard().empty()) {     // out of memory: now the graveyard has to go
+        if (e != cudaSuccess && yard && !yard->empty()) {     // out of memory: now the graveyard has to go
             cudaGetLastError();
-            dbuf_graveyard().bury_all();
+            yard->bury_all();
             e = cudaMalloc(&p, want * sizeof(T));
         }
         if (e == cudaSuccess) cap = want;
@@ -80,6 +84,7 @@ struct TickHeader {            // small device block read back once per tick pha
 }  // namespace
 
 struct SfgWorld {
+    Graveyard* graveyard = nullptr;          // this world's outgrown device buffers (freed by sfg_world_clear / sfg_world_destroy)
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;          // the island pass runs here, next to the colouring (both only read the pair list)
@@ -161,6 +166,7 @@ struct SfgWorld {
     DBuf<ContactRec> ct[2];       // contact list of the last tick (with retention for sleeping islands), double-buffered
     uint32_t ct_n = 0, ct_cur = 0;
     bool islands_valid = false;   // the last tick ran the island pass
+    bool island_flags_live = false;   // BF_ASLEEP / BF_FOREIGN may be set on bodies (an island pass ran since they were last cleared)
     // tick in flight (sfg_tick_begin .. sfg_tick_end)
     bool in_tick = false, tick_sleeping = false;
     uint32_t tick_substeps = 0, tick_next_substep = 0;
@@ -398,6 +404,16 @@ __global__ void k_find_nonfinite(uint32_t nb, const float4* P, const float4* Q, 
     if (!isfinite(s)) atomicMin(first, b);
 }
 
+// The per-tick island flags on the bodies (asleep / solved by another rank) are rewritten by k_isl_init whenever the island pass
+// runs. A tick that skips the pass (sleeping switched off, a slab world, island sharding switched off) must not inherit them:
+// a body left "asleep" would never be integrated or solved again, and nothing could wake it.
+__global__ void k_clear_island_flags(uint32_t nb, float4* MI) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    const uint32_t fl = __float_as_uint(MI[b].z);
+    if (fl & (BF_ASLEEP | BF_FOREIGN)) MI[b].z = __uint_as_float(fl & ~(BF_ASLEEP | BF_FOREIGN));
+}
+
 int ensure_device(int device) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SFG_E_NO_DEVICE;
@@ -528,19 +544,24 @@ void sfg_default_mask_matrix(uint64_t out[64]) {   // collision.rs:132-140
 int sfg_world_create(const SfgTuning* tuning, const uint64_t mask_matrix[64], int device, SfgWorld** out) {
     if (!out) return SFG_E_INVALID;
     *out = nullptr;
+    if (tuning && tuning->substeps == 0) return SFG_E_INVALID;      // same rule as sfg_set_tuning: dt = frame_dt / substeps
     int rc = ensure_device(device);
     if (rc != SFG_OK) return rc;
+    Graveyard* yard = new Graveyard();
+    tl_ctor_yard = yard;                     // every DBuf member of the new world retires its outgrown allocations here
     SfgWorld* w = new SfgWorld();
+    tl_ctor_yard = nullptr;
+    w->graveyard = yard;
     w->device = device;
     if (tuning) w->tuning = *tuning; else sfg_default_tuning(&w->tuning);
     if (mask_matrix) memcpy(w->mask, mask_matrix, sizeof(w->mask)); else sfg_default_mask_matrix(w->mask);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) w->n_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; return SFG_E_CUDA; }
-    if (cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(w->stream); delete w; return SFG_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking) != cudaSuccess) { delete w; delete yard; return SFG_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(w->stream); delete w; delete yard; return SFG_E_CUDA; }
     cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming);
     for (auto& e : w->ev) cudaEventCreate(&e);
-    if (w->d_mask.ensure(64) != cudaSuccess || w->hdr.ensure(1) != cudaSuccess) { delete w; return SFG_E_CUDA; }
+    if (w->d_mask.ensure(64) != cudaSuccess || w->hdr.ensure(1) != cudaSuccess) { delete w; delete yard; return SFG_E_CUDA; }
     cudaMemcpyAsync(w->d_mask.p, w->mask, sizeof(w->mask), cudaMemcpyHostToDevice, w->stream);
     cudaStreamSynchronize(w->stream);
     *out = w;
@@ -552,7 +573,7 @@ void sfg_world_destroy(SfgWorld* w) {
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
     if (w->stream2) cudaStreamSynchronize(w->stream2);
-    dbuf_graveyard().bury_all();
+    w->graveyard->bury_all();
     DBuf<float4>* f4[] = {&w->P, &w->Q, &w->V, &w->OV, &w->MI, &w->CS, &w->CL, &w->CM, &w->AABB, &w->KA, &w->KB, &w->RPA, &w->RPB, &w->SA,
                           &w->H, &w->S, &w->G0, &w->G1, &w->L0, &w->L1, &w->M0, &w->M1, &w->M2, &w->K0, &w->K1, &w->K2};
     for (auto* b : f4) b->release();
@@ -574,14 +595,17 @@ void sfg_world_destroy(SfgWorld* w) {
     if (w->ev_join) cudaEventDestroy(w->ev_join);
     if (w->stream2) cudaStreamDestroy(w->stream2);
     if (w->stream) cudaStreamDestroy(w->stream);
+    Graveyard* yard = w->graveyard;
     delete w;
+    delete yard;
 }
 
 int sfg_world_clear(SfgWorld* w) {   // physics.rs:386-393
     if (!w) return SFG_E_INVALID;
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
-    dbuf_graveyard().bury_all();         // outgrown buffers of the run that ends here
+    if (w->stream2) cudaStreamSynchronize(w->stream2);
+    w->graveyard->bury_all();            // outgrown buffers of the run that ends here (this world's only)
     w->n_bodies = w->n_colls = w->n_constraints = w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0;
     w->n_units = w->n_kunits = 0;
     w->ct_n = 0; w->islands_valid = false;
@@ -594,6 +618,7 @@ const char* sfg_last_error(const SfgWorld* w) { return w ? w->err.c_str() : "nul
 int sfg_set_tuning(SfgWorld* w, const SfgTuning* t) {
     if (!w || !t) return SFG_E_INVALID;
     if (t->substeps == 0) return fail(w, SFG_E_INVALID, "substeps must be > 0");
+    if (t->substeps > SFG_MAX_SUBSTEPS) return fail(w, SFG_E_INVALID, "substeps exceed SFG_MAX_SUBSTEPS");
     w->tuning = *t;
     return SFG_OK;
 }
@@ -621,6 +646,7 @@ int sfg_set_bodies(SfgWorld* w, uint32_t n, const SfgBody* b) {
     cudaSetDevice(w->device);
     CK(w->P.ensure(n)); CK(w->Q.ensure(n)); CK(w->V.ensure(n)); CK(w->OV.ensure(n)); CK(w->MI.ensure(n)); CK(w->EA.ensure(n));
     if (n != w->n_bodies) { w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0; w->n_constraints = 0; }   // slot space changed: re-upload ropes / constraints
+    if (n < w->n_bodies) { w->n_colls = 0; w->ticked = false; }   // colliders already uploaded may point at slots that no longer exist: they have to be re-uploaded too
     // a new slot space starts a new world as far as sleeping is concerned: no island is being watched, no contact retained.
     // (Re-uploading the same slots every tick, as the PhysicsWorld mirror does, keeps the records: physics.rs:711-741 only
     // looks at velocities and at the island's identity.)
@@ -1071,9 +1097,14 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     double dt;
     if (!has_time_scale) { substeps = w->tuning.substeps; dt = frame_dt / double(substeps); }
     else {
-        substeps = uint32_t(std::ceil(time_scale * double(w->tuning.substeps)));
-        dt = time_scale * frame_dt / double(substeps);
+        // physics.rs:411-415: `(time_scale * substeps).ceil() as usize` — Rust's float-to-int cast saturates: negative and NaN
+        // give 0 substeps (the tick then only runs the broadphase and the bookkeeping), it never wraps
+        const double want = std::ceil(time_scale * double(w->tuning.substeps));
+        if (!(want >= 1.0)) { substeps = 0; dt = 0.0; }
+        else if (want > double(SFG_MAX_SUBSTEPS)) return fail(w, SFG_E_INVALID, "time_scale * substeps exceeds SFG_MAX_SUBSTEPS");
+        else { substeps = uint32_t(want); dt = time_scale * frame_dt / double(substeps); }
     }
+    if (substeps > SFG_MAX_SUBSTEPS) return fail(w, SFG_E_INVALID, "substeps exceed SFG_MAX_SUBSTEPS");
     w->launches = 0;
     w->islands_in_flight = false;
     w->frame_dt = float(frame_dt);
@@ -1092,13 +1123,21 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     if (w->tick_sleeping) {
         CK(cudaEventRecord(w->ev_fork, st));
         CK(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));
+        w->island_flags_live = true;
         rc = island_pass(w, w->stream2);
-        if (rc != SFG_OK) return rc;
+        if (rc != SFG_OK) { cudaStreamSynchronize(w->stream2); return rc; }
         CK(cudaEventRecord(w->ev_join, w->stream2));
         w->islands_in_flight = true;
+    } else if (w->island_flags_live && w->n_bodies) {
+        // the island pass is off this tick: nobody stays asleep (or foreign) from a tick that ran it, and no island is being watched
+        k_clear_island_flags<<<nblk(w->n_bodies), 256, 0, st>>>(w->n_bodies, w->MI.p);
+        CKL(w); w->launches++;
+        if (w->sl_valid.p) CK(cudaMemsetAsync(w->sl_valid.p, 0, size_t(w->n_bodies + 1) * 4, st));
+        w->island_flags_live = false;
+        w->ct_n = 0;
     }
     rc = build_graph(w);
-    if (rc != SFG_OK) return rc;
+    if (rc != SFG_OK) { if (w->islands_in_flight) { cudaStreamSynchronize(w->stream2); w->islands_in_flight = false; } return rc; }
     rc = join_islands(w);
     if (rc != SFG_OK) return rc;
     CK(cudaEventRecord(w->ev[2], st));

@@ -6,7 +6,11 @@ ghost too (so that pairs across the cut see both bodies move inside a substep) a
 state after every substep. The only data that crosses ranks are 64-byte body records between x-neighbours:
 
     per tick:  refresh (who is near the cut, by position)          1 exchange
-               after every substep but the last (owner -> ghost)    substeps - 1 exchanges
+               after every substep, the last included (owner -> ghost)   substeps exchanges
+
+The exchange after the LAST substep is what keeps ownership well defined: the next tick's refresh decides by position, each
+rank from its own copy, so the owner's and the ghost's copy of a body near a cut must be bitwise equal at that moment
+(otherwise a body whose two copies ended on different sides of the cut would be sent by nobody, or by both).
 
 The C library packs / unpacks device buffers (sfg_slab_pack / sfg_slab_unpack); this module owns the buffers (torch
 tensors) and the transport: torch.distributed point-to-point ops (NCCL over NVLink on GPUs, gloo in the CPU tests) or
@@ -110,7 +114,7 @@ class SlabDriver:
         self.exchanges += 1
 
     def tick(self, frame_dt=1.0 / 60.0, forcefield=None):
-        """One frame: refresh the halo, then `substeps` substeps with an owner -> ghost exchange between them."""
+        """One frame: refresh the halo, then `substeps` substeps with an owner -> ghost exchange after each of them."""
         self.sent_records, self.exchanges = 0, 0
         w = self.world
         w.slab_begin()
@@ -118,8 +122,7 @@ class SlabDriver:
         w.tick_begin(frame_dt, None, forcefield)
         for s in range(self.substeps):
             w.tick_substeps(1)
-            if s + 1 < self.substeps:
-                self._exchange(1)
+            self._exchange(1)
         w.tick_end()
 
 
@@ -140,8 +143,7 @@ def tick_local(drivers, transport, frame_dt=1.0 / 60.0, forcefield=None):
     for s in range(drivers[0].substeps):
         for d in drivers:
             d.world.tick_substeps(1)
-        if s + 1 < drivers[0].substeps:
-            exchange(1)
+        exchange(1)
     for d in drivers:
         d.world.tick_end()
 

@@ -141,3 +141,34 @@ def test_no_sleeping_flag_skips_the_pass(oracle):
     assert len(fb) == 0
     assert len(g.get_contacts()) > 0
     g.close()
+
+
+def test_switching_sleeping_off_wakes_everything():
+    """A stack that fell asleep must not stay frozen when the island pass is switched off (the pass is the only thing that
+    rewrites the per-tick asleep flag): with sleeping off every body is integrated again, and a body pushed through the pose-only
+    path moves its neighbours."""
+    sc = scenes.c1_sandbox_stack()
+    g = GpuWorld(tuning=abi.default_tuning(substeps=10))
+    g.load_scene(sc)
+    nb = len(sc["bodies"])
+    for t in range(400):
+        g.tick()
+        gb = g.get_bodies()
+        asleep = (gb["flags"] & abi.BODY_ASLEEP) != 0
+        if asleep.sum() > 0.5 * nb:
+            break
+    assert asleep.sum() > 0.5 * nb, "the stack did not fall asleep"
+    g.set_tuning(abi.default_tuning(substeps=10, flags=abi.TUNE_NO_SLEEPING))
+    # lift one sleeping box through the pose-only path (no flags are re-uploaded there)
+    victim = int(np.flatnonzero(asleep)[0])
+    poses = g.get_poses()
+    poses[victim, 1] += 0.5
+    g.set_poses(poses[victim:victim + 1], first=victim)
+    y0 = float(poses[victim, 1])
+    for _ in range(5):
+        g.tick()
+    gb2 = g.get_bodies()
+    assert not ((gb2["flags"] & abi.BODY_ASLEEP) != 0).any(), "a body stayed asleep although the island pass is off"
+    assert float(gb2["y"][victim]) < y0 - 1e-3, "the lifted box did not fall: it was never integrated"
+    assert (gb2["vy"] != 0).sum() > 0.9 * nb, "bodies of the former sleeping island are not integrated"
+    g.close()

@@ -105,14 +105,14 @@ def test_two_ranks_gloo_exchange_and_call_order():
     _, calls1, got1, sent1, ex1, b1 = res[1]
     assert b0 == (-math.inf, 0.0) and b1 == (0.0, math.inf)
     want_order = ["begin", ("pack", 0, 1), "unpack", "tick_begin", ("substeps", 1), ("pack", 1, 1), "unpack", ("substeps", 1), ("pack", 1, 1), "unpack",
-                  ("substeps", 1), "tick_end"]
+                  ("substeps", 1), ("pack", 1, 1), "unpack", "tick_end"]
     assert calls0[1:] == want_order
     assert calls1[1:] == [c if not (isinstance(c, tuple) and c[0] == "pack") else ("pack", c[1], 0) for c in want_order]
-    assert ex0 == ex1 == 3                      # refresh + (substeps - 1)
-    # what rank 0 received is what rank 1 packed for its side 0 (count 3 + 1 + 0 = 4), refresh then two syncs; and vice versa
-    assert got0 == [[1000.0 + 10.0 * m + i for i in range(4)] for m in (0, 1, 1)]
-    assert got1 == [[100.0 + 10.0 * m + i for i in range(4)] for m in (0, 1, 1)]
-    assert sent0 == 3 * 4 and sent1 == 3 * 4
+    assert ex0 == ex1 == 4                      # refresh + one per substep (the last included: ownership is decided from equal copies)
+    # what rank 0 received is what rank 1 packed for its side 0 (count 3 + 1 + 0 = 4), refresh then one sync per substep; and vice versa
+    assert got0 == [[1000.0 + 10.0 * m + i for i in range(4)] for m in (0, 1, 1, 1)]
+    assert got1 == [[100.0 + 10.0 * m + i for i in range(4)] for m in (0, 1, 1, 1)]
+    assert sent0 == 4 * 4 and sent1 == 4 * 4
 
 
 def _shard_worker(rank, world_size, port, out):
