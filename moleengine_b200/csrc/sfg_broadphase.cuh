@@ -316,14 +316,18 @@ __global__ void __launch_bounds__(256) k_pairs(const __grid_constant__ GridParam
 
 // ---------------------------------------------------------------- graph colouring
 // unit = one candidate pair (or one user constraint); ub = its dynamic bodies (or -1); prio = sfg_hash3
+// world position of a collider's origin at tick start, in the exactly rounded arithmetic of include/sfg_hash.h
 SFG_DI V2 collider_centre(int4 ci, float4 l, const float4* __restrict__ P, const float4* __restrict__ Q) {
     if (ci.x < 0) return mk(l.x, l.y);
     const float4 p = P[ci.x], q = Q[ci.x];
-    return mkrot(q.x, q.y) * mk(l.x, l.y) + mk(p.x + p.z, p.y + p.w);
+    V2 c;
+    sfg_collider_centre(__fadd_rn(p.x, p.z), __fadd_rn(p.y, p.w), q.x, q.y, l.x, l.y, &c.x, &c.y);
+    return c;
 }
 // per candidate pair: the bodies it couples (only bodies that see forces count for conflicts), its colouring priority
 // (include/sfg_hash.h) and the degree of its bodies. The priority's top bit is the `near` hint: the colliders' bounding
-// circles are closer than the bodies can come in one frame at their current relative speed (a hint, not a proof).
+// circles are closer than the bodies can come in one frame at their current relative speed (a hint, not a proof). Its
+// definition — sfg_near_hint, exactly rounded f32 — is shared with the CPU oracle, which computes it on its own.
 __global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const uint2* __restrict__ ids, const int4* __restrict__ CI,
                                                          const float4* __restrict__ MI, const float4* __restrict__ CS,
                                                          const float4* __restrict__ CL, const float4* __restrict__ P,
@@ -339,8 +343,9 @@ __global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const
     if (b0 >= 0) { const float4 v = V[b0]; v0 = mk(v.x, v.y); }
     if (b1 >= 0) { const float4 v = V[b1]; v1 = mk(v.x, v.y); }
     const V2 t0 = collider_centre(c0, CL[id.x], P, Q), t1 = collider_centre(c1, CL[id.y], P, Q);
-    const float gap = mag(t1 - t0) - (bound_radius(mkshape(CS[id.x])) + bound_radius(mkshape(CS[id.y])));
-    const bool near_hint = !(gap > 0.02f + 1.5f * frame_dt * mag(v1 - v0));
+    const Shape s0 = mkshape(CS[id.x]), s1 = mkshape(CS[id.y]);
+    const bool near_hint = sfg_near_hint(t0.x, t0.y, sfg_bound_radius(s0.kind, s0.p0, s0.p1, s0.r), t1.x, t1.y, sfg_bound_radius(s1.kind, s1.p0, s1.p1, s1.r),
+                                         v0.x, v0.y, v1.x, v1.y, frame_dt) != 0u;
     if (b0 >= 0 && !(__float_as_uint(MI[b0].z) & (BF_MASS | BF_INERTIA))) b0 = -1;
     if (b1 >= 0 && !(__float_as_uint(MI[b1].z) & (BF_MASS | BF_INERTIA))) b1 = -1;
     ub[u] = make_int2(b0, b1);

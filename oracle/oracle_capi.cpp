@@ -28,6 +28,8 @@ size_t sfo_n_pairs(void* w) { return static_cast<IWorld*>(w)->n_pairs(); }
 void sfo_get_pairs(void* w, uint32_t* out) { static_cast<IWorld*>(w)->get_pairs(out); }
 size_t sfo_n_pair_units(void* w) { return static_cast<IWorld*>(w)->n_pair_units(); }
 void sfo_get_pair_units(void* w, uint32_t* hi, uint32_t* lo, uint32_t* mult, uint32_t* colour) { static_cast<IWorld*>(w)->get_pair_units(hi, lo, mult, colour); }
+// the `near` bit of each pair unit's priority as the oracle computed it (include/sfg_hash.h), in the order of sfo_get_pair_units
+void sfo_get_pair_unit_hints(void* w, uint8_t* near_hint) { static_cast<IWorld*>(w)->get_pair_unit_hints(near_hint); }
 size_t sfo_n_constraint_units(void* w) { return static_cast<IWorld*>(w)->n_constraint_units(); }
 void sfo_get_constraint_units(void* w, uint32_t* idx, uint32_t* mult, uint32_t* colour) { static_cast<IWorld*>(w)->get_constraint_units(idx, mult, colour); }
 size_t sfo_n_entries(void* w) { return static_cast<IWorld*>(w)->n_entries(); }

@@ -41,7 +41,7 @@ def load():
             "sfo_set_external_pair_hints": [vp, vp, vp, C.c_size_t],
             "sfo_tick": [vp, C.c_double, C.c_int, C.c_double, vp, C.c_int, C.c_int],
             "sfo_get_bodies": [vp, C.c_uint32, C.c_uint32, vp], "sfo_n_pairs": [vp], "sfo_get_pairs": [vp, vp],
-            "sfo_n_pair_units": [vp], "sfo_get_pair_units": [vp, vp, vp, vp, vp], "sfo_n_constraint_units": [vp],
+            "sfo_n_pair_units": [vp], "sfo_get_pair_units": [vp, vp, vp, vp, vp], "sfo_get_pair_unit_hints": [vp, vp], "sfo_n_constraint_units": [vp],
             "sfo_get_constraint_units": [vp, vp, vp, vp], "sfo_n_entries": [vp], "sfo_get_manifolds": [vp, vp],
             "sfo_n_contacts": [vp], "sfo_get_contacts": [vp, vp, vp], "sfo_get_aabbs": [vp, vp],
             "sfo_cast_batch": [vp, C.c_uint32, vp, vp, C.c_int],
@@ -97,15 +97,15 @@ class OracleWorld:
         self.n_bodies = len(b)
 
     def set_external_pairs(self, pairs, hints=None):
-        """Candidate pairs of the device's broadphase and, for MODE_COLOURED, the `near` bit the device put in front of each
-        pair's colouring priority (GpuWorld.debug_pair_hints; include/sfg_hash.h). Without hints every pair counts as near."""
+        """Candidate pairs of the device's broadphase. The `near` bit in front of each pair's colouring priority (include/sfg_hash.h)
+        is computed by the oracle itself from its tick-start state; `hints` overrides it (tests of the priority rule only)."""
         p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
         self.lib.sfo_set_external_pairs(self.h, _p(p), len(p))
         if hints is not None:
             self.set_pair_hints(p, hints)
 
     def set_pair_hints(self, pairs, hints):
-        """Only the `near` bits, keyed by pair: the oracle keeps finding the pairs with its own BVH."""
+        """Override the `near` bits the oracle would compute, keyed by pair (tests of the priority rule)."""
         p = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
         h = np.ascontiguousarray(hints, np.uint8)
         assert len(h) == len(p)
@@ -136,6 +136,15 @@ class OracleWorld:
         if n:
             self.lib.sfo_get_pair_units(self.h, *[_p(x) for x in a])
         return a  # hi, lo, mult, colour
+
+    def pair_unit_hints(self):
+        """The `near` bit the oracle computed for each pair unit of the last MODE_COLOURED tick, as {(hi, lo): bit}."""
+        n = self.lib.sfo_n_pair_units(self.h)
+        h = np.zeros(n, np.uint8)
+        if n:
+            self.lib.sfo_get_pair_unit_hints(self.h, _p(h))
+        hi, lo, _, _ = self.pair_units()
+        return dict(zip(zip(hi.tolist(), lo.tolist()), h.tolist()))
 
     def constraint_units(self):
         n = self.lib.sfo_n_constraint_units(self.h)

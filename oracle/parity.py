@@ -72,6 +72,11 @@ def _manifold_diff(gmr, omr, cnt_o):
 
 def compare_tick(g, o, scene, tol_manifold=1e-5, tol_state=1e-4, hops=3, flip_threshold=1e-3):
     """g: GpuWorld after a tick, o: OracleWorld after the replayed tick. Returns a dict of measured errors."""
+    # the order the oracle replayed is the device's only if both computed the same `near` bits (include/sfg_hash.h): checked, not fed
+    gh = dict(zip(map(tuple, g.debug_pairs().tolist()), g.debug_pair_hints().tolist()))
+    oh = o.pair_unit_hints()
+    hint_mismatches = sum(1 for k, v in oh.items() if gh.get(k) != v) + abs(len(gh) - len(oh))
+    assert hint_mismatches == 0, f"{hint_mismatches} `near` hints differ between the device and the oracle"
     gmr, omr, uh, ul, visit = match_manifolds(g, o)
     cnt_g, cnt_o = gmr[:, 2].astype(int), omr[:, 2].astype(int)
     mism = cnt_g != cnt_o

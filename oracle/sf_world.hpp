@@ -96,6 +96,7 @@ struct IWorld {
     virtual void get_pairs(uint32_t* out) const = 0;
     virtual size_t n_pair_units() const = 0;
     virtual void get_pair_units(uint32_t* hi, uint32_t* lo, uint32_t* mult, uint32_t* colour) const = 0;
+    virtual void get_pair_unit_hints(uint8_t* near_hint) const = 0;
     virtual size_t n_constraint_units() const = 0;
     virtual void get_constraint_units(uint32_t* idx, uint32_t* mult, uint32_t* colour) const = 0;
     virtual size_t n_entries() const = 0;
@@ -355,6 +356,7 @@ public:
         stat_substeps = substeps;
         dt = R(dtd); inv_dt = R(1.0 / dtd); inv_dt_sq = R((1.0 / dtd) * (1.0 / dtd));
         const R frame_dt = R(frame_dt_d);
+        frame_dt_f32_ = float(frame_dt_d);
 
         compute_aabbs(frame_dt);
         if (use_ext_pairs_) pair_keys = ext_pairs_;
@@ -596,13 +598,33 @@ public:
         return n_colours;
     }
     int32_t dyn_body(int32_t b) const { return (b >= 0 && bodies[size_t(b)].sees_forces()) ? b : -1; }
+    // include/sfg_hash.h: f32 on purpose, whatever R is (the state a tick starts from is the f32 upload or an f32 read-back)
+    uint32_t compute_near_hint(uint32_t hi, uint32_t lo) const {
+        float c[2][2], r[2], v[2][2];
+        const uint32_t ids[2] = {hi, lo};
+        for (int k = 0; k < 2; ++k) {
+            const ColliderS<R>& co = colliders[ids[k]];
+            r[k] = sfg_bound_radius(co.shape.kind, float(co.shape.p0), float(co.shape.p1), float(co.shape.circle_r));
+            v[k][0] = v[k][1] = 0.0f;
+            if (co.body < 0) { c[k][0] = float(co.pose.t.x); c[k][1] = float(co.pose.t.y); }
+            else {
+                const BodyS<R>& b = bodies[size_t(co.body)];
+                sfg_collider_centre(float(b.pose.t.x), float(b.pose.t.y), float(b.pose.r.s), float(b.pose.r.b), float(co.pose.t.x), float(co.pose.t.y),
+                                    &c[k][0], &c[k][1]);
+                v[k][0] = float(b.lin.x); v[k][1] = float(b.lin.y);
+            }
+        }
+        return sfg_near_hint(c[0][0], c[0][1], r[0], c[1][0], c[1][1], r[1], v[0][0], v[0][1], v[1][0], v[1][1], float(frame_dt_f32_));
+    }
 
     void tick_coloured(const SfgForceField& ff, size_t substeps) {
         // units
         pair_units.clear();
         for (size_t p = 0; p + 1 < kept_pairs.size(); p += 2) {
             uint32_t hi = kept_pairs[p], lo = kept_pairs[p + 1];
-            uint32_t near_hint = 1u;
+            // the `near` bit of the priority: computed here from the tick-start state with the shared exactly-rounded f32
+            // definition (include/sfg_hash.h sfg_near_hint); hints set from outside (tests of the priority rule) override it
+            uint32_t near_hint = compute_near_hint(hi, lo);
             if (!ext_hints_.empty()) { auto it = ext_hints_.find((uint64_t(hi) << 32) | lo); if (it != ext_hints_.end()) near_hint = it->second ? 1u : 0u; }
             pair_units.push_back({hi, lo, (cbody(hi) >= 0 && cbody(lo) >= 0) ? 2u : 1u, 0, near_hint});
         }
@@ -1077,6 +1099,7 @@ public:
     void get_pair_units(uint32_t* hi, uint32_t* lo, uint32_t* mult, uint32_t* colour) const override {
         for (size_t i = 0; i < pair_units.size(); ++i) { hi[i] = pair_units[i].hi; lo[i] = pair_units[i].lo; mult[i] = pair_units[i].mult; colour[i] = pair_units[i].colour; }
     }
+    void get_pair_unit_hints(uint8_t* near_hint) const override { for (size_t i = 0; i < pair_units.size(); ++i) near_hint[i] = uint8_t(pair_units[i].near_hint); }
     size_t n_constraint_units() const override { return constraint_units.size(); }
     void get_constraint_units(uint32_t* idx, uint32_t* mult, uint32_t* colour) const override {
         for (size_t i = 0; i < constraint_units.size(); ++i) { idx[i] = constraint_units[i].idx; mult[i] = constraint_units[i].mult; colour[i] = constraint_units[i].colour; }
@@ -1123,6 +1146,7 @@ private:
     std::vector<uint32_t> ext_pairs_;
     bool use_ext_pairs_ = false;
     std::unordered_map<uint64_t, uint8_t> ext_hints_;
+    float frame_dt_f32_ = 1.0f / 60.0f;
 };
 
 }  // namespace sfo

@@ -26,8 +26,7 @@ def test_pairs_and_colours_bit_exact(oracle, scene_fn):
     g.tick()
     o32 = oracle.OracleWorld(use_f32=True, tuning=tun)
     o32.load_scene(sc)
-    o32.set_pair_hints(g.debug_pairs(), g.debug_pair_hints())   # the `near` bit of the priorities (include/sfg_hash.h); pairs come from the oracle's own BVH
-    o32.tick(mode=oracle.MODE_COLOURED)
+    o32.tick(mode=oracle.MODE_COLOURED)     # pairs from the oracle's own BVH, `near` bits from its own evaluation of include/sfg_hash.h
     # AABBs bit-exact against the f32 oracle
     ga = g.debug_aabbs(len(sc["colliders"]))
     oa = o32.aabbs().astype(np.float32)
@@ -36,6 +35,11 @@ def test_pairs_and_colours_bit_exact(oracle, scene_fn):
     # candidate pair set bit-exact
     gp, op = _pairset(g.debug_pairs()), _pairset(o32.pairs())
     assert len(gp) > 0 and np.array_equal(gp, op)
+    # the `near` bit of every pair's priority: computed independently on both sides from the same f32 tick-start state
+    gh = dict(zip(map(tuple, g.debug_pairs().tolist()), g.debug_pair_hints().tolist()))
+    oh = o32.pair_unit_hints()
+    assert gh == oh
+    assert 0 < sum(gh.values()), "no near pair at all: the hint is not exercised"
     # colouring bit-exact
     hi, lo, mult, col = g.debug_contact_units()
     ohi, olo, omult, ocol = o32.pair_units()
@@ -58,7 +62,7 @@ def test_tick_matches_oracle_replay(oracle, substeps, separate):
     g.tick()
     o = oracle.OracleWorld(tuning=tun)
     o.load_scene(sc)
-    o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+    o.set_external_pairs(g.debug_pairs())
     o.tick(mode=oracle.MODE_COLOURED)
     tol = 1e-4 if substeps == 1 else 1e-3
     r = parity.compare_tick(g, o, sc, tol_state=tol, hops=3 if substeps == 1 else 8)

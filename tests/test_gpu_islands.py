@@ -34,7 +34,7 @@ def test_island_ids_bit_exact(oracle, scene_fn):
         gb = g.get_bodies()
         gb["flags"] &= 15
         o.set_bodies(gb)                       # same state in, so the graph is the only thing compared
-        o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+        o.set_external_pairs(g.debug_pairs())
         o.tick(mode=oracle.MODE_REFERENCE)
         got = _island_table(*g.debug_islands(), mask=1)
         want = _island_table(*o.islands(), mask=1)

@@ -34,7 +34,7 @@ def test_reference_scene_one_substep_parity(oracle, path):
             gb = g.get_bodies(); gb["flags"] &= 15
             o.set_bodies(gb)
         g.tick(forcefield=ff)
-        o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+        o.set_external_pairs(g.debug_pairs())
         o.tick(mode=oracle.MODE_COLOURED, forcefield=ff)
     r = parity.compare_tick(g, o, sc, hops=3)
     print(os.path.basename(path), r)

@@ -16,7 +16,7 @@ def _replay(oracle, sc, substeps=1, ff=None, f32=False):
     g.tick(forcefield=ff)
     o = oracle.OracleWorld(tuning=tun, use_f32=f32)
     o.load_scene(sc)
-    o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+    o.set_external_pairs(g.debug_pairs())
     o.tick(mode=oracle.MODE_COLOURED, forcefield=ff)
     return g, o
 
@@ -79,7 +79,7 @@ def test_c5_worlds_and_casts(oracle):
     sc_after["bodies"] = g.get_bodies()
     # oracle needs the same tick-time boxes: tick it from the same start, then give it the GPU's post-tick bodies
     o32.load_scene(sc)
-    o32.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+    o32.set_external_pairs(g.debug_pairs())
     o32.tick(mode=oracle.MODE_COLOURED)
     o32.set_bodies(sc_after["bodies"])
     want = o32.cast_batch(rays, use_bvh=False)
@@ -167,7 +167,7 @@ def test_point_gravity_and_time_scale(oracle):
     assert g.stats()["substeps"] == 2
     o = oracle.OracleWorld(tuning=tun)
     o.load_scene(sc)
-    o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+    o.set_external_pairs(g.debug_pairs())
     o.tick(1.0 / 60.0, 0.5, ff, mode=oracle.MODE_COLOURED)
     r = parity.compare_tick(g, o, sc, tol_state=5e-4, hops=6)
     print(r)
@@ -282,7 +282,7 @@ def test_far_from_the_origin(oracle, offset):
     g.tick()
     o = oracle.OracleWorld(tuning=tun)
     o.load_scene(sc)
-    o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+    o.set_external_pairs(g.debug_pairs())
     o.tick(mode=oracle.MODE_COLOURED)
     r = parity.compare_tick(g, o, sc, tol_state=1e-4, hops=3)
     print(offset, r)
@@ -309,7 +309,7 @@ def test_restitution_added_by_a_partial_update(oracle):
     g.tick()
     o = oracle.OracleWorld(tuning=tun)
     o.load_scene(sc)
-    o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints())
+    o.set_external_pairs(g.debug_pairs())
     o.tick(mode=oracle.MODE_COLOURED)
     r = parity.compare_tick(g, o, sc)
     _check(r)

@@ -144,7 +144,8 @@ def test_sleeping_matches_reference_rules(oracle):
 def test_near_hint_is_a_priority_not_a_filter(oracle):
     """include/sfg_hash.h: the `near` bit goes in front of the colouring priority. So (a) the colouring stays a proper colouring
     of ALL pairs whatever the hints are, (b) near pairs outrank the rest: their colours are exactly the ones they would get if the
-    other pairs did not exist, and (c) without hints every pair counts as near."""
+    other pairs did not exist, and (c) the hints the oracle computes itself (sfg_near_hint) are a mix of both values here and
+    feeding them back as overrides changes nothing."""
     sc = scenes.parity_mix(300, 9)
     w = _world(oracle, sc, 1)
     w.tick(mode=oracle.MODE_COLOURED)
@@ -153,9 +154,11 @@ def test_near_hint_is_a_priority_not_a_filter(oracle):
     assert len(pairs) > 300
     rng = np.random.default_rng(5)
     hints = (rng.random(len(pairs)) < 0.4).astype(np.uint8)
-    # (c): all-ones hints change nothing
+    # (c): the oracle's own hints, fed back as overrides, change nothing
+    own = w.pair_unit_hints()
+    assert 0 < sum(own.values()) < len(own)
     w1 = _world(oracle, sc, 1)
-    w1.set_pair_hints(pairs, np.ones(len(pairs), np.uint8))
+    w1.set_pair_hints(pairs, np.array([own[(int(a), int(b))] for a, b in pairs], np.uint8))
     w1.tick(mode=oracle.MODE_COLOURED)
     hi1, lo1, _, col1 = w1.pair_units()
     key = lambda h, l: h.astype(np.uint64) << np.uint64(32) | l.astype(np.uint64)   # noqa: E731
@@ -178,7 +181,7 @@ def test_near_hint_is_a_priority_not_a_filter(oracle):
     near = dict(zip(key(pairs[:, 0], pairs[:, 1]).tolist(), hints.tolist()))
     near_pairs = pairs[hints == 1]
     w3 = _world(oracle, sc, 1)
-    w3.set_external_pairs(near_pairs)
+    w3.set_external_pairs(near_pairs, np.ones(len(near_pairs), np.uint8))
     w3.tick(mode=oracle.MODE_COLOURED)
     hi3, lo3, _, col3 = w3.pair_units()
     alone = dict(zip(key(hi3, lo3).tolist(), col3.tolist()))

@@ -31,7 +31,7 @@ for sub in (1, 2, 3, 4):
         pairs = g2.debug_pairs()
         for f32 in (False, True):
             o = O.OracleWorld(use_f32=f32, tuning=abi.default_tuning(substeps=sub, flags=abi.TUNE_NO_SLEEPING)); o.load_scene(sc2)
-            o.set_external_pairs(pairs, g2.debug_pair_hints())
+            o.set_external_pairs(pairs)
             o.tick(1.0 / 60.0 * sub / 4.0, mode=O.MODE_COLOURED)
             ob = o.get_bodies()
             obad = np.flatnonzero(~np.isfinite(ob[:, 0]))

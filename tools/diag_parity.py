@@ -12,7 +12,7 @@ def run(name, sc, substeps=1, ff=None):
     tun = abi.default_tuning(substeps=substeps, flags=abi.TUNE_SEPARATE_LAUNCHES)
     g = GpuWorld(tuning=tun); g.load_scene(sc); g.tick(forcefield=ff)
     got = state(g.get_bodies())
-    o = O.OracleWorld(tuning=tun); o.load_scene(sc); o.set_external_pairs(g.debug_pairs(), g.debug_pair_hints()); o.tick(mode=O.MODE_COLOURED, forcefield=ff)
+    o = O.OracleWorld(tuning=tun); o.load_scene(sc); o.set_external_pairs(g.debug_pairs()); o.tick(mode=O.MODE_COLOURED, forcefield=ff)
     ref = o.get_bodies()
     ep = np.abs(got[:, :4] - ref[:, :4]).max(1)
     ev = (np.abs(got[:, 4:] - ref[:, 4:]) / np.maximum(1.0, np.abs(ref[:, 4:]))).max(1)
