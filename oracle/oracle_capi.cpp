@@ -41,6 +41,7 @@ void sfo_cast_batch(void* w, uint32_t n, const SfgRay* rays, double* out6, int u
 uint32_t sfo_query_point(void* w, double x, double y, uint32_t domain, int32_t* out, uint32_t cap) { return static_cast<IWorld*>(w)->query_point(x, y, domain, out, cap); }
 uint32_t sfo_query_shape(void* w, const SfgShapeQuery* q, int32_t* out, uint32_t cap) { return static_cast<IWorld*>(w)->query_shape(*q, out, cap); }
 void sfo_get_stats(void* w, uint64_t* out8) { static_cast<IWorld*>(w)->get_stats(out8); }
+size_t sfo_penetrations(void* w, double* out, size_t cap) { return static_cast<IWorld*>(w)->penetrations(out, cap); }
 size_t sfo_n_islands(void* w) { return static_cast<IWorld*>(w)->n_all_islands(); }
 void sfo_get_islands(void* w, uint64_t* first_body, uint64_t* edge_sum, uint64_t* body_count, uint64_t* flags) {
     static_cast<IWorld*>(w)->get_all_islands(first_body, edge_sum, body_count, flags);

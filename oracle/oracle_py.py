@@ -29,7 +29,7 @@ def load():
         lib.sfo_create.restype = C.c_void_p
         lib.sfo_create.argtypes = [C.c_int]
         lib.sfo_n_pairs.restype = lib.sfo_n_pair_units.restype = lib.sfo_n_constraint_units.restype = C.c_size_t
-        lib.sfo_n_entries.restype = lib.sfo_n_contacts.restype = lib.sfo_n_islands.restype = C.c_size_t
+        lib.sfo_n_entries.restype = lib.sfo_n_contacts.restype = lib.sfo_n_islands.restype = lib.sfo_penetrations.restype = C.c_size_t
         lib.sfo_query_point.restype = C.c_uint32
         lib.sfo_query_shape.restype = C.c_uint32
         vp = C.c_void_p
@@ -45,7 +45,7 @@ def load():
             "sfo_get_constraint_units": [vp, vp, vp, vp], "sfo_n_entries": [vp], "sfo_get_manifolds": [vp, vp],
             "sfo_n_contacts": [vp], "sfo_get_contacts": [vp, vp, vp], "sfo_get_aabbs": [vp, vp],
             "sfo_cast_batch": [vp, C.c_uint32, vp, vp, C.c_int],
-            "sfo_query_point": [vp, C.c_double, C.c_double, C.c_uint32, vp, C.c_uint32], "sfo_get_stats": [vp, vp], "sfo_query_shape": [vp, vp, vp, C.c_uint32], "sfo_n_islands": [vp], "sfo_get_islands": [vp, vp, vp, vp, vp],
+            "sfo_query_point": [vp, C.c_double, C.c_double, C.c_uint32, vp, C.c_uint32], "sfo_get_stats": [vp, vp], "sfo_query_shape": [vp, vp, vp, C.c_uint32], "sfo_n_islands": [vp], "sfo_penetrations": [vp, vp, C.c_size_t], "sfo_get_islands": [vp, vp, vp, vp, vp],
             "sfo_intersection_check": [C.c_int, C.c_uint32, vp, vp, vp],
             "sfo_spherecast_collider": [C.c_int, C.c_uint32, vp, vp, vp, vp],
             "sfo_geometry": [C.c_int, C.c_uint32, C.c_uint32, vp, vp, vp], "sfo_clip_edge": [vp, vp, vp],
@@ -191,6 +191,17 @@ class OracleWorld:
         q = np.ascontiguousarray(query).reshape(1)
         n = self.lib.sfo_query_shape(self.h, _p(q), _p(out), cap)
         return out[: min(n, cap)]
+
+    def penetrations(self):
+        """Depth of every contact point (> 0) between solid colliders in the CURRENT state (solver.rs:425-431's depth): a statistic
+        for long-run parity gates, evaluated by the same code for device states (loaded with set_bodies) and oracle states."""
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap)
+            n = self.lib.sfo_penetrations(self.h, _p(out), cap)
+            if n <= cap:
+                return out[:n]
+            cap = int(n)
 
     def islands(self):
         """Every island of the last MODE_REFERENCE tick: first_body, edge_sum, body_count, flags (1 cannot sleep, 8 asleep)."""

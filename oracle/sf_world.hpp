@@ -108,6 +108,7 @@ struct IWorld {
     virtual uint32_t query_point(double x, double y, uint32_t domain, int32_t* out, uint32_t cap) const = 0;
     virtual uint32_t query_shape(const SfgShapeQuery& q, int32_t* out, uint32_t cap) const = 0;
     virtual void get_stats(uint64_t* out8) const = 0;
+    virtual size_t penetrations(double* out, size_t cap) = 0;
     virtual size_t n_all_islands() const = 0;
     virtual void get_all_islands(uint64_t* first_body, uint64_t* edge_sum, uint64_t* body_count, uint64_t* flags) const = 0;
 };
@@ -331,6 +332,33 @@ public:
         }
         std::sort(found.begin(), found.end());
         for (auto& p : found) { pair_keys.push_back(p.first); pair_keys.push_back(p.second); }
+    }
+
+    // A statistic of the current STATE, not part of the tick (long-run parity gates compare its distribution between the device
+    // and the reference order): the depth of every contact point of every overlapping solid pair, depth as solve_contacts
+    // measures it (solver.rs:425-431: (p0 - p1) . normal with the points on the two rounded surfaces). Returns how many were
+    // found; the first `cap` are written.
+    size_t penetrations(double* out, size_t cap) override {
+        compute_aabbs(R(0));                                               // tight boxes: overlapping shapes have overlapping boxes
+        broadphase_sweep();
+        size_t n = 0;
+        for (size_t p = 0; p + 1 < pair_keys.size(); p += 2) {
+            const uint32_t ck[2] = {pair_keys[p], pair_keys[p + 1]};
+            if (!pair_kept(ck[0], ck[1])) continue;
+            const ColliderS<R>* cl[2] = {&colliders[ck[0]], &colliders[ck[1]]};
+            if (cl[0]->sensor || cl[1]->sensor) continue;
+            Iso2<R> pw[2];
+            for (int i = 0; i < 2; ++i) pw[i] = cl[i]->body >= 0 ? bodies[size_t(cl[i]->body)].pose * cl[i]->pose : cl[i]->pose;
+            Shape<R> sh[2] = {cl[0]->shape, cl[1]->shape};
+            ContactResult<R> c = intersection_check(pw, sh, false);
+            for (int k = 0; k < c.count; ++k) {
+                const R depth = (pw[0] * c.c[k].offsets[0] - pw[1] * c.c[k].offsets[1]).dot(c.c[k].normal);
+                if (!(depth > R(0))) continue;
+                if (n < cap) out[n] = double(depth);
+                ++n;
+            }
+        }
+        return n;
     }
 
     // body slot of a collider or -1 (entity_set.coll_bodies)

@@ -6,5 +6,5 @@ timeout 600 ncu --profile-from-start off --set full --clock-control none --impor
 python tools/summarise_ncu.py full gpurun_out/r02a_settled_solver.ncu-rep gpurun_out/r02a_solver_full_settled.txt "k_solve_persistent, C3 settled (tick 301)"
 timeout 600 ncu --profile-from-start off --set full --clock-control none -o gpurun_out/r02a_settled_tick -f python tools/prof_ticks.py c3 300 1 > gpurun_out/r02a_ncu2.log 2>&1
 python tools/summarise_ncu.py full gpurun_out/r02a_settled_tick.ncu-rep gpurun_out/r02a_tick_full_settled.txt "all kernels of one settled C3 tick (tick 301)"
-ls -la gpurun_out/
+rm -f gpurun_out/r02a_settled_tick.ncu-rep
 du -sh gpurun_out
