@@ -49,6 +49,8 @@ typedef struct SfgTuning {
 } SfgTuning;
 #define SFG_TUNE_NO_SLEEPING 1u      /* skip island / sleeping bookkeeping entirely */
 #define SFG_TUNE_SEPARATE_LAUNCHES 2u /* debug: one launch per colour instead of the persistent kernel */
+#define SFG_TUNE_COUNT_ENTRIES 4u     /* measurement: count the contact entries that found a contact (SfgStats.n_touching_entries); one more
+                                      * warp-aggregated atomic per group of touching units in the solver, so off by default */
 #define SFG_MAX_SUBSTEPS 4096u       /* substeps of one tick (after time scaling) are capped: per-substep tables are sized by it */
 
 /* body.rs:7-13 Body. flags carry the Mass enum discriminants (body.rs:105-129). */
@@ -168,7 +170,9 @@ typedef struct SfgStats {
     uint32_t kernel_launches;                /* kernels launched by the last tick */
     float ms_broadphase, ms_graph, ms_solver, ms_total; /* CUDA-event times of the last tick */
     float cell_size;
-    uint32_t reserved[3];
+    uint32_t n_stages;                       /* stages per substep of the persistent solver's table */
+    uint32_t n_touching_units;               /* SFG_TUNE_COUNT_ENTRIES: pair units whose first visit found a contact, summed over the substeps */
+    uint32_t n_touching_entries;             /* the same counted in contact entries (a body-body unit is two entries), summed over the substeps */
 } SfgStats;
 
 /* ---- lifetime: PhysicsWorld::new (physics.rs:366), clear (:386) ---- */
@@ -240,6 +244,8 @@ int sfg_get_stats(SfgWorld* w, SfgStats* out);
 
 /* ---- PhysicsWorld::raycast / spherecast (physics.rs:1255-1311), batched ---- */
 int sfg_cast_batch(SfgWorld* w, uint32_t n, const SfgRay* rays, SfgCastHit* out);
+/* measurement: device time of the k_cast_batch launch of the last sfg_cast_batch (CUDA events on the world's stream, copies excluded) */
+int sfg_get_cast_kernel_ms(SfgWorld* w, float* out_ms);
 /* ---- PhysicsWorld::query_point (physics.rs:1188-1210), batched: for each point, up to
  *      `max_hits` collider slots (-1 padded) ---- */
 int sfg_query_point_batch(SfgWorld* w, uint32_t n, const float* points_xy, const uint32_t* domains,

@@ -20,7 +20,7 @@ POLY_POINT, POLY_SEGMENT, POLY_RECT, POLY_TRIANGLE, POLY_HEXAGON = 0, 1, 2, 3, 4
 COLL_ALIVE, COLL_SENSOR, COLL_HAS_STATIC_FRICTION, COLL_HAS_DYNAMIC_FRICTION = 1, 2, 4, 8
 LIMIT_EQ, LIMIT_LT, LIMIT_GT, CONSTRAINT_CAN_SLEEP = 0, 1, 2, 4
 FF_NONE, FF_GRAVITY, FF_POINT_GRAVITY = 0, 1, 2
-TUNE_NO_SLEEPING, TUNE_SEPARATE_LAUNCHES = 1, 2
+TUNE_NO_SLEEPING, TUNE_SEPARATE_LAUNCHES, TUNE_COUNT_ENTRIES = 1, 2, 4
 ROPE_LAYER = 63  # collision.rs:130
 
 tuning_dtype = np.dtype([("substeps", "<u4"), ("sleep_vel_threshold", "<f4"), ("fall_asleep_frames", "<u4"),
@@ -54,14 +54,14 @@ stats_dtype = np.dtype([("n_bodies", "<u4"), ("n_colliders", "<u4"), ("n_pairs",
                         ("n_rope_particles", "<u4"), ("n_ropes", "<u4"), ("n_contacts", "<u4"), ("substeps", "<u4"),
                         ("grid_levels", "<u4"), ("grid_cells", "<u4"), ("n_islands", "<u4"), ("n_sleeping_bodies", "<u4"),
                         ("kernel_launches", "<u4"), ("ms_broadphase", "<f4"), ("ms_graph", "<f4"), ("ms_solver", "<f4"),
-                        ("ms_total", "<f4"), ("cell_size", "<f4"), ("reserved", "<u4", (3,))])
+                        ("ms_total", "<f4"), ("cell_size", "<f4"), ("n_stages", "<u4"), ("n_touching_units", "<u4"), ("n_touching_entries", "<u4")])
 
 # every symbol include/starframe_gpu.h declares (tests check the library exports each one)
 EXPORTS = [
     "sfg_abi_version", "sfg_world_create", "sfg_world_destroy", "sfg_world_clear", "sfg_last_error", "sfg_set_tuning",
     "sfg_set_mask_matrix", "sfg_default_tuning", "sfg_default_mask_matrix", "sfg_set_bodies", "sfg_update_bodies",
     "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_tick", "sfg_tick_begin", "sfg_tick_substeps", "sfg_tick_end", "sfg_slab_configure", "sfg_island_shard_configure", "sfg_slab_begin", "sfg_slab_pack", "sfg_slab_unpack", "sfg_get_bodies",
-    "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_tick_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_query_point_batch", "sfg_query_shape_batch", "sfg_debug_get_pairs", "sfg_debug_get_pair_hints",
+    "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_tick_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_get_cast_kernel_ms", "sfg_query_point_batch", "sfg_query_shape_batch", "sfg_debug_get_pairs", "sfg_debug_get_pair_hints",
     "sfg_debug_get_contact_entries", "sfg_debug_get_constraint_entries", "sfg_debug_get_manifolds", "sfg_debug_get_aabbs", "sfg_debug_get_islands",
     "sfg_debug_intersection_check", "sfg_debug_spherecast_collider", "sfg_debug_geometry",
 ]
@@ -115,6 +115,7 @@ def load():
     lib.sfg_tick_poses.argtypes = [vp, vp, C.c_double, i32, C.c_double, vp, vp]
     lib.sfg_get_stats.argtypes = [vp, vp]
     lib.sfg_cast_batch.argtypes = [vp, u32, vp, vp]
+    lib.sfg_get_cast_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     lib.sfg_query_point_batch.argtypes = [vp, u32, vp, vp, u32, vp, vp]
     lib.sfg_query_shape_batch.argtypes = [vp, u32, vp, u32, vp, vp]
     lib.sfg_debug_get_pairs.argtypes = [vp, vp, sz, C.POINTER(sz)]

@@ -91,6 +91,9 @@ struct SfgWorld {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool islands_in_flight = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_cast[2] = {nullptr, nullptr};
+    float last_cast_ms = 0.f;
+    uint32_t n_k_two = 0;                    // two-body constraints (visited twice per substep)
     std::string err;
     SfgTuning tuning{};
     uint64_t mask[64];
@@ -121,6 +124,7 @@ struct SfgWorld {
     DBuf<unsigned char> stage, stage2;   // stage2: pose read-back on the second stream (sfg_tick_poses)
     DBuf<unsigned long long> d_mask;
     DBuf<TickHeader> hdr;
+    DBuf<uint32_t> tick_counts;   // [0] body-body pair units of the tick (visited twice), [2] / [3] touching units / entries (SFG_TUNE_COUNT_ENTRIES)
     // broadphase scratch
     GridParams grid{};
     uint32_t n_live = 0, n_entries = 0;
@@ -561,7 +565,8 @@ int sfg_world_create(const SfgTuning* tuning, const uint64_t mask_matrix[64], in
     if (cudaStreamCreateWithFlags(&w->stream2, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(w->stream); delete w; delete yard; return SFG_E_CUDA; }
     cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming);
     for (auto& e : w->ev) cudaEventCreate(&e);
-    if (w->d_mask.ensure(64) != cudaSuccess || w->hdr.ensure(1) != cudaSuccess) { delete w; delete yard; return SFG_E_CUDA; }
+    for (auto& e : w->ev_cast) cudaEventCreate(&e);
+    if (w->d_mask.ensure(64) != cudaSuccess || w->hdr.ensure(1) != cudaSuccess || w->tick_counts.ensure(4) != cudaSuccess) { delete w; delete yard; return SFG_E_CUDA; }
     cudaMemcpyAsync(w->d_mask.p, w->mask, sizeof(w->mask), cudaMemcpyHostToDevice, w->stream);
     cudaStreamSynchronize(w->stream);
     *out = w;
@@ -591,6 +596,7 @@ void sfg_world_destroy(SfgWorld* w) {
     w->U_ids.release(); w->slab_stamp.release(); w->isl_sum.release(); w->sl_sum.release(); w->ct[0].release(); w->ct[1].release(); w->adj2.release(); w->KU_ids.release(); w->RC.release(); w->WL.release(); w->wl_count.release(); w->near_count.release(); w->far_min.release(); w->body_word.release(); w->trace.release(); w->adj_body.release(); w->adj_rank.release(); w->U_cls.release(); w->adj_colour.release(); w->U_slot.release(); w->U_ub.release(); w->KU_ub.release();
     w->stage.release(); w->stage2.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : w->ev_cast) if (e) cudaEventDestroy(e);
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
     if (w->ev_join) cudaEventDestroy(w->ev_join);
     if (w->stream2) cudaStreamDestroy(w->stream2);
@@ -705,6 +711,8 @@ int sfg_set_constraints(SfgWorld* w, uint32_t n, const SfgConstraint* c) {
         if ((c[i].flags & SFG_LIMIT_MASK) > SFG_LIMIT_GT) return fail(w, SFG_E_INVALID, "unknown constraint limit");
     }
     w->n_constraints = n;
+    w->n_k_two = 0;
+    for (uint32_t i = 0; i < n; ++i) if (c[i].target >= 0) w->n_k_two++;
     if (n == 0) return SFG_OK;
     cudaStream_t st = w->stream;
     CK(w->KI.ensure(n)); CK(w->KA.ensure(n)); CK(w->KB.ensure(n));
@@ -941,7 +949,7 @@ int build_graph(SfgWorld* w) {
         { int jr = join_islands(w); if (jr != SFG_OK) return jr; }
         k_build_pair_units<<<nblk(n), 256, 0, st>>>(n, perm, w->U_ids.p, w->CS.p, w->CL.p, w->CM.p, w->CI.p, w->MI.p,
                                                     w->n_ropes ? w->rope_next.p : nullptr, w->n_ropes ? w->rope_prev.p : nullptr, w->H.p, w->S.p,
-                                                    w->G0.p, w->G1.p, w->L0.p, w->L1.p, w->RC.p);
+                                                    w->G0.p, w->G1.p, w->L0.p, w->L1.p, w->RC.p, w->tick_counts.p);
         CKL(w); w->launches++;
         CK(cudaMemsetAsync(w->LN.p, 0xFF, size_t(n) * 2 * sizeof(float2), st));
         CK(cudaMemsetAsync(w->M0.p, 0, size_t(n) * 2 * sizeof(float4), st));
@@ -970,6 +978,7 @@ void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
     c.rope_next = w->rope_next.p; c.rope_prev = w->rope_prev.p; c.n_bodies = w->n_bodies; c.bouncy = w->bouncy_seen ? 1u : 0u;
     c.H = w->H.p; c.S = w->S.p; c.G0 = w->G0.p; c.G1 = w->G1.p; c.L0 = w->L0.p; c.L1 = w->L1.p;
     c.M0 = w->M0.p; c.M1 = w->M1.p; c.M2 = w->M2.p; c.LN = w->LN.p; c.n_units = w->n_units;
+    c.stat_touch = (w->tuning.flags & SFG_TUNE_COUNT_ENTRIES) ? w->tick_counts.p + 2 : nullptr;
     c.RC = w->RC.p; c.WL = w->WL.p; c.wl_count = w->wl_count.p; c.near_count = w->near_count.p; c.n_colours = w->n_unit_colours;
     c.K0 = w->K0.p; c.K1 = w->K1.p; c.K2 = w->K2.p; c.n_kunits = w->n_kunits;
     c.RU = w->RU.p; c.RD = w->RD.p; c.RPA = w->RPA.p; c.RPB = w->RPB.p; c.rp_body = w->rp_body.p; c.rp_rope = w->rp_rope.p;
@@ -1109,6 +1118,7 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     w->islands_in_flight = false;
     w->frame_dt = float(frame_dt);
     CK(cudaEventRecord(w->ev[0], st));
+    CK(cudaMemsetAsync(w->tick_counts.p, 0, 4 * sizeof(uint32_t), st));
     if (w->n_bodies) CK(cudaMemsetAsync(w->EA.p, 0, size_t(w->n_bodies) * sizeof(float2), st));
     if (w->n_ropes) CK(cudaMemsetAsync(w->LAT.p, 0xFF, size_t(w->n_bodies) * sizeof(float2), st));
     if (w->slab_on || w->slab_was_on) { rc = slab_classify(w); if (rc != SFG_OK) return rc; }
@@ -1283,6 +1293,8 @@ static int tick_end_impl(SfgWorld* w, float* poses_out) {
     if (sleeping) { rc = island_post(w); if (rc != SFG_OK) return rc; }
     uint32_t isl_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (sleeping && w->n_bodies) CK(cudaMemcpyAsync(isl_counts, w->isl_counters.p, sizeof(isl_counts), cudaMemcpyDeviceToHost, st));
+    uint32_t tick_counts[4] = {0, 0, 0, 0};
+    if (w->tick_counts.p) CK(cudaMemcpyAsync(tick_counts, w->tick_counts.p, sizeof(tick_counts), cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(w->ev[4], st));
     CK(cudaStreamSynchronize(st));
     if (poses_out) CK(cudaStreamSynchronize(w->stream2));
@@ -1294,7 +1306,7 @@ static int tick_end_impl(SfgWorld* w, float* poses_out) {
     SfgStats& s = w->stats;
     memset(&s, 0, sizeof(s));
     s.n_bodies = w->n_bodies; s.n_colliders = w->n_live; s.n_pairs = w->n_units;
-    s.n_constraint_entries = 0;
+    s.n_constraint_entries = w->n_constraints + w->n_k_two;      // two-body constraints are stored on both bodies (physics.rs:519-532)
     s.n_contact_colours = w->n_unit_colours; s.n_constraint_colours = w->n_k_colours;
     s.n_rope_particles = w->n_particles; s.n_ropes = w->n_ropes; s.substeps = substeps;
     s.grid_levels = uint32_t(w->grid.n_levels); s.grid_cells = w->grid.n_cells; s.cell_size = w->grid.cell[0];
@@ -1304,8 +1316,9 @@ static int tick_end_impl(SfgWorld* w, float* poses_out) {
     cudaEventElapsedTime(&s.ms_graph, w->ev[1], w->ev[2]);
     cudaEventElapsedTime(&s.ms_solver, w->ev[2], w->ev[3]);
     cudaEventElapsedTime(&s.ms_total, w->ev[0], w->ev[4]);
-    s.reserved[0] = uint32_t(w->h_stages.size());
-    s.reserved[1] = w->stats_jp_rounds;
+    s.n_stages = uint32_t(w->h_stages.size());
+    s.n_contact_entries = w->n_units + tick_counts[0];
+    s.n_touching_units = tick_counts[2]; s.n_touching_entries = tick_counts[3];
     return SFG_OK;
 }
 
@@ -1501,10 +1514,18 @@ int sfg_cast_batch(SfgWorld* w, uint32_t n, const SfgRay* rays, SfgCastHit* out)
     if (w->n_live == 0) { for (uint32_t i = 0; i < n; ++i) { memset(&out[i], 0, sizeof(SfgCastHit)); out[i].collider = -1; } return SFG_OK; }
     CK(w->d_rays.ensure(n)); CK(w->d_hits.ensure(n));
     CK(cudaMemcpyAsync(w->d_rays.p, rays, size_t(n) * sizeof(SfgRay), cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(w->ev_cast[0], st));
     k_cast_batch<<<nblk(n, 128), 128, 0, st>>>(c, n, w->d_rays.p, w->d_hits.p);
     CKL(w);
+    CK(cudaEventRecord(w->ev_cast[1], st));
     CK(cudaMemcpyAsync(out, w->d_hits.p, size_t(n) * sizeof(SfgCastHit), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&w->last_cast_ms, w->ev_cast[0], w->ev_cast[1]);
+    return SFG_OK;
+}
+int sfg_get_cast_kernel_ms(SfgWorld* w, float* out_ms) {
+    if (!w || !out_ms) return SFG_E_INVALID;
+    *out_ms = w->last_cast_ms;
     return SFG_OK;
 }
 

@@ -623,10 +623,17 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
                                                           const float4* __restrict__ MI, const int* __restrict__ rope_next,
                                                           const int* __restrict__ rope_prev, float4* __restrict__ H, float4* __restrict__ S,
                                                           float4* __restrict__ G0, float4* __restrict__ G1, float4* __restrict__ L0,
-                                                          float4* __restrict__ L1, float* __restrict__ RC) {
+                                                          float4* __restrict__ L1, float* __restrict__ RC, uint32_t* __restrict__ counts) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_units) return;
-    const uint2 id = ids[perm[s]];
+    const bool in = s < n_units;
+    uint2 id = make_uint2(0u, 0u);
+    if (in) id = ids[perm[s]];
+    {   // statistics: how many units are body-body pairs (visited twice per substep, physics.rs:641,651) -> counts[0]
+        const bool two = in && CI[id.x].x >= 0 && CI[id.y].x >= 0;
+        const uint32_t n2 = __syncthreads_count(two);
+        if (threadIdx.x == 0 && n2) atomicAdd(counts, n2);
+    }
+    if (!in) return;
     const int4 c0 = CI[id.x], c1 = CI[id.y];
     const float4 m0 = CM[id.x], m1 = CM[id.y];
     const uint32_t f0 = uint32_t(c0.w), f1 = uint32_t(c1.w);

@@ -413,6 +413,10 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
         if (int(lane) == leader) base = atomicAdd(c.wl_count + sub * c.n_colours + colour, uint32_t(__popc(act)));
         base = __shfl_sync(act, base, leader);
         __stcg(c.WL + colour_begin + base + uint32_t(__popc(act & ((1u << lane) - 1u))), u);
+        if (c.stat_touch) {                                               // measurement only (SFG_TUNE_COUNT_ENTRIES)
+            const uint32_t two = __ballot_sync(act, mult == 2);
+            if (int(lane) == leader) { atomicAdd(c.stat_touch, uint32_t(__popc(act))); atomicAdd(c.stat_touch + 1, uint32_t(__popc(act) + __popc(two))); }
+        }
         SFG_STAMP(6, base);
     }
 #ifdef SFG_PROBE

@@ -99,6 +99,7 @@ struct SolverCtx {
     uint32_t* WL;
     uint32_t* wl_count;
     uint32_t* far_min;            // [substep * n_stages + first stage of a merged far-only run]: the first stage of that run with a surviving unit (0xFFFFFFFF = none)
+    uint32_t* stat_touch;         // SFG_TUNE_COUNT_ENTRIES: [0] += units, [1] += entries whose first visit found a contact (nullptr = not counted)
     const uint32_t* near_count;   // per contact colour: units sorted first inside the colour because they may touch this tick
     uint32_t n_units, n_colours;
     // constraint units (sorted colour-major)

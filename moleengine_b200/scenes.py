@@ -262,30 +262,36 @@ def c4_ropes(n_ropes=10000, particles_per_rope=64, n_free_blocks=30000, seed=0xC
 
 
 # ---- C5: batched independent worlds ----------------------------------------------------------------
-def c5_worlds(n_worlds=8192, bodies_per_side=16, seed=0xC5, first_world=0):
-    """Each world: 4 static walls of a 20 x 10 box (scenes/minimal.ron:4-15) + bodies_per_side^2 bodies of the C3 mix
-    on a grid. Worlds are independent `domain`s sharing coordinates; seed = 0xC5 + world index."""
+def c5_worlds(n_worlds=8192, bodies_per_side=16, seed=0xC5, first_world=0, dense=False):
+    """Each world: 4 static walls + bodies_per_side^2 bodies of the C3 mix on a grid. Worlds are independent `domain`s sharing
+    coordinates; seed = 0xC5 + GLOBAL world index (first_world + i), so a rank that builds only its share of the worlds gets the
+    same worlds a single GPU would.
+    Default = SURVEY.md §8(d)'s C5: a 20 x 20 box (walls as scenes/minimal.ron:4-15, the box made square so that 256 bodies of
+    the C3 mix — about 205 m^2 of them — have room to fall and pile up), bodies on a 1.15 m grid.
+    dense=True is round 1's variant: minimal.ron's own 20 x 10 box with the rows squeezed to 0.56 m — the bodies fill the box
+    completely and start out overlapping; kept as a stress case (tools/bench_configs.py c5d)."""
     bps = bodies_per_side
     per = bps * bps
-    wall_shapes = [(20.0, 0.2, 0.0, 5.0), (20.0, 0.2, 0.0, -5.0), (0.2, 10.0, 10.0, 0.0), (0.2, 10.0, -10.0, 0.0)]
+    if dense:
+        wall_shapes = [(20.0, 0.2, 0.0, 5.0), (20.0, 0.2, 0.0, -5.0), (0.2, 10.0, 10.0, 0.0), (0.2, 10.0, -10.0, 0.0)]
+        y0, pitch_y = -4.2, 0.56
+    else:
+        wall_shapes = [(20.0, 0.2, 0.0, 10.0), (20.0, 0.2, 0.0, -10.0), (0.2, 20.0, 10.0, 0.0), (0.2, 20.0, -10.0, 0.0)]
+        y0, pitch_y = -(bps - 1) / 2.0 * 1.15, 1.15
     all_b, all_c = [], []
     i, j = np.meshgrid(np.arange(bps), np.arange(bps), indexing="xy")
-    coll_base = 0
     for wld in range(n_worlds):
-        gw = first_world + wld
-        s = seed + gw
+        s = seed + first_world + wld
         x = (i.ravel() - (bps - 1) / 2.0) * 1.15 + uniform(s, 1, per, -0.02, 0.02)
-        y = -4.2 + j.ravel() * 0.56 + uniform(s, 2, per, -0.01, 0.01)
+        y = y0 + j.ravel() * pitch_y + uniform(s, 2, per, -0.01, 0.01)
         b, c = _mixed_bodies(per, s, x, y, domain=wld, body_base=wld * per)
-        # keep worlds small: scale positions only (shapes are the C3 mix)
         walls = np.zeros(4, abi.collider_dtype)
         for k, (w_, h_, wx, wy) in enumerate(wall_shapes):
             shapes.fill_colliders(walls[k:k + 1], shapes.rounded_rect(w_, h_, 0.0), x=wx, y=wy, domain=wld)
         all_b.append(b)
         all_c.append(walls)
         all_c.append(c)
-        coll_base += 4 + len(c)
-    return _scene(f"c5_worlds_{n_worlds}x{per}", np.concatenate(all_b), np.concatenate(all_c), 4)
+    return _scene(f"c5_worlds_{n_worlds}x{per}" + ("_dense" if dense else ""), np.concatenate(all_b), np.concatenate(all_c), 4)
 
 
 def c5_rays(scene_bodies, n_worlds, bodies_per_world, rays_per_world=64):

@@ -39,6 +39,7 @@ def neighbours(rank, n_ranks):
 
 class DistTransport:
     """torch.distributed point-to-point exchange with both x-neighbours in one batch (no collective over all ranks)."""
+    name = "torch.distributed send/recv between x-neighbours (NCCL P2P over NVLink on GPUs)"
 
     def __init__(self, group=None):
         self.group = group
@@ -61,6 +62,7 @@ class DistTransport:
 
 class LocalTransport:
     """All slabs in one process (tests): the 'wire' is a copy between the drivers' buffers."""
+    name = "in-process device copies"
 
     def __init__(self):
         self.drivers = {}
@@ -85,6 +87,7 @@ class SlabDriver:
         self.lo, self.hi = slab_bounds(rank, n_ranks, x_min, x_max)
         self.halo = halo
         self.transport = transport if transport is not None else DistTransport()
+        self.transport_name = getattr(self.transport, "name", type(self.transport).__name__)
         f32max = 3.0e38
         world.slab_configure(max(self.lo, -f32max), min(self.hi, f32max), halo)
         words = (capacity + 1) * REC_WORDS

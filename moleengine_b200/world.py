@@ -163,6 +163,12 @@ class GpuWorld:
         self._ck(self.lib.sfg_cast_batch(self.h, len(rays), abi.ptr(rays), abi.ptr(out)))
         return out
 
+    def cast_kernel_ms(self):
+        """Device time of the k_cast_batch launch of the last cast_batch (copies excluded)."""
+        ms = C.c_float()
+        self._ck(self.lib.sfg_get_cast_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def query_point_batch(self, points, domains=None, max_hits=8):
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 2)
         dom = None if domains is None else np.ascontiguousarray(domains, dtype=np.uint32)

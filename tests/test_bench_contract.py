@@ -19,6 +19,20 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] >= 3 and d["n_gpus"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # both arms describe the same workload: the driver compares `config` of the two JSON lines
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.CONFIG and "workload" in d["config"]
+
+
+def test_solver_bytes_follow_the_survey_formula():
+    """192 N_b + 64 N_c + 96 N_k + 64 N_r + 152 per touching entry (device-counted) + 52 per rejected unit, per substep."""
+    sys.path.insert(0, ROOT)
+    import bench
+    st = {"n_pairs": 1000, "n_touching_units": 4 * 300, "n_touching_entries": 4 * 500, "n_colliders": 120, "n_constraint_entries": 10, "n_rope_particles": 7, "n_contact_entries": 1600}
+    b, counts = bench.solver_bytes_per_tick(st, 100, 4)
+    assert b == 4 * (192 * 100 + 64 * 120 + 96 * 10 + 64 * 7 + 152 * 500 + 52 * 700)
+    assert counts["touching_entries_per_substep"] == 500 and counts["pair_units"] == 1000
 
 
 def test_other_ranks_of_the_reference_arm_exit_quietly():

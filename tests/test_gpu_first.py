@@ -80,3 +80,48 @@ def test_tick_matches_oracle_replay(oracle, substeps, separate):
         assert r["bad_bodies"] <= 0.25 * r["bodies"]
         assert r["momentum_rel_err"] < 1e-3 and r["kinetic_rel_err"] < 1e-2
     g.close()
+
+
+@pytest.mark.parametrize("name", ["c3_tenth", "c5_64"])
+def test_pairs_hints_colours_islands_bit_exact_at_scale(oracle, name):
+    """1/10-scale C3 (100 000 bodies) and 64-world C5, at the first tick and again after the device has run the scene for a
+    while (bodies landing / piled up): tick-time boxes, candidate pairs, `near` bits, colours (f32 oracle, coloured order) and
+    island ids (f32 oracle, reference order, its own BVH and DFS) all bit-exact from the SAME f32 state."""
+    sc = scenes.c3_mixed(400, 250) if name == "c3_tenth" else scenes.c5_worlds(64, 16)
+    tun = abi.default_tuning(substeps=4)
+    tun["fall_asleep_frames"] = 1000000           # the island pass runs, nothing falls asleep
+    g = GpuWorld(tuning=tun)
+    g.load_scene(sc)
+    alive = (sc["colliders"]["flags"] & abi.COLL_ALIVE) != 0
+    for warm in (0, 30):
+        for _ in range(warm):
+            g.tick()
+        state = g.get_bodies()
+        state["flags"] &= 15
+        g.tick()
+        # coloured order, f32: boxes, pairs, hints, colours
+        o = oracle.OracleWorld(use_f32=True, tuning=tun)
+        o.load_scene(sc)
+        o.set_bodies(state)
+        o.tick(mode=oracle.MODE_COLOURED)
+        ga, oa = g.debug_aabbs(len(sc["colliders"])), o.aabbs().astype(np.float32)
+        assert np.array_equal(ga[alive].view(np.uint32), oa[alive].view(np.uint32))
+        gp = g.debug_pairs()
+        assert len(gp) > 50000 and np.array_equal(_pairset(gp), _pairset(o.pairs()))
+        gh = dict(zip(map(tuple, gp.tolist()), g.debug_pair_hints().tolist()))
+        assert gh == o.pair_unit_hints()
+        hi, lo, mult, col = g.debug_contact_units()
+        ohi, olo, omult, ocol = o.pair_units()
+        key = lambda h, l: (h.astype(np.uint64) << np.uint64(32)) | l.astype(np.uint64)   # noqa: E731
+        go, oo = np.argsort(key(hi, lo)), np.argsort(key(ohi, olo))
+        assert np.array_equal(key(hi, lo)[go], key(ohi, olo)[oo]) and np.array_equal(mult[go], omult[oo]) and np.array_equal(col[go], ocol[oo])
+        # reference order, f32: islands from the oracle's own BVH pairs and DFS
+        o = oracle.OracleWorld(use_f32=True, tuning=tun)
+        o.load_scene(sc)
+        o.set_bodies(state)
+        o.tick(mode=oracle.MODE_REFERENCE)
+        table = lambda fb, es, bc, fl: sorted(zip(np.asarray(fb, np.uint64).tolist(), np.asarray(es, np.uint64).tolist(), np.asarray(bc, np.uint64).tolist()))  # noqa: E731
+        got, want = table(*g.debug_islands()), table(*o.islands())
+        assert len(got) > 0 and got == want
+        print(name, "after", warm, "ticks: pairs", len(gp), "near", sum(gh.values()), "colours", int(col.max()) + 1, "islands", len(got))
+    g.close()

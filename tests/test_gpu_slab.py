@@ -133,3 +133,63 @@ def test_island_shards_are_bit_identical_to_one_gpu(n_shards):
     assert merged == key(ref.get_contacts())
     for w in worlds + [ref]:
         w.close()
+
+
+def test_ropes_and_attachments_across_a_cut():
+    """ropes / constraints crossing slabs (rope.rs:61-85 chains, constraint.rs:40-58 attachments). Four of the
+    twelve rope-connected block pairs lie ACROSS the cut (particles and both end blocks on different ranks), free blocks are
+    dropped on them. Ownership stays unique, the chains stay chains (link lengths, attachment distances) and the straddling ropes
+    follow the single-world run statistically."""
+    import torch
+    sc = scenes.c4_ropes(n_ropes=12, particles_per_rope=32, n_free_blocks=36)
+    nb = len(sc["bodies"])
+    tun = abi.default_tuning(substeps=4, flags=abi.TUNE_NO_SLEEPING)
+    ref = GpuWorld(tuning=tun)
+    ref.load_scene(sc)
+    transport = slab.LocalTransport()
+    worlds, drivers = [], []
+    for r in range(2):
+        w = GpuWorld(tuning=tun)
+        w.load_scene(sc)
+        worlds.append(w)
+        drivers.append(slab.SlabDriver(w, r, 2, -30.0, 30.0, halo=4.0, substeps=4, capacity=4096, device=torch.device("cuda", 0), transport=transport))
+    rp = sc["rope_particles"]
+    ropes = sc["ropes"]
+    x0 = sc["bodies"]["x"]
+    straddle = [i for i, r in enumerate(ropes) if x0[rp[r["first_particle"]]] < 0.0 < x0[rp[r["first_particle"] + r["particle_count"] - 1]]]
+    assert len(straddle) == 4
+
+    def chain_metrics(b):
+        stretch, attach = 0.0, 0.0
+        for i in straddle:
+            r = ropes[i]
+            p = rp[r["first_particle"]: r["first_particle"] + r["particle_count"]]
+            d = np.hypot(np.diff(b["x"][p].astype(np.float64)), np.diff(b["y"][p].astype(np.float64)))
+            stretch = max(stretch, float(np.abs(d - 0.1).max()))
+        for k in sc["constraints"]:
+            o, t = int(k["owner"]), int(k["target"])
+            c, s = 1.0 - 2.0 * float(b["rot_b"][t]) ** 2, -2.0 * float(b["rot_s"][t]) * float(b["rot_b"][t])   # rotor -> rotation by theta: cos, sin
+            ax = float(b["x"][t]) + c * float(k["off1x"]) - s * float(k["off1y"])
+            ay = float(b["y"][t]) + s * float(k["off1x"]) + c * float(k["off1y"])
+            attach = max(attach, float(np.hypot(float(b["x"][o]) - ax, float(b["y"][o]) - ay)))
+        return stretch, attach
+
+    for t in range(90):
+        ref.tick()
+        slab.tick_local(drivers, transport)
+        if t % 15 == 14:
+            got, owners = _assemble(worlds, nb)
+            assert np.array_equal(owners, np.ones(nb, np.int32)), "every body has exactly one owner"
+            want = ref.get_bodies()
+            sg, ag = chain_metrics(got)
+            sw, aw = chain_metrics(want)
+            part = np.concatenate([rp[ropes[i]["first_particle"]: ropes[i]["first_particle"] + ropes[i]["particle_count"]] for i in straddle])
+            dy = abs(float(got["y"][part].mean()) - float(want["y"][part].mean()))
+            dmed = float(np.median(np.hypot(got["x"][part] - want["x"][part], got["y"][part] - want["y"][part])))
+            print({"tick": t + 1, "stretch": (sg, sw), "attach": (ag, aw), "mean_y_diff": dy, "median_dev": dmed, "records": sum(d.sent_records for d in drivers)})
+            assert np.isfinite(_state(got)).all()
+            assert sg < max(2.0 * sw, 0.02) and ag < max(2.0 * aw, 0.05), "a chain across the cut came apart"
+            assert dy < 0.1
+    assert sum(d.sent_records for d in drivers) > 100, "no rope crossed the cut"
+    for w in worlds + [ref]:
+        w.close()
