@@ -108,7 +108,7 @@ struct SfgWorld {
     DBuf<int> rope_next, rope_prev;
     // colliders
     uint32_t n_colls = 0;
-    DBuf<float4> CS, CL, CM, AABB;
+    DBuf<float4> CS, CL, CM, AABB, CREC;   // CREC: (CS, CL, CM, CI) interleaved, 64 B per collider, for the kernels that gather whole colliders
     DBuf<int4> CI;
     // constraints (raw columns in host order)
     uint32_t n_constraints = 0;
@@ -249,15 +249,20 @@ __global__ void k_get_poses(float4* out, uint32_t n, uint32_t first, const float
     const float4 p = P[first + i], q = Q[first + i];
     out[i] = make_float4(p.x + p.z, p.y + p.w, q.x, q.y);
 }
-__global__ void k_unpack_colliders(const SfgCollider* in, uint32_t n, uint32_t first, float4* CS, float4* CL, float4* CM, int4* CI) {
+__global__ void k_unpack_colliders(const SfgCollider* in, uint32_t n, uint32_t first, float4* CS, float4* CL, float4* CM, int4* CI, float4* CREC) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const SfgCollider c = in[i];
     const uint32_t s = first + i;
-    CS[s] = make_float4(c.p0, c.p1, c.circle_r, __uint_as_float(c.kind));
-    CL[s] = make_float4(c.x, c.y, c.rot_s, c.rot_b);
-    CM[s] = make_float4(c.static_friction, c.dynamic_friction, c.restitution, __uint_as_float(c.flags & 15u));
-    CI[s] = make_int4(c.body, int(c.layer), int(c.domain), int(c.flags & 15u));
+    const float4 cs = make_float4(c.p0, c.p1, c.circle_r, __uint_as_float(c.kind));
+    const float4 cl = make_float4(c.x, c.y, c.rot_s, c.rot_b);
+    const float4 cm = make_float4(c.static_friction, c.dynamic_friction, c.restitution, __uint_as_float(c.flags & 15u));
+    const int4 ci = make_int4(c.body, int(c.layer), int(c.domain), int(c.flags & 15u));
+    CS[s] = cs; CL[s] = cl; CM[s] = cm; CI[s] = ci;
+    // the same four columns once more as ONE 64-byte record per collider: the per-pair kernels of the graph phase gather whole
+    // colliders at random (two per pair), and four 16-byte columns cost four half-used 32-byte sectors where the record costs two full ones
+    float4* r = CREC + size_t(s) * 4;
+    r[0] = cs; r[1] = cl; r[2] = cm; r[3] = make_float4(__int_as_float(ci.x), __int_as_float(ci.y), __int_as_float(ci.z), __int_as_float(ci.w));
 }
 __global__ void k_unpack_constraints(const SfgConstraint* in, uint32_t n, int4* KI, float4* KA, float4* KB) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,7 +584,7 @@ void sfg_world_destroy(SfgWorld* w) {
     cudaStreamSynchronize(w->stream);
     if (w->stream2) cudaStreamSynchronize(w->stream2);
     w->graveyard->bury_all();
-    DBuf<float4>* f4[] = {&w->P, &w->Q, &w->V, &w->OV, &w->MI, &w->CS, &w->CL, &w->CM, &w->AABB, &w->KA, &w->KB, &w->RPA, &w->RPB, &w->SA,
+    DBuf<float4>* f4[] = {&w->P, &w->Q, &w->V, &w->OV, &w->MI, &w->CS, &w->CL, &w->CM, &w->AABB, &w->CREC, &w->KA, &w->KB, &w->RPA, &w->RPB, &w->SA,
                           &w->H, &w->S, &w->G0, &w->G1, &w->L0, &w->L1, &w->M0, &w->M1, &w->M2, &w->K0, &w->K1, &w->K2};
     for (auto* b : f4) b->release();
     DBuf<float2>* f2[] = {&w->EA, &w->PCD, &w->LAT, &w->LN};
@@ -682,7 +687,7 @@ static int upload_colliders(SfgWorld* w, uint32_t first, uint32_t count, const S
     cudaStream_t st = w->stream;
     CK(w->stage.ensure(size_t(count) * sizeof(SfgCollider)));
     CK(cudaMemcpyAsync(w->stage.p, c, size_t(count) * sizeof(SfgCollider), cudaMemcpyHostToDevice, st));
-    k_unpack_colliders<<<nblk(count), 256, 0, st>>>((const SfgCollider*)w->stage.p, count, first, w->CS.p, w->CL.p, w->CM.p, w->CI.p);
+    k_unpack_colliders<<<nblk(count), 256, 0, st>>>((const SfgCollider*)w->stage.p, count, first, w->CS.p, w->CL.p, w->CM.p, w->CI.p, w->CREC.p);
     CKL(w);
     CK(cudaStreamSynchronize(st));
     return SFG_OK;
@@ -690,7 +695,7 @@ static int upload_colliders(SfgWorld* w, uint32_t first, uint32_t count, const S
 int sfg_set_colliders(SfgWorld* w, uint32_t n, const SfgCollider* c) {
     if (!w || (n && !c)) return SFG_E_INVALID;
     cudaSetDevice(w->device);
-    CK(w->CS.ensure(n)); CK(w->CL.ensure(n)); CK(w->CM.ensure(n)); CK(w->CI.ensure(n)); CK(w->AABB.ensure(n));
+    CK(w->CS.ensure(n)); CK(w->CL.ensure(n)); CK(w->CM.ensure(n)); CK(w->CI.ensure(n)); CK(w->AABB.ensure(n)); CK(w->CREC.ensure(size_t(n) * 4));
     w->n_colls = n;
     w->ticked = false;
     w->bouncy_seen = false;
@@ -938,7 +943,7 @@ int build_graph(SfgWorld* w) {
         const size_t nr = std::max<size_t>(n, size_t(w->n_live) * RESERVE_PAIRS_PER_COLLIDER);
         CK(w->U_ub.ensure(nr)); CK(w->U_prio.ensure(nr)); CK(w->U_cls.ensure(nr));
         CK(cudaMemsetAsync(w->deg.p, 0, size_t(nb + 2) * 4, st));
-        k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CI.p, w->MI.p, w->CS.p, w->CL.p, w->P.p, w->Q.p, w->V.p, w->frame_dt, w->U_ub.p, w->U_prio.p, w->deg.p, w->U_cls.p);
+        k_pair_unit_setup<<<nblk(n), 256, 0, st>>>(n, w->U_ids.p, w->CREC.p, w->MI.p, w->P.p, w->Q.p, w->V.p, w->frame_dt, w->U_ub.p, w->U_prio.p, w->deg.p, w->U_cls.p);
         CKL(w); w->launches++;
         uint32_t* perm = nullptr;
         int rc = colour_units(w, n, w->U_ids.p, w->U_ub.p, w->U_prio.p, w->U_colour, &perm, w->unit_colour_start, &w->n_unit_colours, true);
@@ -947,7 +952,7 @@ int build_graph(SfgWorld* w) {
         CK(w->H.ensure(nr)); CK(w->S.ensure(nr)); CK(w->G0.ensure(nr)); CK(w->G1.ensure(nr)); CK(w->L0.ensure(nr)); CK(w->L1.ensure(nr));
         CK(w->M0.ensure(nr * 2)); CK(w->M1.ensure(nr * 2)); CK(w->M2.ensure(nr * 2)); CK(w->LN.ensure(nr * 2));
         { int jr = join_islands(w); if (jr != SFG_OK) return jr; }
-        k_build_pair_units<<<nblk(n), 256, 0, st>>>(n, perm, w->U_ids.p, w->CS.p, w->CL.p, w->CM.p, w->CI.p, w->MI.p,
+        k_build_pair_units<<<nblk(n), 256, 0, st>>>(n, perm, w->U_ids.p, w->CREC.p, w->MI.p,
                                                     w->n_ropes ? w->rope_next.p : nullptr, w->n_ropes ? w->rope_prev.p : nullptr, w->H.p, w->S.p,
                                                     w->G0.p, w->G1.p, w->L0.p, w->L1.p, w->RC.p, w->tick_counts.p);
         CKL(w); w->launches++;

@@ -328,22 +328,28 @@ SFG_DI V2 collider_centre(int4 ci, float4 l, const float4* __restrict__ P, const
 // (include/sfg_hash.h) and the degree of its bodies. The priority's top bit is the `near` hint: the colliders' bounding
 // circles are closer than the bodies can come in one frame at their current relative speed (a hint, not a proof). Its
 // definition — sfg_near_hint, exactly rounded f32 — is shared with the CPU oracle, which computes it on its own.
-__global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const uint2* __restrict__ ids, const int4* __restrict__ CI,
-                                                         const float4* __restrict__ MI, const float4* __restrict__ CS,
-                                                         const float4* __restrict__ CL, const float4* __restrict__ P,
+SFG_DI int4 crec_ci(const float4* __restrict__ CREC, uint32_t slot) {
+    const float4 v = __ldg(CREC + size_t(slot) * 4 + 3);
+    return make_int4(__float_as_int(v.x), __float_as_int(v.y), __float_as_int(v.z), __float_as_int(v.w));
+}
+__global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const uint2* __restrict__ ids, const float4* __restrict__ CREC,
+                                                         const float4* __restrict__ MI, const float4* __restrict__ P,
                                                          const float4* __restrict__ Q, const float4* __restrict__ V, float frame_dt,
                                                          int2* __restrict__ ub, uint32_t* __restrict__ prio, uint32_t* __restrict__ deg,
                                                          uint8_t* __restrict__ ucls) {
     const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     const uint2 id = ids[u];
-    const int4 c0 = CI[id.x], c1 = CI[id.y];
+    // whole 64-byte collider records (sfg_api.cu k_unpack_colliders): (shape, local pose, material, ids)
+    const float4* r0 = CREC + size_t(id.x) * 4; const float4* r1 = CREC + size_t(id.y) * 4;
+    const float4 cs0 = __ldg(r0), cl0 = __ldg(r0 + 1), cs1 = __ldg(r1), cl1 = __ldg(r1 + 1);
+    const int4 c0 = crec_ci(CREC, id.x), c1 = crec_ci(CREC, id.y);
     int b0 = c0.x, b1 = c1.x;
     V2 v0 = mk(0.f, 0.f), v1 = v0;
     if (b0 >= 0) { const float4 v = V[b0]; v0 = mk(v.x, v.y); }
     if (b1 >= 0) { const float4 v = V[b1]; v1 = mk(v.x, v.y); }
-    const V2 t0 = collider_centre(c0, CL[id.x], P, Q), t1 = collider_centre(c1, CL[id.y], P, Q);
-    const Shape s0 = mkshape(CS[id.x]), s1 = mkshape(CS[id.y]);
+    const V2 t0 = collider_centre(c0, cl0, P, Q), t1 = collider_centre(c1, cl1, P, Q);
+    const Shape s0 = mkshape(cs0), s1 = mkshape(cs1);
     const bool near_hint = sfg_near_hint(t0.x, t0.y, sfg_bound_radius(s0.kind, s0.p0, s0.p1, s0.r), t1.x, t1.y, sfg_bound_radius(s1.kind, s1.p0, s1.p1, s1.r),
                                          v0.x, v0.y, v1.x, v1.y, frame_dt) != 0u;
     if (b0 >= 0 && !(__float_as_uint(MI[b0].z) & (BF_MASS | BF_INERTIA))) b0 = -1;
@@ -351,7 +357,7 @@ __global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const
     ub[u] = make_int2(b0, b1);
     prio[u] = sfg_pair_priority(id.x, id.y, near_hint ? 1u : 0u);
     {   // order inside a colour (k_unit_sort_keys): far units last, the rest grouped by narrowphase path and visit count
-        const uint32_t k0 = __float_as_uint(CS[id.x].w), k1 = __float_as_uint(CS[id.y].w);
+        const uint32_t k0 = s0.kind, k1 = s1.kind;
         uint32_t path;
         if (k0 == K_POINT && k1 == K_POINT) path = 0;
         else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
@@ -618,8 +624,7 @@ __global__ void __launch_bounds__(SFG_COLOUR_THREADS, SFG_COLOUR_BLOCKS) k_colou
 
 // after the stable sort by colour: write the streaming columns of each pair unit
 __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, const uint32_t* __restrict__ perm, const uint2* __restrict__ ids,
-                                                          const float4* __restrict__ CS, const float4* __restrict__ CL,
-                                                          const float4* __restrict__ CM, const int4* __restrict__ CI,
+                                                          const float4* __restrict__ CREC,
                                                           const float4* __restrict__ MI, const int* __restrict__ rope_next,
                                                           const int* __restrict__ rope_prev, float4* __restrict__ H, float4* __restrict__ S,
                                                           float4* __restrict__ G0, float4* __restrict__ G1, float4* __restrict__ L0,
@@ -629,13 +634,14 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
     uint2 id = make_uint2(0u, 0u);
     if (in) id = ids[perm[s]];
     {   // statistics: how many units are body-body pairs (visited twice per substep, physics.rs:641,651) -> counts[0]
-        const bool two = in && CI[id.x].x >= 0 && CI[id.y].x >= 0;
+        const bool two = in && __float_as_int(__ldg(CREC + size_t(id.x) * 4 + 3).x) >= 0 && __float_as_int(__ldg(CREC + size_t(id.y) * 4 + 3).x) >= 0;
         const uint32_t n2 = __syncthreads_count(two);
         if (threadIdx.x == 0 && n2) atomicAdd(counts, n2);
     }
     if (!in) return;
-    const int4 c0 = CI[id.x], c1 = CI[id.y];
-    const float4 m0 = CM[id.x], m1 = CM[id.y];
+    const float4* r0 = CREC + size_t(id.x) * 4; const float4* r1 = CREC + size_t(id.y) * 4;      // whole 64-byte collider records
+    const float4 g0 = __ldg(r0), l0 = __ldg(r0 + 1), m0 = __ldg(r0 + 2), g1 = __ldg(r1), l1 = __ldg(r1 + 1), m1 = __ldg(r1 + 2);
+    const int4 c0 = crec_ci(CREC, id.x), c1 = crec_ci(CREC, id.y);
     const uint32_t f0 = uint32_t(c0.w), f1 = uint32_t(c1.w);
     uint32_t fl = 0;
     if (c0.x >= 0 && c1.x >= 0) fl |= UF_MULT2;
@@ -656,7 +662,6 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
     }
     H[s] = make_float4(__int_as_float(c0.x), __int_as_float(c1.x), __uint_as_float(fl), (m0.x + m1.x) / 2.0f);
     S[s] = make_float4(__uint_as_float(id.x), __uint_as_float(id.y), (m0.y + m1.y) / 2.0f, fmaxf(m0.z, m1.z));
-    const float4 g0 = CS[id.x], g1 = CS[id.y], l0 = CL[id.x], l1 = CL[id.y];
     G0[s] = g0; G1[s] = g1;
     L0[s] = l0; L1[s] = l1;
     // bodies (or static collider origins) farther apart than this cannot touch: the colliders' bounding radii, never less
