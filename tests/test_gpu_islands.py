@@ -160,9 +160,10 @@ def test_switching_sleeping_off_wakes_everything():
     assert asleep.sum() > 0.5 * nb, "the stack did not fall asleep"
     g.set_tuning(abi.default_tuning(substeps=10, flags=abi.TUNE_NO_SLEEPING))
     # lift one sleeping box through the pose-only path (no flags are re-uploaded there)
-    victim = int(np.flatnonzero(asleep)[0])
+    cand = np.flatnonzero(asleep)
+    victim = int(cand[np.argmax(gb["y"][cand])])          # the highest sleeping body: nothing lies on top of it
     poses = g.get_poses()
-    poses[victim, 1] += 0.5
+    poses[victim, 1] += 1.0
     g.set_poses(poses[victim:victim + 1], first=victim)
     y0 = float(poses[victim, 1])
     for _ in range(5):
