@@ -198,6 +198,17 @@ int sfg_set_constraints(SfgWorld* w, uint32_t n, const SfgConstraint* constraint
 int sfg_set_ropes(SfgWorld* w, uint32_t n_ropes, const SfgRope* ropes, uint32_t n_particles,
                   const int32_t* particle_bodies);
 
+/* ---- rope topology edits without re-uploading the ropes (rope.rs:147-165 Rope::cut_after, :88-110 Rope::extend_line,
+ *      :226-286 RopeSet::remove_dead_particles). The library keeps one range per rope on the host and the particle -> body
+ *      array on the device; the solver's rope units are rebuilt on the device before the next tick. Ropes are addressed by their
+ *      index in the table (sfg_set_ropes order; new ropes are appended; sfg_rope_remove_dead_particles compacts the table and
+ *      reports its new size; sfg_get_ropes returns it). ---- */
+int sfg_rope_cut_after(SfgWorld* w, uint32_t rope, uint32_t particle_index, uint32_t* new_rope_out);   /* *new_rope_out = UINT32_MAX: the last particle was popped */
+int sfg_rope_extend(SfgWorld* w, uint32_t rope, uint32_t n_new, const int32_t* particle_bodies);
+int sfg_rope_remove_dead_particles(SfgWorld* w, uint32_t* n_ropes_out);
+int sfg_get_ropes(SfgWorld* w, SfgRope* ropes_out, uint32_t rope_capacity, uint32_t* n_ropes_out, int32_t* particle_bodies_out,
+                  uint32_t particle_capacity, uint32_t* n_particles_out);
+
 /* ---- PhysicsWorld::tick (physics.rs:396-1158) ---- */
 int sfg_tick(SfgWorld* w, double frame_dt, int has_time_scale, double time_scale, const SfgForceField* ff);
 /* The same tick in three calls, for callers that must act between substeps (slab halo exchange):
@@ -234,6 +245,10 @@ int sfg_get_contacts(SfgWorld* w, SfgContactInfo* out, size_t capacity, size_t* 
  *      poses: `count` rows of (x, y, rot_s, rot_b); velocities and masses are untouched. ---- */
 int sfg_set_poses(SfgWorld* w, uint32_t first_slot, uint32_t count, const float* poses_xysb);
 int sfg_get_poses(SfgWorld* w, uint32_t first_slot, uint32_t count, float* poses_xysb);
+/* The same for a LIST of body slots: HecsSyncManager only touches the entities whose HecsSyncOptions say hecs_to_physics /
+ * physics_to_hecs (hecs_sync.rs:149-158, 196-204), so only those poses cross the bus: n rows of (x, y, rot_s, rot_b) for slots[i]. */
+int sfg_set_poses_indexed(SfgWorld* w, uint32_t n, const uint32_t* slots, const float* poses_xysb);
+int sfg_get_poses_indexed(SfgWorld* w, uint32_t n, const uint32_t* slots, float* poses_xysb);
 /* Game::physics_tick in one call (game.rs:297-303): poses of ALL body slots in (NULL = keep the device's), sfg_tick, poses of
  * all body slots out (NULL = none). Same results as sfg_set_poses + sfg_tick + sfg_get_poses; the upload is queued in front of
  * the tick instead of being waited for and the download overlaps the end of the tick. Pinned host buffers make both copies

@@ -73,6 +73,9 @@ struct DBuf {
 // fresh memory, which showed up as a hitch every time a growing pile outgrew its buffers. ~330 B per reserved pair.
 constexpr size_t RESERVE_PAIRS_PER_COLLIDER = 6;
 
+// per rope, uploaded before k_rope_build: where the rope's particles sit and where its units go in the colour-major lists
+struct RopeBuildRec { uint32_t first, count, ru_off[3], rd_off[2], pad; };
+
 struct TickHeader {            // small device block read back once per tick phase
     Bounds bounds;
     uint32_t n_pairs;
@@ -119,7 +122,10 @@ struct SfgWorld {
     uint32_t rope_colour_start[4] = {0, 0, 0, 0}, damp_colour_start[3] = {0, 0, 0};
     DBuf<int4> RU, RD;
     DBuf<float4> RPA, RPB;
-    DBuf<int> rp_body, rp_rope;
+    DBuf<int> rp_body, rp_rope;      // particle array: body slot (-1 = hole left by an edit) and rope index of every particle
+    std::vector<SfgRope> rope_tab;   // host table: one range of the particle array + parameters per rope
+    bool ropes_dirty = false;        // the unit lists have to be rebuilt from (rope_tab, rp_body) before the next tick
+    DBuf<RopeBuildRec> rope_build;
     // staging
     DBuf<unsigned char> stage, stage2;   // stage2: pose read-back on the second stream (sfg_tick_poses)
     DBuf<unsigned long long> d_mask;
@@ -242,6 +248,21 @@ __global__ void k_set_poses(const float4* in, uint32_t n, uint32_t first, float4
     const float4 v = in[i];
     P[first + i] = make_float4(v.x, v.y, 0.f, 0.f);
     Q[first + i] = make_float4(v.z, v.w, v.z, v.w);
+}
+__global__ void k_set_poses_indexed(const float4* in, const uint32_t* slots, uint32_t n, float4* P, float4* Q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = in[i];
+    const uint32_t s = slots[i];
+    P[s] = make_float4(v.x, v.y, 0.f, 0.f);
+    Q[s] = make_float4(v.z, v.w, v.z, v.w);
+}
+__global__ void k_get_poses_indexed(float4* out, const uint32_t* slots, uint32_t n, const float4* P, const float4* Q) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = slots[i];
+    const float4 p = P[s], q = Q[s];
+    out[i] = make_float4(p.x + p.z, p.y + p.w, q.x, q.y);
 }
 __global__ void k_get_poses(float4* out, uint32_t n, uint32_t first, const float4* P, const float4* Q) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -402,6 +423,43 @@ __global__ void k_slab_unpack(const HaloRec* in, uint32_t cap, uint32_t nb, floa
     if (r.slot >= nb) return;
     P[r.slot] = r.P; Q[r.slot] = r.Q; V[r.slot] = r.V;
     stamp[r.slot] = epoch;
+}
+
+// ---- rope topology on the device (sfg_set_ropes' comment): one thread per slot of the particle array
+__global__ void k_rope_build(uint32_t n_slots, const int* __restrict__ rp_body, const int* __restrict__ rp_rope, const RopeBuildRec* __restrict__ recs,
+                             int4* __restrict__ RU, int4* __restrict__ RD, int* __restrict__ rope_next, int* __restrict__ rope_prev) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_slots) return;
+    const int r = rp_rope[p];
+    if (r < 0) return;                                   // a hole
+    const RopeBuildRec rec = recs[r];
+    const uint32_t i = p - rec.first;
+    if (i + 1 >= rec.count) return;                      // the last particle starts no link
+    const int cur = rp_body[p], nxt = rp_body[p + 1], aft = i + 2 < rec.count ? rp_body[p + 2] : -1;
+    RU[rec.ru_off[i % 3] + i / 3] = make_int4(cur, nxt, aft, r);
+    RD[rec.rd_off[i % 2] + i / 2] = make_int4(cur, nxt, r, 0);
+    rope_next[cur] = nxt; rope_prev[nxt] = cur;
+}
+__global__ void k_rope_assign(uint32_t first, uint32_t count, int rope, int* rp_rope) {      // a range of the particle array changes hands
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) rp_rope[first + i] = rope;
+}
+__global__ void k_rope_move(uint32_t from, uint32_t to, uint32_t count, int rope, int* rp_body, int* rp_rope) {   // to >= from + count (moves go to the end of the array)
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    rp_body[to + i] = rp_body[from + i]; rp_rope[to + i] = rope;
+    rp_body[from + i] = -1; rp_rope[from + i] = -1;
+}
+// rope.rs:226-286: which particles lost their body? appends their positions in the particle array to `out` (unordered)
+__global__ void k_rope_find_dead(uint32_t n_slots, const int* __restrict__ rp_body, const int* __restrict__ rp_rope, const float4* __restrict__ MI, uint32_t n_bodies,
+                                 uint32_t* count, uint32_t* out, uint32_t cap) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_slots || rp_rope[p] < 0) return;
+    const int b = rp_body[p];
+    const bool dead = b < 0 || uint32_t(b) >= n_bodies || !(__float_as_uint(MI[b].z) & BF_EXISTS);
+    if (!dead) return;
+    const uint32_t k = atomicAdd(count, 1u);
+    if (k < cap) out[k] = p;
 }
 
 // debug (SFG_DEBUG_NAN=1 with SFG_TUNE_SEPARATE_LAUNCHES): first body whose state is not finite after a stage
@@ -618,6 +676,7 @@ int sfg_world_clear(SfgWorld* w) {   // physics.rs:386-393
     if (w->stream2) cudaStreamSynchronize(w->stream2);
     w->graveyard->bury_all();            // outgrown buffers of the run that ends here (this world's only)
     w->n_bodies = w->n_colls = w->n_constraints = w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0;
+    w->rope_tab.clear(); w->ropes_dirty = false;
     w->n_units = w->n_kunits = 0;
     w->ct_n = 0; w->islands_valid = false;
     w->ticked = false;
@@ -656,7 +715,10 @@ int sfg_set_bodies(SfgWorld* w, uint32_t n, const SfgBody* b) {
     if (!w || (n && !b)) return SFG_E_INVALID;
     cudaSetDevice(w->device);
     CK(w->P.ensure(n)); CK(w->Q.ensure(n)); CK(w->V.ensure(n)); CK(w->OV.ensure(n)); CK(w->MI.ensure(n)); CK(w->EA.ensure(n));
-    if (n != w->n_bodies) { w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0; w->n_constraints = 0; }   // slot space changed: re-upload ropes / constraints
+    // a SHRINKING slot space may leave ropes / constraints pointing at slots that no longer exist: they have to be uploaded again.
+    // A growing one (the host spawned bodies, e.g. Rope::extend_line) keeps them; the per-body link tables are rebuilt at the new size
+    if (n < w->n_bodies) { w->n_ropes = w->n_particles = w->n_rope_units = w->n_rope_damp = 0; w->n_constraints = 0; w->rope_tab.clear(); w->ropes_dirty = false; }
+    else if (n > w->n_bodies && !w->rope_tab.empty()) w->ropes_dirty = true;
     if (n < w->n_bodies) { w->n_colls = 0; w->ticked = false; }   // colliders already uploaded may point at slots that no longer exist: they have to be re-uploaded too
     // a new slot space starts a new world as far as sleeping is concerned: no island is being watched, no contact retained.
     // (Re-uploading the same slots every tick, as the PhysicsWorld mirror does, keeps the records: physics.rs:711-741 only
@@ -729,57 +791,202 @@ int sfg_set_constraints(SfgWorld* w, uint32_t n, const SfgConstraint* c) {
     return SFG_OK;
 }
 
-// Rope topology is turned into colour-major unit lists on the host (it only changes when the host edits ropes):
-// step units (curr, next, after) coloured i mod 3 (solver.rs:118-179 touches particles i, i+1, i+2) and damping
-// pairs coloured i mod 2 (solver.rs:722-740).
+// Rope topology lives in two places: a small table of ranges on the host (one entry per rope: where its particles sit in the
+// device's particle array, and its parameters) and the particle array itself on the device (rp_body: particle -> body slot, -1 =
+// hole). Everything the solver reads — step units (curr, next, after) coloured i mod 3 (solver.rs:118-179 touches particles i,
+// i+1, i+2), damping pairs coloured i mod 2 (solver.rs:722-740), the next / prev links of the contact stage — is BUILT ON THE
+// DEVICE from those two (k_rope_build), lazily before the next tick. So a topology edit (cut, extend, dead-particle split:
+// sfg_rope_*) only changes the host table and a few device words; the particle array is never re-uploaded.
 int sfg_set_ropes(SfgWorld* w, uint32_t n_ropes, const SfgRope* ropes, uint32_t n_particles, const int32_t* particle_bodies) {
     if (!w || (n_ropes && (!ropes || !particle_bodies))) return SFG_E_INVALID;
     cudaSetDevice(w->device);
     cudaStream_t st = w->stream;
-    std::vector<int4> ru[3], rd[2];
-    std::vector<float4> pa(n_ropes), pb(n_ropes);
-    std::vector<int> rp_rope(n_particles, 0), next(w->n_bodies, -1), prev(w->n_bodies, -1);
+    std::vector<int> rp_rope(n_particles, -1);
+    std::vector<int> rp_body(n_particles, -1);
     for (uint32_t r = 0; r < n_ropes; ++r) {
         const SfgRope& rp = ropes[r];
         if (rp.particle_count < 2) return fail(w, SFG_E_INVALID, "Rope only had one particle");   // solver.rs:120 panics
         if (uint64_t(rp.first_particle) + rp.particle_count > n_particles) return fail(w, SFG_E_INVALID, "rope particle range out of bounds");
-        pa[r] = make_float4(rp.spacing, rp.compliance, rp.bending_max_angle, rp.bending_compliance);
-        pb[r] = make_float4(rp.damping, 0.f, 0.f, 0.f);
         const int32_t* p = particle_bodies + rp.first_particle;
         for (uint32_t i = 0; i < rp.particle_count; ++i) {
             if (p[i] < 0 || uint32_t(p[i]) >= w->n_bodies) return fail(w, SFG_E_INVALID, "rope particle body slot out of range");
+            if (rp_rope[rp.first_particle + i] >= 0) return fail(w, SFG_E_INVALID, "rope particle ranges overlap");
             rp_rope[rp.first_particle + i] = int(r);
-            if (i + 1 < rp.particle_count) {
-                next[p[i]] = p[i + 1]; prev[p[i + 1]] = p[i];
-                ru[i % 3].push_back(make_int4(p[i], p[i + 1], i + 2 < rp.particle_count ? p[i + 2] : -1, int(r)));
-                rd[i % 2].push_back(make_int4(p[i], p[i + 1], int(r), 0));
-            }
+            rp_body[rp.first_particle + i] = p[i];
         }
     }
-    std::vector<int4> ru_all, rd_all;
-    for (int c = 0; c < 3; ++c) { w->rope_colour_start[c] = uint32_t(ru_all.size()); ru_all.insert(ru_all.end(), ru[c].begin(), ru[c].end()); }
-    w->rope_colour_start[3] = uint32_t(ru_all.size());
-    for (int c = 0; c < 2; ++c) { w->damp_colour_start[c] = uint32_t(rd_all.size()); rd_all.insert(rd_all.end(), rd[c].begin(), rd[c].end()); }
-    w->damp_colour_start[2] = uint32_t(rd_all.size());
+    w->rope_tab.assign(ropes, ropes + n_ropes);
     w->n_ropes = n_ropes; w->n_particles = n_particles;
-    w->n_rope_units = uint32_t(ru_all.size()); w->n_rope_damp = uint32_t(rd_all.size());
-    CK(w->rope_next.ensure(w->n_bodies + 1)); CK(w->rope_prev.ensure(w->n_bodies + 1));
-    if (w->n_bodies) {
-        CK(cudaMemcpyAsync(w->rope_next.p, next.data(), size_t(w->n_bodies) * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(w->rope_prev.p, prev.data(), size_t(w->n_bodies) * 4, cudaMemcpyHostToDevice, st));
-    }
-    if (n_ropes) {
-        CK(w->RU.ensure(ru_all.size())); CK(w->RD.ensure(rd_all.size())); CK(w->RPA.ensure(n_ropes)); CK(w->RPB.ensure(n_ropes));
+    w->n_rope_units = w->n_rope_damp = 0;
+    w->ropes_dirty = true;
+    if (n_particles) {
         CK(w->rp_body.ensure(n_particles)); CK(w->rp_rope.ensure(n_particles));
-        CK(w->PCD.ensure(w->n_bodies)); CK(w->LAT.ensure(w->n_bodies));
-        CK(cudaMemcpyAsync(w->RU.p, ru_all.data(), ru_all.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(w->RD.p, rd_all.data(), rd_all.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(w->RPA.p, pa.data(), size_t(n_ropes) * sizeof(float4), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(w->RPB.p, pb.data(), size_t(n_ropes) * sizeof(float4), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(w->rp_body.p, particle_bodies, size_t(n_particles) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w->rp_body.p, rp_body.data(), size_t(n_particles) * 4, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(w->rp_rope.p, rp_rope.data(), size_t(n_particles) * 4, cudaMemcpyHostToDevice, st));
     }
     CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+// Rope::cut_after (rope.rs:147-165), by position: the rope keeps particles [0, particle_index], the rest becomes a NEW rope with
+// the same parameters, appended to the rope table (*new_rope_out = its index). Cutting after the last particle removes that
+// particle from the rope (`self.particles.pop()`) and creates nothing (*new_rope_out = UINT32_MAX). No particle data moves.
+int sfg_rope_cut_after(SfgWorld* w, uint32_t rope, uint32_t particle_index, uint32_t* new_rope_out) {
+    if (!w) return SFG_E_INVALID;
+    if (new_rope_out) *new_rope_out = 0xFFFFFFFFu;
+    if (rope >= w->rope_tab.size()) return fail(w, SFG_E_INVALID, "rope index out of range");
+    SfgRope& r = w->rope_tab[rope];
+    if (particle_index >= r.particle_count) return fail(w, SFG_E_INVALID, "particle index beyond the rope");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    if (particle_index + 1 == r.particle_count) {
+        k_rope_assign<<<1, 32, 0, st>>>(r.first_particle + particle_index, 1, -1, w->rp_rope.p);    // the popped particle leaves the rope (its body lives on)
+        CKL(w);
+        r.particle_count -= 1;
+    } else {
+        SfgRope tail = r;
+        tail.first_particle = r.first_particle + particle_index + 1;
+        tail.particle_count = r.particle_count - particle_index - 1;
+        r.particle_count = particle_index + 1;
+        const uint32_t idx = uint32_t(w->rope_tab.size());
+        k_rope_assign<<<nblk(tail.particle_count), 256, 0, st>>>(tail.first_particle, tail.particle_count, int(idx), w->rp_rope.p);
+        CKL(w);
+        w->rope_tab.push_back(tail);          // (invalidates r)
+        if (new_rope_out) *new_rope_out = idx;
+    }
+    w->n_ropes = uint32_t(w->rope_tab.size());
+    w->ropes_dirty = true;
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+// Rope::extend_line (rope.rs:88-110): the host spawned `n_new` particle bodies (Rope::build_line) and uploaded them with the
+// bodies / colliders; here their slots are appended to the rope. A rope that is not the last range of the particle array is
+// moved to its end first (a device copy), so only the n_new slots cross the bus.
+int sfg_rope_extend(SfgWorld* w, uint32_t rope, uint32_t n_new, const int32_t* particle_bodies) {
+    if (!w || (n_new && !particle_bodies)) return SFG_E_INVALID;
+    if (rope >= w->rope_tab.size()) return fail(w, SFG_E_INVALID, "rope index out of range");
+    if (n_new == 0) return SFG_OK;
+    for (uint32_t i = 0; i < n_new; ++i)
+        if (particle_bodies[i] < 0 || uint32_t(particle_bodies[i]) >= w->n_bodies) return fail(w, SFG_E_INVALID, "rope particle body slot out of range (set bodies first)");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    SfgRope& r = w->rope_tab[rope];
+    const bool at_end = r.first_particle + r.particle_count == w->n_particles;
+    const uint32_t new_len = at_end ? w->n_particles + n_new : w->n_particles + r.particle_count + n_new;
+    if (new_len > w->rp_body.cap) {          // grow both columns, keeping their contents
+        DBuf<int> nb, nr;
+        nb.yard = w->graveyard; nr.yard = w->graveyard;
+        CK(nb.ensure(size_t(new_len) * 2)); CK(nr.ensure(size_t(new_len) * 2));
+        if (w->n_particles) {
+            CK(cudaMemcpyAsync(nb.p, w->rp_body.p, size_t(w->n_particles) * 4, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpyAsync(nr.p, w->rp_rope.p, size_t(w->n_particles) * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        CK(cudaStreamSynchronize(st));
+        std::swap(w->rp_body.p, nb.p); std::swap(w->rp_body.cap, nb.cap);
+        std::swap(w->rp_rope.p, nr.p); std::swap(w->rp_rope.cap, nr.cap);
+        if (nb.p) { w->graveyard->add(nb.p); nb.p = nullptr; nb.cap = 0; }      // never cudaFree in the middle of a run (DBuf's comment)
+        if (nr.p) { w->graveyard->add(nr.p); nr.p = nullptr; nr.cap = 0; }
+    }
+    if (!at_end) {
+        k_rope_move<<<nblk(r.particle_count), 256, 0, st>>>(r.first_particle, w->n_particles, r.particle_count, int(rope), w->rp_body.p, w->rp_rope.p);
+        CKL(w);
+        r.first_particle = w->n_particles;
+    }
+    CK(cudaMemcpyAsync(w->rp_body.p + r.first_particle + r.particle_count, particle_bodies, size_t(n_new) * 4, cudaMemcpyHostToDevice, st));
+    k_rope_assign<<<nblk(n_new), 256, 0, st>>>(r.first_particle + r.particle_count, n_new, int(rope), w->rp_rope.p);
+    CKL(w);
+    r.particle_count += n_new;
+    w->n_particles = new_len;
+    w->ropes_dirty = true;
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+// RopeSet::remove_dead_particles (rope.rs:226-286) against the bodies the device holds: a particle whose body slot is no longer
+// alive is taken out of its rope and the rope is cut there; runs of dead particles are skipped; the first surviving piece keeps
+// the rope's index, later pieces are appended as new ropes in the order the reference creates them; ropes left with no particle
+// are deleted (the indices above them shift down, as thunderdome's iteration order does not matter to the solver). The device
+// reports only the positions of the dead particles — a few words — and nothing is re-uploaded.
+int sfg_rope_remove_dead_particles(SfgWorld* w, uint32_t* n_ropes_out) {
+    if (!w) return SFG_E_INVALID;
+    if (n_ropes_out) *n_ropes_out = uint32_t(w->rope_tab.size());
+    if (w->rope_tab.empty() || w->n_particles == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    const uint32_t cap = 65536;
+    CK(w->stage.ensure(size_t(cap + 1) * 4));
+    uint32_t* cnt = (uint32_t*)w->stage.p;
+    CK(cudaMemsetAsync(cnt, 0, 4, st));
+    k_rope_find_dead<<<nblk(w->n_particles), 256, 0, st>>>(w->n_particles, w->rp_body.p, w->rp_rope.p, w->MI.p, w->n_bodies, cnt, cnt + 1, cap);
+    CKL(w);
+    uint32_t n_dead = 0;
+    CK(cudaMemcpyAsync(&n_dead, cnt, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_dead == 0) return SFG_OK;
+    if (n_dead > cap) return fail(w, SFG_E_CAPACITY, "more than 65536 rope particles died at once: upload the ropes again (sfg_set_ropes)");
+    std::vector<uint32_t> dead(n_dead);
+    CK(cudaMemcpyAsync(dead.data(), cnt + 1, size_t(n_dead) * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::sort(dead.begin(), dead.end());
+    std::vector<SfgRope> fresh;
+    const size_t n_old = w->rope_tab.size();
+    for (size_t ri = 0; ri < n_old; ++ri) {
+        SfgRope& r = w->rope_tab[ri];
+        const uint32_t lo = r.first_particle, hi = r.first_particle + r.particle_count;
+        auto d0 = std::lower_bound(dead.begin(), dead.end(), lo), d1 = std::lower_bound(dead.begin(), dead.end(), hi);
+        if (d0 == d1) continue;
+        // live runs of [lo, hi) between the dead positions: the first one (possibly empty) stays in this rope, every later
+        // non-empty one becomes a new rope (rope.rs:241-268)
+        uint32_t run_start = lo;
+        bool first = true;
+        auto piece = [&](uint32_t a, uint32_t b) {
+            if (first) { r.particle_count = b - a; r.first_particle = a; first = false; return; }
+            if (b > a) { SfgRope t = r; t.first_particle = a; t.particle_count = b - a; fresh.push_back(t); }
+        };
+        for (auto d = d0; d != d1; ++d) { piece(run_start, *d); run_start = *d + 1; }
+        piece(run_start, hi);
+    }
+    for (const SfgRope& t : fresh) w->rope_tab.push_back(t);
+    // delete empty ropes (rope.rs:275-285); a rope left with ONE particle stays, and the next tick reports the reference's panic
+    std::vector<SfgRope> kept;
+    for (const SfgRope& r : w->rope_tab) if (r.particle_count > 0) kept.push_back(r);
+    w->rope_tab.swap(kept);
+    // the particle array: dead slots become holes, every piece is re-labelled with its rope's (new) index
+    for (uint32_t d : dead) { k_rope_assign<<<1, 32, 0, st>>>(d, 1, -1, w->rp_rope.p); CKL(w); }
+    for (size_t ri = 0; ri < w->rope_tab.size(); ++ri) {
+        const SfgRope& r = w->rope_tab[ri];
+        k_rope_assign<<<nblk(r.particle_count), 256, 0, st>>>(r.first_particle, r.particle_count, int(ri), w->rp_rope.p);
+        CKL(w);
+    }
+    w->n_ropes = uint32_t(w->rope_tab.size());
+    w->ropes_dirty = true;
+    if (n_ropes_out) *n_ropes_out = w->n_ropes;
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+// The rope table as the library holds it now, compacted: ropes_out[i].first_particle indexes particle_bodies_out (holes removed).
+int sfg_get_ropes(SfgWorld* w, SfgRope* ropes_out, uint32_t rope_capacity, uint32_t* n_ropes_out, int32_t* particle_bodies_out, uint32_t particle_capacity,
+                  uint32_t* n_particles_out) {
+    if (!w || !n_ropes_out || !n_particles_out) return SFG_E_INVALID;
+    uint32_t total = 0;
+    for (const SfgRope& r : w->rope_tab) total += r.particle_count;
+    *n_ropes_out = uint32_t(w->rope_tab.size()); *n_particles_out = total;
+    if (!ropes_out || !particle_bodies_out) return SFG_OK;
+    if (rope_capacity < w->rope_tab.size() || particle_capacity < total) return fail(w, SFG_E_CAPACITY, "sfg_get_ropes: output buffers too small");
+    cudaSetDevice(w->device);
+    std::vector<int32_t> all(w->n_particles);
+    if (w->n_particles) {
+        CK(cudaMemcpyAsync(all.data(), w->rp_body.p, size_t(w->n_particles) * 4, cudaMemcpyDeviceToHost, w->stream));
+        CK(cudaStreamSynchronize(w->stream));
+    }
+    uint32_t o = 0;
+    for (size_t i = 0; i < w->rope_tab.size(); ++i) {
+        const SfgRope& r = w->rope_tab[i];
+        ropes_out[i] = r; ropes_out[i].first_particle = o;
+        for (uint32_t k = 0; k < r.particle_count; ++k) particle_bodies_out[o++] = all[r.first_particle + k];
+    }
     return SFG_OK;
 }
 
@@ -831,6 +1038,57 @@ void choose_grid(SfgWorld* w, const Bounds& b) {
         }
         c0 *= 1.5;
     }
+}
+
+// (rope_tab, rp_body) -> RU / RD / rope_next / rope_prev / per-rope parameters, all on the device (sfg_set_ropes' comment)
+int rebuild_rope_units(SfgWorld* w) {
+    cudaStream_t st = w->stream;
+    w->ropes_dirty = false;
+    const uint32_t nr = uint32_t(w->rope_tab.size());
+    w->n_ropes = nr;
+    w->n_rope_units = w->n_rope_damp = 0;
+    for (int c = 0; c < 4; ++c) w->rope_colour_start[c] = 0;
+    for (int c = 0; c < 3; ++c) w->damp_colour_start[c] = 0;
+    CK(w->rope_next.ensure(w->n_bodies + 1)); CK(w->rope_prev.ensure(w->n_bodies + 1));
+    if (w->n_bodies) {
+        CK(cudaMemsetAsync(w->rope_next.p, 0xFF, size_t(w->n_bodies) * 4, st));
+        CK(cudaMemsetAsync(w->rope_prev.p, 0xFF, size_t(w->n_bodies) * 4, st));
+    }
+    if (nr == 0) { w->n_particles = 0; return SFG_OK; }
+    std::vector<RopeBuildRec> recs(nr);
+    std::vector<float4> pa(nr), pb(nr);
+    uint32_t ru_n[3] = {0, 0, 0}, rd_n[2] = {0, 0};
+    for (uint32_t r = 0; r < nr; ++r) {
+        const SfgRope& rp = w->rope_tab[r];
+        if (rp.particle_count < 2) return fail(w, SFG_E_INVALID, "Rope only had one particle");   // solver.rs:120 panics
+        if (uint64_t(rp.first_particle) + rp.particle_count > w->n_particles) return fail(w, SFG_E_STATE, "rope table out of step with the particle array");
+        const uint32_t links = rp.particle_count - 1;
+        for (uint32_t c = 0; c < 3; ++c) ru_n[c] += links > c ? (links - c + 2) / 3 : 0;
+        for (uint32_t c = 0; c < 2; ++c) rd_n[c] += links > c ? (links - c + 1) / 2 : 0;
+    }
+    w->rope_colour_start[0] = 0; w->rope_colour_start[1] = ru_n[0]; w->rope_colour_start[2] = ru_n[0] + ru_n[1]; w->rope_colour_start[3] = ru_n[0] + ru_n[1] + ru_n[2];
+    w->damp_colour_start[0] = 0; w->damp_colour_start[1] = rd_n[0]; w->damp_colour_start[2] = rd_n[0] + rd_n[1];
+    uint32_t ru_cur[3] = {w->rope_colour_start[0], w->rope_colour_start[1], w->rope_colour_start[2]}, rd_cur[2] = {w->damp_colour_start[0], w->damp_colour_start[1]};
+    for (uint32_t r = 0; r < nr; ++r) {
+        const SfgRope& rp = w->rope_tab[r];
+        const uint32_t links = rp.particle_count - 1;
+        RopeBuildRec& o = recs[r];
+        o.first = rp.first_particle; o.count = rp.particle_count; o.pad = 0;
+        for (uint32_t c = 0; c < 3; ++c) { o.ru_off[c] = ru_cur[c]; ru_cur[c] += links > c ? (links - c + 2) / 3 : 0; }
+        for (uint32_t c = 0; c < 2; ++c) { o.rd_off[c] = rd_cur[c]; rd_cur[c] += links > c ? (links - c + 1) / 2 : 0; }
+        pa[r] = make_float4(rp.spacing, rp.compliance, rp.bending_max_angle, rp.bending_compliance);
+        pb[r] = make_float4(rp.damping, 0.f, 0.f, 0.f);
+    }
+    w->n_rope_units = w->rope_colour_start[3]; w->n_rope_damp = w->damp_colour_start[2];
+    CK(w->RU.ensure(w->n_rope_units + 1)); CK(w->RD.ensure(w->n_rope_damp + 1)); CK(w->RPA.ensure(nr)); CK(w->RPB.ensure(nr)); CK(w->rope_build.ensure(nr));
+    CK(w->PCD.ensure(w->n_bodies)); CK(w->LAT.ensure(w->n_bodies));
+    CK(cudaMemcpyAsync(w->rope_build.p, recs.data(), size_t(nr) * sizeof(RopeBuildRec), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w->RPA.p, pa.data(), size_t(nr) * sizeof(float4), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w->RPB.p, pb.data(), size_t(nr) * sizeof(float4), cudaMemcpyHostToDevice, st));
+    k_rope_build<<<nblk(w->n_particles), 256, 0, st>>>(w->n_particles, w->rp_body.p, w->rp_rope.p, w->rope_build.p, w->RU.p, w->RD.p, w->rope_next.p, w->rope_prev.p);
+    CKL(w);
+    CK(cudaStreamSynchronize(st));        // recs / pa / pb are stack-lifetime host buffers
+    return SFG_OK;
 }
 
 template <uint32_t KIND>
@@ -1122,6 +1380,7 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     w->launches = 0;
     w->islands_in_flight = false;
     w->frame_dt = float(frame_dt);
+    if (w->ropes_dirty) { rc = rebuild_rope_units(w); if (rc != SFG_OK) return rc; }
     CK(cudaEventRecord(w->ev[0], st));
     CK(cudaMemsetAsync(w->tick_counts.p, 0, 4 * sizeof(uint32_t), st));
     if (w->n_bodies) CK(cudaMemsetAsync(w->EA.p, 0, size_t(w->n_bodies) * sizeof(float2), st));
@@ -1461,6 +1720,38 @@ int sfg_get_poses(SfgWorld* w, uint32_t first, uint32_t count, float* poses) {
     k_get_poses<<<nblk(count), 256, 0, st>>>((float4*)w->stage.p, count, first, w->P.p, w->Q.p);
     CKL(w);
     CK(cudaMemcpyAsync(poses, w->stage.p, size_t(count) * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+
+// pose sync for a list of slots (HecsSyncManager syncs only the entities whose options ask for that direction)
+int sfg_set_poses_indexed(SfgWorld* w, uint32_t n, const uint32_t* slots, const float* poses) {
+    if (!w || (n && (!slots || !poses))) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    for (uint32_t i = 0; i < n; ++i) if (slots[i] >= w->n_bodies) return fail(w, SFG_E_INVALID, "body slot out of range");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(n) * 20));
+    float4* d_pose = (float4*)w->stage.p; uint32_t* d_slot = (uint32_t*)(w->stage.p + size_t(n) * 16);
+    CK(cudaMemcpyAsync(d_pose, poses, size_t(n) * 16, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_slot, slots, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+    k_set_poses_indexed<<<nblk(n), 256, 0, st>>>(d_pose, d_slot, n, w->P.p, w->Q.p);
+    CKL(w);
+    CK(cudaStreamSynchronize(st));
+    return SFG_OK;
+}
+int sfg_get_poses_indexed(SfgWorld* w, uint32_t n, const uint32_t* slots, float* poses) {
+    if (!w || (n && (!slots || !poses))) return SFG_E_INVALID;
+    if (n == 0) return SFG_OK;
+    for (uint32_t i = 0; i < n; ++i) if (slots[i] >= w->n_bodies) return fail(w, SFG_E_INVALID, "body slot out of range");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    CK(w->stage.ensure(size_t(n) * 20));
+    float4* d_pose = (float4*)w->stage.p; uint32_t* d_slot = (uint32_t*)(w->stage.p + size_t(n) * 16);
+    CK(cudaMemcpyAsync(d_slot, slots, size_t(n) * 4, cudaMemcpyHostToDevice, st));
+    k_get_poses_indexed<<<nblk(n), 256, 0, st>>>(d_pose, d_slot, n, w->P.p, w->Q.p);
+    CKL(w);
+    CK(cudaMemcpyAsync(poses, d_pose, size_t(n) * 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return SFG_OK;
 }

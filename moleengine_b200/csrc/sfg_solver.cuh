@@ -117,6 +117,7 @@ SFG_DI void stage_rope_damp(const SolverCtx& c, uint32_t u) {
 }
 // solver.rs:750-765, one thread per rope particle
 SFG_DI void stage_rope_lateral(const SolverCtx& c, uint32_t p) {
+    if (c.rp_rope[p] < 0) return;              // a hole in the particle array (left by a topology edit, sfg_api.cu sfg_rope_*)
     const int b = c.rp_body[p];
     float2 corr = ldb(c.LAT + b);
     if (isnan(corr.x)) return;
@@ -139,6 +140,7 @@ SFG_DI void stage_rope_lateral(const SolverCtx& c, uint32_t p) {
 }
 // pre_contact_poses (solver.rs:83-85), only rope particles ever read them (solver.rs:337-362)
 SFG_DI void stage_precontact(const SolverCtx& c, uint32_t p) {
+    if (c.rp_rope[p] < 0) return;
     const int b = c.rp_body[p];
     float4 pp = ldb(c.P + b);
     stb(c.PCD + b, make_float2(pp.z, pp.w));

@@ -74,6 +74,31 @@ class GpuWorld:
         self._ck(self.lib.sfg_set_ropes(self.h, len(ropes), abi.ptr(ropes) if len(ropes) else None, len(pb),
                                         abi.ptr(pb) if len(pb) else None))
 
+    # ---- rope topology edits on the device (rope.rs:147-165, 88-110, 226-286) ------------------------------
+    def rope_cut_after(self, rope, particle_index):
+        """-> index of the new rope holding the tail, or None if the last particle was popped."""
+        out = C.c_uint32()
+        self._ck(self.lib.sfg_rope_cut_after(self.h, rope, particle_index, C.byref(out)))
+        return None if out.value == 0xFFFFFFFF else out.value
+
+    def rope_extend(self, rope, particle_bodies):
+        pb = np.ascontiguousarray(particle_bodies, dtype=np.int32)
+        self._ck(self.lib.sfg_rope_extend(self.h, rope, len(pb), abi.ptr(pb)))
+
+    def rope_remove_dead_particles(self):
+        n = C.c_uint32()
+        self._ck(self.lib.sfg_rope_remove_dead_particles(self.h, C.byref(n)))
+        return n.value
+
+    def get_ropes(self):
+        """-> (ropes, particle_bodies) as the library holds them now (compacted)."""
+        nr, npart = C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.sfg_get_ropes(self.h, None, 0, C.byref(nr), None, 0, C.byref(npart)))
+        ropes, pb = np.zeros(nr.value, abi.rope_dtype), np.zeros(npart.value, np.int32)
+        if nr.value:
+            self._ck(self.lib.sfg_get_ropes(self.h, abi.ptr(ropes), nr.value, C.byref(nr), abi.ptr(pb), npart.value, C.byref(npart)))
+        return ropes, pb
+
     def load_scene(self, scene):
         """scene: dict with bodies / colliders / constraints / ropes / rope_particles (see scenes.py)."""
         self.set_bodies(scene["bodies"])
@@ -130,6 +155,19 @@ class GpuWorld:
         count = self.n_bodies - first if count is None else count
         out = np.zeros((count, 4), np.float32) if out is None else out
         self._ck(self.lib.sfg_get_poses(self.h, first, count, abi.ptr(out)))
+        return out
+
+    def set_poses_indexed(self, slots, poses):
+        """Poses of the listed body slots only (HecsSyncManager: entities whose options say hecs_to_physics)."""
+        sl = np.ascontiguousarray(slots, np.uint32)
+        p = np.ascontiguousarray(poses, np.float32).reshape(-1, 4)
+        assert len(sl) == len(p)
+        self._ck(self.lib.sfg_set_poses_indexed(self.h, len(sl), abi.ptr(sl), abi.ptr(p)))
+
+    def get_poses_indexed(self, slots):
+        sl = np.ascontiguousarray(slots, np.uint32)
+        out = np.zeros((len(sl), 4), np.float32)
+        self._ck(self.lib.sfg_get_poses_indexed(self.h, len(sl), abi.ptr(sl), abi.ptr(out)))
         return out
 
     def tick_poses(self, poses_in=None, frame_dt=1.0 / 60.0, time_scale=None, forcefield=None, out=None):
