@@ -1,3 +1,2 @@
 set -x
-python -m pytest tests -m gpu -q > gpurun_out/r02c_pytest.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/r02c_pytest.log
-python tools/diag_settled.py c3 300 gpurun_out/t.bin > gpurun_out/r02c_settled.json 2>&1; rm -f gpurun_out/t.bin; cat gpurun_out/r02c_settled.json
+python -m pytest tests/test_gpu_rope_edits.py tests/test_gpu_islands.py tests/test_gpu_scenes.py tests/test_gpu_slab.py tests/test_gpu_longrun.py -m gpu -q > gpurun_out/r02d_pytest.log 2>&1; echo "pytest rc=$?"; tail -40 gpurun_out/r02d_pytest.log
