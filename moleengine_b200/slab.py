@@ -198,3 +198,85 @@ def tick_island_shards_local(drivers, frame_dt=1.0 / 60.0, forcefield=None):
             d.recv[src.rank * words:(src.rank + 1) * words].copy_(src.send)
     for d in drivers:
         d.unpack()
+
+
+# ---------------------------------------------------------------- ray batches over slabs (physics.rs:1255-1311)
+# Every rank knows the colliders of its own bodies, of the ghosts within `halo` of its cuts and every static collider, all at
+# their true poses. A ray is therefore sent to the slabs its swept segment crosses; each of them reports its first hit, and the
+# first hit of the world is the minimum over those reports: min t, ties to the lowest collider slot — the rule of the
+# single-world cast (sfg_cast.cuh). A ghost and its owner report the same hit; the lower rank's copy is kept.
+def route_rays(rays, lo, hi):
+    """Boolean mask: rays whose swept x-interval [min(x0, x1) - radius, max(x0, x1) + radius] meets the slab [lo, hi)."""
+    import numpy as np
+    x0 = rays["sx"].astype(np.float64)
+    x1 = x0 + rays["dx"].astype(np.float64) * rays["max_distance"].astype(np.float64)
+    r = rays["radius"].astype(np.float64)
+    return (np.minimum(x0, x1) - r < hi) & (np.maximum(x0, x1) + r >= lo)
+
+
+def hit_keys(hits):
+    """Sort key of a hit: (t as ordered bits) << 32 | collider slot; a miss is the largest key."""
+    import numpy as np
+    t = np.ascontiguousarray(hits["t"], np.float32).view(np.uint32).astype(np.uint64)       # non-negative floats order like their bits
+    key = (t << np.uint64(32)) | hits["collider"].astype(np.int64).astype(np.uint64) & np.uint64(0xFFFFFFFF)
+    return np.where(hits["collider"] >= 0, key, np.uint64(0xFFFFFFFFFFFFFFFF))
+
+
+def merge_hits(per_rank_hits):
+    """First hit of the world from every slab's report (numpy; the in-process form of SlabDriver.cast's reduction)."""
+    import numpy as np
+    keys = np.stack([hit_keys(h) for h in per_rank_hits])
+    win = keys.argmin(0)                         # argmin returns the FIRST minimum: the lowest rank among equal reports
+    out = per_rank_hits[0].copy()
+    for r, h in enumerate(per_rank_hits):
+        sel = win == r
+        out[sel] = h[sel]
+    return out
+
+
+def cast_local(drivers, rays):
+    """All slabs in one process (tests): route, cast on every slab's world, merge."""
+    import numpy as np
+    from . import abi
+    reports = []
+    for d in drivers:
+        hits = np.zeros(len(rays), abi.hit_dtype)
+        hits["collider"] = -1
+        m = route_rays(rays, d.lo, d.hi)
+        if m.any():
+            hits[m] = d.world.cast_batch(np.ascontiguousarray(rays[m]))
+        reports.append(hits)
+    return merge_hits(reports), [int(route_rays(rays, d.lo, d.hi).sum()) for d in drivers]
+
+
+def cast_distributed(driver, rays, group=None, device=None):
+    """One rank of a slab-decomposed world: cast the rays routed to this slab, then reduce over the ranks (three small
+    all-reduces: the winning key, the winning rank, the winner's payload). Every rank passes the same `rays` and gets all hits."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import abi
+    hits = np.zeros(len(rays), abi.hit_dtype)
+    hits["collider"] = -1
+    m = route_rays(rays, driver.lo, driver.hi)
+    if m.any():
+        hits[m] = driver.world.cast_batch(np.ascontiguousarray(rays[m]))
+    key = torch.from_numpy(hit_keys(hits).view(np.int64) ^ np.int64(-2 ** 63)).to(device)      # unsigned order -> signed order
+    best = key.clone()
+    dist.all_reduce(best, op=dist.ReduceOp.MIN, group=group)
+    who = torch.where(key == best, torch.full_like(key, driver.rank), torch.full_like(key, 1 << 30))
+    dist.all_reduce(who, op=dist.ReduceOp.MIN, group=group)
+    mine = (who == driver.rank).cpu().numpy()
+    payload = np.zeros((len(rays), 6), np.float32)
+    for k, f in enumerate(("t", "px", "py", "nx", "ny")):
+        payload[mine, k] = hits[f][mine]
+    payload[mine, 5] = hits["collider"][mine].astype(np.float32)        # exact below 2^24 slots; the key carries the exact slot
+    p = torch.from_numpy(payload).to(device)
+    dist.all_reduce(p, op=dist.ReduceOp.SUM, group=group)
+    p = p.cpu().numpy()
+    out = np.zeros(len(rays), abi.hit_dtype)
+    bestk = (best.cpu().numpy() ^ np.int64(-2 ** 63)).view(np.uint64)
+    out["collider"] = np.where(bestk == np.uint64(0xFFFFFFFFFFFFFFFF), -1, (bestk & np.uint64(0xFFFFFFFF)).astype(np.int64)).astype(np.int32)
+    for k, f in enumerate(("t", "px", "py", "nx", "ny")):
+        out[f] = p[:, k]
+    return out

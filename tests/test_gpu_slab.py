@@ -193,3 +193,55 @@ def test_ropes_and_attachments_across_a_cut():
     assert sum(d.sent_records for d in drivers) > 100, "no rope crossed the cut"
     for w in worlds + [ref]:
         w.close()
+
+
+def test_ray_batches_over_slabs_match_the_single_world():
+    """SURVEY.md §8e row 5 (physics.rs:1255-1311): every ray goes to the slabs its segment crosses, the reports are min-t reduced.
+    In this scene the slab run is bit-identical to the single world away from the cuts, so the merged first hits must be the
+    single-world first hits; long horizontal rays cross all three slabs."""
+    import torch
+    sc = scenes.c3_mixed(120, 30, seed=0xC3)
+    x0 = float(sc["bodies"]["x"].min()), float(sc["bodies"]["x"].max())
+    tun = abi.default_tuning(substeps=4, flags=abi.TUNE_NO_SLEEPING)
+    ref = GpuWorld(tuning=tun)
+    ref.load_scene(sc)
+    transport = slab.LocalTransport()
+    worlds, drivers = [], []
+    for r in range(3):
+        w = GpuWorld(tuning=tun)
+        w.load_scene(sc)
+        worlds.append(w)
+        drivers.append(slab.SlabDriver(w, r, 3, x0[0], x0[1], halo=4.0, substeps=4, capacity=4096, device=torch.device("cuda", 0), transport=transport))
+    for _ in range(30):
+        ref.tick()
+        slab.tick_local(drivers, transport)
+    rng = np.random.default_rng(11)
+    n = 4000
+    rays = np.zeros(n, abi.ray_dtype)
+    ys = sc["bodies"]["y"]
+    rays["sx"] = rng.uniform(x0[0] - 5.0, x0[1] + 5.0, n)
+    rays["sy"] = rng.uniform(float(ys.min()) - 2.0, float(ys.max()) + 6.0, n)
+    ang = rng.uniform(-np.pi, np.pi, n)
+    ang[: n // 4] = rng.choice([0.0, np.pi], n // 4) + rng.uniform(-0.02, 0.02, n // 4)       # long, nearly horizontal: cross every cut
+    rays["dx"], rays["dy"] = np.cos(ang), np.sin(ang)
+    rays["max_distance"] = np.where(np.arange(n) < n // 4, 400.0, rng.uniform(2.0, 60.0, n))
+    rays["radius"] = np.where(rng.random(n) < 0.3, 0.25, 0.0)
+    want = ref.cast_batch(rays)
+    got, routed = slab.cast_local(drivers, rays)
+    crossing = sum(routed) - n
+    same_coll = got["collider"] == want["collider"]
+    both_hit = same_coll & (want["collider"] >= 0)
+    dt = np.abs(got["t"][both_hit] - want["t"][both_hit])
+    print({"rays": n, "routed": routed, "extra_routes": crossing, "hits": int((want["collider"] >= 0).sum()), "same_collider": float(same_coll.mean()),
+           "t_err_max": float(dt.max(initial=0.0))})
+    assert crossing > n // 4, "the long rays did not cross the cuts"
+    assert (want["collider"] >= 0).mean() > 0.3
+    assert same_coll.mean() > 0.995 and (dt < 1e-4).mean() > 0.995
+    # the merge rule on its own: min t, ties to the lowest slot, misses last
+    a = np.zeros(3, abi.hit_dtype); b = np.zeros(3, abi.hit_dtype)
+    a["collider"], a["t"] = [5, -1, 9], [2.0, 0.0, 1.0]
+    b["collider"], b["t"] = [7, 3, 4], [1.5, 9.0, 1.0]
+    m = slab.merge_hits([a, b])
+    assert m["collider"].tolist() == [7, 3, 4] and m["t"].tolist() == [1.5, 9.0, 1.0]
+    for w in worlds + [ref]:
+        w.close()

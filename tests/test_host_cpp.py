@@ -40,3 +40,25 @@ def test_sandbox_scene_runs(exe):
     assert int([l for l in lines if l.startswith("ball_contacts")][0].split()[1]) >= 1
     assert int([l for l in lines if l.startswith("query_point_hits")][0].split()[1]) >= 1
     assert int([l for l in lines if l.startswith("query_shape_hits")][0].split()[1]) >= 1
+
+
+@pytest.fixture(scope="module")
+def hecs_exe(tmp_path_factory):
+    out = tmp_path_factory.mktemp("host") / "hecs_sync_test"
+    lib_dir = os.path.join(ROOT, "moleengine_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", str(out), os.path.join(ROOT, "tests", "host_cpp", "hecs_sync_test.cpp"),
+                           "-L" + lib_dir, "-lstarframe_gpu", "-Wl,-rpath," + lib_dir])
+    return str(out)
+
+
+def test_hecs_sync_rules_on_the_host(hecs_exe):
+    """HecsSyncManager mirror vs hecs_sync.rs:121-227: presets, both directions, auto-register, auto-delete, collider entities."""
+    r = subprocess.run([hecs_exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_physics_tick_with_hecs_sync(hecs_exe):
+    """Game::physics_tick (game.rs:297-303) through the mirror on the GPU: sync in, tick, sync out; teleport; despawn."""
+    r = subprocess.run([hecs_exe, "tick"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

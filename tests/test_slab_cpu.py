@@ -158,3 +158,58 @@ def test_island_shard_driver_all_gather_gloo():
         assert calls == [("shard", rank, 2), "tick", ("pack", 2, 0), "unpack"]
         assert sent == 3 + rank                                  # FakeWorld packs 3 + rank + side records
         assert got == [[1000.0 * other + 10.0 * 2 + i for i in range(3 + other)]]   # exactly the other rank's buffer, once
+
+
+def _cast_worker(rank, world_size, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from moleengine_b200 import abi
+
+    class CastWorld(FakeWorld):
+        def cast_batch(self, rays):
+            # rank 0 sees nearer hits for even rays, rank 1 for odd rays; ray 4 is an exact tie (a ghost and its owner); ray 6 misses everywhere
+            h = np.zeros(len(rays), abi.hit_dtype)
+            idx = np.round(rays["sy"]).astype(int)                     # the test stores the ray number in sy
+            h["collider"] = 10 * idx + self.rank
+            h["t"] = np.where(idx % 2 == self.rank, 1.0, 2.0) + idx
+            tie = idx == 4
+            h["collider"][tie], h["t"][tie] = 77, 3.25
+            h["collider"][idx == 6] = -1
+            h["px"] = 100.0 * self.rank + idx
+            return h
+
+    w = CastWorld(rank)
+    d = slab.SlabDriver(w, rank, world_size, -100.0, 100.0, halo=4.0, substeps=1, capacity=8, device="cpu")
+    rays = np.zeros(8, abi.ray_dtype)
+    rays["sy"] = np.arange(8)
+    rays["sx"] = [-50, -50, -50, -50, -1, -1, -1, 50]                  # rays 0..3 stay in slab 0, 4..6 cross the cut at 0, 7 stays in slab 1
+    rays["dx"], rays["max_distance"] = 1.0, [10, 10, 10, 10, 5, 5, 5, 10]
+    hits = slab.cast_distributed(d, rays, device="cpu")
+    out.put((rank, hits["collider"].tolist(), hits["t"].tolist(), hits["px"].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cast_over_slabs_routes_and_min_reduces_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_cast_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r = out.get(timeout=120)
+        res[r[0]] = r
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert res[0][1:] == res[1][1:]                                     # every rank ends up with all hits
+    coll, t, px = res[0][1], res[0][2], res[0][3]
+    # rays 0..3: only slab 0 was asked (rank 0's answer, whatever rank 1 would have said); ray 7: only slab 1
+    assert coll[:4] == [0, 10, 20, 30] and t[:4] == [1.0, 3.0, 3.0, 5.0] and px[:4] == [0.0, 1.0, 2.0, 3.0]
+    assert coll[7] == 71 and t[7] == 8.0 and px[7] == 107.0
+    # ray 4: both slabs report the same hit (ghost + owner) -> rank 0's copy; ray 5: rank 1 is nearer; ray 6: a miss everywhere
+    assert coll[4] == 77 and t[4] == 3.25 and px[4] == 4.0
+    assert coll[5] == 51 and t[5] == 6.0 and px[5] == 105.0
+    assert coll[6] == -1
