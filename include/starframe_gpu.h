@@ -235,6 +235,15 @@ int sfg_island_shard_configure(SfgWorld* w, uint32_t rank, uint32_t n_ranks);
 int sfg_slab_begin(SfgWorld* w);
 int sfg_slab_pack(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records, uint32_t* count_out);   /* mode 0 refresh, 1 substep sync, 2 island shard */
 int sfg_slab_unpack(SfgWorld* w, const void* device_in, uint32_t capacity_records);
+/* The same two without any host synchronisation: the kernels are only queued on the world's stream and the record count stays on
+ * the device (record 0 of the buffer; read it back after sfg_tick_end to check it against the capacity). sfg_stream_fence orders
+ * the world's stream against the transport's stream without the host waiting: direction 0 = `external_stream` (a cudaStream_t)
+ * waits for everything queued on the world's stream so far, 1 = the world's stream waits for everything queued on
+ * `external_stream` so far. With these a halo exchange is pack, fence(0), send / receive on the transport's stream, fence(1),
+ * unpack — all asynchronous; the tick's only host synchronisation is the one at its end. */
+int sfg_slab_pack_async(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records);
+int sfg_slab_unpack_async(SfgWorld* w, const void* device_in, uint32_t capacity_records);
+int sfg_stream_fence(SfgWorld* w, void* external_stream, int direction);
 
 /* ---- results: bodies written back (physics.rs:1150-1157), contacts (:1097-1122, :1165) ---- */
 int sfg_get_bodies(SfgWorld* w, uint32_t first_slot, uint32_t count, SfgBody* out);

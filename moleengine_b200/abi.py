@@ -60,7 +60,7 @@ stats_dtype = np.dtype([("n_bodies", "<u4"), ("n_colliders", "<u4"), ("n_pairs",
 EXPORTS = [
     "sfg_abi_version", "sfg_world_create", "sfg_world_destroy", "sfg_world_clear", "sfg_last_error", "sfg_set_tuning",
     "sfg_set_mask_matrix", "sfg_default_tuning", "sfg_default_mask_matrix", "sfg_set_bodies", "sfg_update_bodies",
-    "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_rope_cut_after", "sfg_rope_extend", "sfg_rope_remove_dead_particles", "sfg_get_ropes", "sfg_tick", "sfg_tick_begin", "sfg_tick_substeps", "sfg_tick_end", "sfg_slab_configure", "sfg_island_shard_configure", "sfg_slab_begin", "sfg_slab_pack", "sfg_slab_unpack", "sfg_get_bodies",
+    "sfg_set_colliders", "sfg_update_colliders", "sfg_set_constraints", "sfg_set_ropes", "sfg_rope_cut_after", "sfg_rope_extend", "sfg_rope_remove_dead_particles", "sfg_get_ropes", "sfg_tick", "sfg_tick_begin", "sfg_tick_substeps", "sfg_tick_end", "sfg_slab_configure", "sfg_island_shard_configure", "sfg_slab_begin", "sfg_slab_pack", "sfg_slab_unpack", "sfg_slab_pack_async", "sfg_slab_unpack_async", "sfg_stream_fence", "sfg_get_bodies",
     "sfg_get_contacts", "sfg_set_poses", "sfg_get_poses", "sfg_set_poses_indexed", "sfg_get_poses_indexed", "sfg_tick_poses", "sfg_get_stats", "sfg_cast_batch", "sfg_get_cast_kernel_ms", "sfg_query_point_batch", "sfg_query_shape_batch", "sfg_debug_get_pairs", "sfg_debug_get_pair_hints",
     "sfg_debug_get_contact_entries", "sfg_debug_get_constraint_entries", "sfg_debug_get_manifolds", "sfg_debug_get_aabbs", "sfg_debug_get_islands",
     "sfg_debug_intersection_check", "sfg_debug_spherecast_collider", "sfg_debug_geometry",
@@ -114,6 +114,9 @@ def load():
     lib.sfg_island_shard_configure.argtypes = [vp, u32, u32]
     lib.sfg_slab_pack.argtypes = [vp, i32, i32, vp, u32, C.POINTER(u32)]
     lib.sfg_slab_unpack.argtypes = [vp, vp, u32]
+    lib.sfg_slab_pack_async.argtypes = [vp, i32, i32, vp, u32]
+    lib.sfg_slab_unpack_async.argtypes = [vp, vp, u32]
+    lib.sfg_stream_fence.argtypes = [vp, vp, i32]
     lib.sfg_get_bodies.argtypes = [vp, u32, u32, vp]
     lib.sfg_get_contacts.argtypes = [vp, vp, sz, C.POINTER(sz)]
     lib.sfg_set_poses.argtypes = [vp, u32, u32, vp]

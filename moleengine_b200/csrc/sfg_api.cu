@@ -95,6 +95,7 @@ struct SfgWorld {
     bool islands_in_flight = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_cast[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fence = nullptr;          // sfg_stream_fence
     float last_cast_ms = 0.f;
     uint32_t n_k_two = 0;                    // two-body constraints (visited twice per substep)
     std::string err;
@@ -660,6 +661,7 @@ void sfg_world_destroy(SfgWorld* w) {
     w->stage.release(); w->stage2.release(); w->d_mask.release(); w->hdr.release(); w->d_stages.release(); w->d_rays.release(); w->d_hits.release();
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     for (auto& e : w->ev_cast) if (e) cudaEventDestroy(e);
+    if (w->ev_fence) cudaEventDestroy(w->ev_fence);
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
     if (w->ev_join) cudaEventDestroy(w->ev_join);
     if (w->stream2) cudaStreamDestroy(w->stream2);
@@ -1674,6 +1676,42 @@ int sfg_slab_unpack(SfgWorld* w, const void* device_in, uint32_t capacity_record
                                                                w->slab_stamp.p, w->slab_epoch);
     CKL(w); w->launches++;
     CK(cudaStreamSynchronize(w->stream));
+    return SFG_OK;
+}
+
+int sfg_slab_pack_async(SfgWorld* w, int mode, int side, void* device_out, uint32_t capacity_records) {
+    if (!w || !device_out || side < 0 || side > 1 || mode < 0 || mode > 2) return SFG_E_INVALID;
+    if (mode < 2 && !w->slab_on) return fail(w, SFG_E_STATE, "sfg_slab_configure first");
+    if (mode == 2 && w->shard_n < 2) return fail(w, SFG_E_STATE, "sfg_island_shard_configure first");
+    cudaSetDevice(w->device);
+    cudaStream_t st = w->stream;
+    HaloRec* out = (HaloRec*)device_out;
+    CK(cudaMemsetAsync(out, 0, sizeof(HaloRec), st));
+    if (w->n_bodies) {
+        k_slab_pack<<<nblk(w->n_bodies), 256, 0, st>>>(w->n_bodies, mode, side, w->slab_lo, w->slab_hi, w->slab_halo, w->P.p, w->Q.p, w->V.p, w->MI.p, out,
+                                                     capacity_records, &out[0].slot);
+        CKL(w); w->launches++;
+    }
+    return SFG_OK;
+}
+int sfg_slab_unpack_async(SfgWorld* w, const void* device_in, uint32_t capacity_records) {
+    if (!w || !device_in) return SFG_E_INVALID;
+    if (!w->slab_on && w->shard_n < 2) return fail(w, SFG_E_STATE, "sfg_slab_configure or sfg_island_shard_configure first");
+    if (capacity_records == 0 || w->n_bodies == 0) return SFG_OK;
+    cudaSetDevice(w->device);
+    CK(w->slab_stamp.ensure(size_t(w->n_bodies) + 1));
+    k_slab_unpack<<<nblk(capacity_records), 256, 0, w->stream>>>((const HaloRec*)device_in, capacity_records, w->n_bodies, w->P.p, w->Q.p, w->V.p,
+                                                               w->slab_stamp.p, w->slab_epoch);
+    CKL(w); w->launches++;
+    return SFG_OK;
+}
+int sfg_stream_fence(SfgWorld* w, void* external_stream, int direction) {
+    if (!w || direction < 0 || direction > 1) return SFG_E_INVALID;
+    cudaSetDevice(w->device);
+    cudaStream_t ext = (cudaStream_t)external_stream;
+    if (!w->ev_fence) CK(cudaEventCreateWithFlags(&w->ev_fence, cudaEventDisableTiming));
+    if (direction == 0) { CK(cudaEventRecord(w->ev_fence, w->stream)); CK(cudaStreamWaitEvent(ext, w->ev_fence, 0)); }
+    else { CK(cudaEventRecord(w->ev_fence, ext)); CK(cudaStreamWaitEvent(w->stream, w->ev_fence, 0)); }
     return SFG_OK;
 }
 

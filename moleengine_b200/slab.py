@@ -39,7 +39,7 @@ def neighbours(rank, n_ranks):
 
 class DistTransport:
     """torch.distributed point-to-point exchange with both x-neighbours in one batch (no collective over all ranks)."""
-    name = "torch.distributed send/recv between x-neighbours (NCCL P2P over NVLink on GPUs)"
+    name = "torch.distributed send/recv between x-neighbours (NCCL P2P over NVLink on GPUs), stream-ordered: no host synchronisation inside a tick"
 
     def __init__(self, group=None):
         self.group = group
@@ -95,6 +95,10 @@ class SlabDriver:
         self.recv = [torch.zeros(words, dtype=torch.float32, device=device) for _ in range(2)]
         self.sent_records = 0      # bodies sent in the last tick (both sides, all exchanges)
         self.exchanges = 0
+        # asynchronous exchanges need a CUDA world (sfg_slab_pack_async / sfg_stream_fence) and a stream-ordered transport (NCCL)
+        self.use_async = (isinstance(self.transport, DistTransport) and hasattr(world, "slab_pack_async") and self.send[0].is_cuda)
+        if self.use_async:
+            self.counts = torch.zeros((substeps + 2, 2), dtype=torch.int32, device=device)
         if isinstance(self.transport, LocalTransport):
             self.transport.register(self)
 
@@ -111,10 +115,46 @@ class SlabDriver:
                 self.world.slab_unpack(self.recv[side].data_ptr(), self.capacity)
 
     def _exchange(self, mode):
+        if self.use_async:
+            return self._exchange_async(mode)
         self.pack(mode)
         self.transport.exchange(self.rank, self.n_ranks, self.send, self.recv)
         self.unpack()
         self.exchanges += 1
+
+    def _exchange_async(self, mode):
+        """The same exchange without the host ever waiting: packs queued on the world's stream, the transport's stream made to wait
+        for them (sfg_stream_fence), NCCL send / receive, the world's stream made to wait for the received records, unpacks queued.
+        Record counts stay on the device (one small copy per exchange into self.counts, read once after the tick)."""
+        import torch
+        import torch.distributed as dist
+        w = self.world
+        sides = [(side, peer) for side, peer in enumerate(neighbours(self.rank, self.n_ranks)) if peer is not None]
+        for side, _ in sides:
+            w.slab_pack_async(mode, side, self.send[side].data_ptr(), self.capacity)
+        ts = torch.cuda.current_stream(self.send[0].device)
+        w.stream_fence(ts.cuda_stream, 0)
+        k = self.exchanges
+        for side, _ in sides:
+            self.counts[k, side].copy_(self.send[side][:1].view(torch.int32)[0], non_blocking=True)
+        ops = []
+        for side, peer in sides:
+            ops.append(dist.P2POp(dist.isend, self.send[side], peer, self.transport.group))
+            ops.append(dist.P2POp(dist.irecv, self.recv[side], peer, self.transport.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()                       # NCCL: the current stream waits for the transfer, the host does not
+        w.stream_fence(ts.cuda_stream, 1)
+        for side, _ in sides:
+            w.slab_unpack_async(self.recv[side].data_ptr(), self.capacity)
+        self.exchanges += 1
+
+    def _collect_counts(self):
+        """After sfg_tick_end (the device is idle): how many records went out in this tick, and did any exchange overflow its buffer?"""
+        c = self.counts[: self.exchanges].cpu()
+        if int(c.max()) > self.capacity:
+            raise RuntimeError(f"slab halo buffer too small: {int(c.max())} records for a capacity of {self.capacity}")
+        self.sent_records = int(c.sum())
 
     def tick(self, frame_dt=1.0 / 60.0, forcefield=None):
         """One frame: refresh the halo, then `substeps` substeps with an owner -> ghost exchange after each of them."""
@@ -127,6 +167,39 @@ class SlabDriver:
             w.tick_substeps(1)
             self._exchange(1)
         w.tick_end()
+        if self.use_async:
+            self._collect_counts()
+
+
+def tick_local_async(drivers, transport, frame_dt=1.0 / 60.0, forcefield=None):
+    """tick_local with the asynchronous pack / fence / unpack calls of SlabDriver._exchange_async (all slabs in one process on one
+    GPU, the 'wire' = copies on torch's current stream): exercises the stream fences without NCCL."""
+    import torch
+    ts = torch.cuda.current_stream()
+
+    def exchange(mode):
+        for d in drivers:
+            for side, peer in enumerate(neighbours(d.rank, d.n_ranks)):
+                if peer is not None:
+                    d.world.slab_pack_async(mode, side, d.send[side].data_ptr(), d.capacity)
+            d.world.stream_fence(ts.cuda_stream, 0)
+        transport.exchange_all()
+        for d in drivers:
+            d.world.stream_fence(ts.cuda_stream, 1)
+            for side, peer in enumerate(neighbours(d.rank, d.n_ranks)):
+                if peer is not None:
+                    d.world.slab_unpack_async(d.recv[side].data_ptr(), d.capacity)
+    for d in drivers:
+        d.world.slab_begin()
+    exchange(0)
+    for d in drivers:
+        d.world.tick_begin(frame_dt, None, forcefield)
+    for s in range(drivers[0].substeps):
+        for d in drivers:
+            d.world.tick_substeps(1)
+        exchange(1)
+    for d in drivers:
+        d.world.tick_end()
 
 
 def tick_local(drivers, transport, frame_dt=1.0 / 60.0, forcefield=None):

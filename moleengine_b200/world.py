@@ -140,6 +140,16 @@ class GpuWorld:
     def slab_unpack(self, device_ptr, capacity_records):
         self._ck(self.lib.sfg_slab_unpack(self.h, C.c_void_p(device_ptr), capacity_records))
 
+    def slab_pack_async(self, mode, side, device_ptr, capacity_records):
+        self._ck(self.lib.sfg_slab_pack_async(self.h, mode, side, C.c_void_p(device_ptr), capacity_records))
+
+    def slab_unpack_async(self, device_ptr, capacity_records):
+        self._ck(self.lib.sfg_slab_unpack_async(self.h, C.c_void_p(device_ptr), capacity_records))
+
+    def stream_fence(self, external_stream, direction):
+        """direction 0: `external_stream` (a cudaStream_t as an int) waits for the world's stream; 1: the world's stream waits for it."""
+        self._ck(self.lib.sfg_stream_fence(self.h, C.c_void_p(external_stream), direction))
+
     def get_bodies(self, first=0, count=None):
         count = self.n_bodies - first if count is None else count
         out = np.zeros(count, abi.body_dtype)

@@ -259,6 +259,9 @@ extern "C" {
     pub fn sfg_slab_begin(w: *mut SfgWorld) -> c_int;
     pub fn sfg_slab_pack(w: *mut SfgWorld, mode: c_int, side: c_int, device_out: *mut c_void, capacity_records: u32, count_out: *mut u32) -> c_int;
     pub fn sfg_slab_unpack(w: *mut SfgWorld, device_in: *const c_void, capacity_records: u32) -> c_int;
+    pub fn sfg_slab_pack_async(w: *mut SfgWorld, mode: c_int, side: c_int, device_out: *mut c_void, capacity_records: u32) -> c_int;
+    pub fn sfg_slab_unpack_async(w: *mut SfgWorld, device_in: *const c_void, capacity_records: u32) -> c_int;
+    pub fn sfg_stream_fence(w: *mut SfgWorld, external_stream: *mut c_void, direction: c_int) -> c_int;
     // results
     pub fn sfg_get_bodies(w: *mut SfgWorld, first_slot: u32, count: u32, out: *mut SfgBody) -> c_int;
     pub fn sfg_get_contacts(w: *mut SfgWorld, out: *mut SfgContactInfo, capacity: usize, n_out: *mut usize) -> c_int;

@@ -245,3 +245,33 @@ def test_ray_batches_over_slabs_match_the_single_world():
     assert m["collider"].tolist() == [7, 3, 4] and m["t"].tolist() == [1.5, 9.0, 1.0]
     for w in worlds + [ref]:
         w.close()
+
+
+def test_async_exchange_gives_the_same_bits_as_the_synchronous_one():
+    """sfg_slab_pack_async / sfg_stream_fence / sfg_slab_unpack_async (no host synchronisation inside the tick) against the
+    synchronous pack / unpack: every slab world ends every tick with the same bits."""
+    import torch
+    sc = scenes.c3_mixed(120, 30, seed=0xC3)
+    x0 = float(sc["bodies"]["x"].min()), float(sc["bodies"]["x"].max())
+    tun = abi.default_tuning(substeps=4, flags=abi.TUNE_NO_SLEEPING)
+    sets = []
+    for _ in range(2):
+        transport = slab.LocalTransport()
+        worlds, drivers = [], []
+        for r in range(3):
+            w = GpuWorld(tuning=tun)
+            w.load_scene(sc)
+            worlds.append(w)
+            drivers.append(slab.SlabDriver(w, r, 3, x0[0], x0[1], halo=4.0, substeps=4, capacity=4096, device=torch.device("cuda", 0), transport=transport))
+        sets.append((worlds, drivers, transport))
+    for t in range(25):
+        slab.tick_local(sets[0][1], sets[0][2])
+        slab.tick_local_async(sets[1][1], sets[1][2])
+        torch.cuda.synchronize()
+        for wa, wb in zip(sets[0][0], sets[1][0]):
+            ga, gb = wa.get_bodies(), wb.get_bodies()
+            for f in ("x", "y", "rot_s", "rot_b", "vx", "vy", "w", "flags"):
+                assert np.array_equal(ga[f], gb[f]), (t, f)
+    for worlds, _, _ in sets:
+        for w in worlds:
+            w.close()
