@@ -72,6 +72,7 @@ struct DBuf {
 // body; C3 peaks at 3.5, C5 at 7): a cudaMalloc in the middle of a run costs 100-700 ms on this platform when it has to map
 // fresh memory, which showed up as a hitch every time a growing pile outgrew its buffers. ~330 B per reserved pair.
 constexpr size_t RESERVE_PAIRS_PER_COLLIDER = 6;
+constexpr uint32_t SLAB_ZONE_CAP = 1u << 18;   // owned bodies within the halo of one cut (262 144 x 4 B per side)
 
 // per rope, uploaded before k_rope_build: where the rope's particles sit and where its units go in the colour-major lists
 struct RopeBuildRec { uint32_t first, count, ru_off[3], rd_off[2], pad; };
@@ -186,7 +187,8 @@ struct SfgWorld {
     bool slab_on = false, slab_was_on = false;
     float slab_lo = 0.f, slab_hi = 0.f, slab_halo = 0.f;
     uint32_t slab_epoch = 0;
-    DBuf<uint32_t> slab_stamp, dbg;
+    DBuf<uint32_t> slab_stamp, dbg, zone_list, zone_count;
+    bool zone_valid = false;      // this tick's classification filled the zone lists
     // island sharding (sfg_island_shard_configure)
     uint32_t shard_rank = 0, shard_n = 1;
     // stats
@@ -377,7 +379,10 @@ __global__ void k_iota(uint32_t* p, uint32_t n) {
 
 // ---- slab decomposition: one world cut into x-intervals, one per GPU; bodies near a cut are exchanged as 64-byte records
 struct HaloRec { uint32_t slot, pad[3]; float4 P, Q, V; };
-__global__ void k_slab_classify(uint32_t nb, const float4* P, float4* MI, const uint32_t* stamp, uint32_t epoch, float lo, float hi, float halo, int on) {
+// zone_list[side * zone_cap + k] / zone_count[side]: the owned bodies within `halo` of the cut on that side, i.e. what every
+// owner -> ghost exchange of this tick sends (k_slab_pack_list walks the list instead of all bodies)
+__global__ void k_slab_classify(uint32_t nb, const float4* P, float4* MI, const uint32_t* stamp, uint32_t epoch, float lo, float hi, float halo, int on,
+                                uint32_t* zone_list, uint32_t* zone_count, uint32_t zone_cap) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     float4 m = MI[b];
@@ -388,12 +393,28 @@ __global__ void k_slab_classify(uint32_t nb, const float4* P, float4* MI, const 
             const float4 p = P[b];
             const float x = p.x + p.z;
             const bool owned = x >= lo && x < hi;
-            if (owned) { fl |= BF_ALIVE; if (x < lo + halo) fl |= BF_ZONE_L; if (x >= hi - halo) fl |= BF_ZONE_R; }
+            if (owned) {
+                fl |= BF_ALIVE;
+                if (x < lo + halo) { fl |= BF_ZONE_L; const uint32_t k = atomicAdd(zone_count, 1u); if (k < zone_cap) zone_list[k] = b; }
+                if (x >= hi - halo) { fl |= BF_ZONE_R; const uint32_t k = atomicAdd(zone_count + 1, 1u); if (k < zone_cap) zone_list[zone_cap + k] = b; }
+            }
             else if (stamp[b] == epoch) fl |= BF_ALIVE | BF_GHOST;     // a neighbour sent it in this tick's refresh
         }
     }
     m.z = __uint_as_float(fl);
     MI[b] = m;
+}
+// mode 1 of k_slab_pack over this tick's zone list of one side (a few thousand bodies instead of all of them)
+__global__ void k_slab_pack_list(const uint32_t* __restrict__ list, const uint32_t* __restrict__ count, uint32_t list_cap, const float4* P, const float4* Q,
+                                 const float4* V, HaloRec* out, uint32_t cap, uint32_t* cursor) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n = min(*count, list_cap);
+    if (i == 0) *cursor = *count;                  // the header carries the count (an overflow of either capacity shows up there)
+    if (i >= n || i >= cap) return;
+    const uint32_t b = list[i];
+    HaloRec r;
+    r.slot = b; r.pad[0] = r.pad[1] = r.pad[2] = 0u; r.P = P[b]; r.Q = Q[b]; r.V = V[b];
+    out[1 + i] = r;
 }
 // mode 0: by position (the refresh that opens a tick, before the classification exists); mode 1: by this tick's flags;
 // mode 2: the bodies of this rank's islands (island sharding)
@@ -1261,8 +1282,12 @@ int slab_classify(SfgWorld* w) {
     const uint32_t nb = w->n_bodies;
     if (nb == 0) return SFG_OK;
     CK(w->slab_stamp.ensure(nb + 1));
-    k_slab_classify<<<nblk(nb), 256, 0, w->stream>>>(nb, w->P.p, w->MI.p, w->slab_stamp.p, w->slab_epoch, w->slab_lo, w->slab_hi, w->slab_halo, w->slab_on ? 1 : 0);
+    CK(w->zone_list.ensure(size_t(2) * SLAB_ZONE_CAP)); CK(w->zone_count.ensure(2));
+    CK(cudaMemsetAsync(w->zone_count.p, 0, 8, w->stream));
+    k_slab_classify<<<nblk(nb), 256, 0, w->stream>>>(nb, w->P.p, w->MI.p, w->slab_stamp.p, w->slab_epoch, w->slab_lo, w->slab_hi, w->slab_halo, w->slab_on ? 1 : 0,
+                                                   w->zone_list.p, w->zone_count.p, SLAB_ZONE_CAP);
     CKL(w); w->launches++;
+    w->zone_valid = w->slab_on;
     w->slab_was_on = w->slab_on;
     return SFG_OK;
 }
@@ -1687,7 +1712,12 @@ int sfg_slab_pack_async(SfgWorld* w, int mode, int side, void* device_out, uint3
     cudaStream_t st = w->stream;
     HaloRec* out = (HaloRec*)device_out;
     CK(cudaMemsetAsync(out, 0, sizeof(HaloRec), st));
-    if (w->n_bodies) {
+    if (w->n_bodies && mode == 1 && w->zone_valid) {
+        const uint32_t threads = std::min<uint32_t>(capacity_records, SLAB_ZONE_CAP);
+        k_slab_pack_list<<<nblk(threads), 256, 0, st>>>(w->zone_list.p + size_t(side) * SLAB_ZONE_CAP, w->zone_count.p + side, SLAB_ZONE_CAP, w->P.p, w->Q.p, w->V.p, out,
+                                                       capacity_records, &out[0].slot);
+        CKL(w); w->launches++;
+    } else if (w->n_bodies) {
         k_slab_pack<<<nblk(w->n_bodies), 256, 0, st>>>(w->n_bodies, mode, side, w->slab_lo, w->slab_hi, w->slab_halo, w->P.p, w->Q.p, w->V.p, w->MI.p, out,
                                                      capacity_records, &out[0].slot);
         CKL(w); w->launches++;

@@ -557,10 +557,18 @@ __global__ void __launch_bounds__(256) k_stage(const __grid_constant__ SolverCtx
 // relaxed polling load (no L1 invalidation per poll, unlike cooperative_groups' grid.sync) and one acquire fence at
 // the end. All data that crosses SMs between stages is accessed with ld.cg / st.cg, so L1 never holds it.
 SFG_DI unsigned long long global_timer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, unsigned long long* trace = nullptr) {
-    if (gridDim.x == 1 && !trace) { __syncthreads(); return; }   // a small world runs in one CTA: bar.sync orders its global accesses (all through L2)
+SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, uint32_t* s_next, unsigned long long* trace = nullptr) {
+    // s_next: the CTA's work counter of the stage that follows (k_solve_persistent deals a stage's items to the warps of a CTA
+    // dynamically); it is reset here, between the two CTA-wide barriers, when no warp can be reading it
+    if (gridDim.x == 1 && !trace) {   // a small world runs in one CTA: bar.sync orders its global accesses (all through L2)
+        __syncthreads();
+        if (threadIdx.x == 0) *s_next = 0u;
+        __syncthreads();
+        return;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
+        *s_next = 0u;
         target += gridDim.x;
         if (trace) trace[0] = global_timer();
         __threadfence();
@@ -579,6 +587,9 @@ SFG_DI void grid_barrier(unsigned int* counter, unsigned int& target, unsigned l
 __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(const __grid_constant__ SolverCtx c, const Stage* __restrict__ stages,
                                                              uint32_t n_stages, uint32_t sub_begin, uint32_t sub_end, uint32_t substeps,
                                                              unsigned int* barrier_counter, unsigned long long* trace, uint32_t* dbg_nan) {
+    __shared__ uint32_t s_next;                         // next item of the current stage that no warp of this CTA has taken yet
+    if (threadIdx.x == 0) s_next = 0u;
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
     const uint32_t first_chunk = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, chunk_stride = gridDim.x * warps_per_cta;
     unsigned int target = 0;
@@ -606,7 +617,7 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
                         while (ks + 1u < k2 && first >= stages[ks].end) ++ks;
                         atomicMin(c.far_min + size_t(s) * n_stages + k, ks);   // one word per run: a substep can hold several runs
                     }
-                    grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
+                    grid_barrier(barrier_counter, target, &s_next, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
                     const uint32_t fm = __ldcg(c.far_min + size_t(s) * n_stages + k);
                     merged_until = k2;
                     if (fm == 0xFFFFFFFFu) { k = k2 - 1u; continue; }       // every unit of the run rejected: all its stages are done
@@ -648,13 +659,22 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
             } else {
             const uint32_t lanes = n_head ? min(32u, (n_head + chunk_stride - 1u) / chunk_stride) : 32u;
             const uint32_t groups = (n_head + lanes - 1u) / lanes, items = groups + (n - n_head + 31u) / 32u;
-            for (uint32_t it = first_chunk; it < items; it += chunk_stride) {
+            // Items go to CTAs round-robin (item it -> CTA it mod gridDim: a run of expensive units is spread over all SMs) and,
+            // inside a CTA, to whichever warp is free next (one shared-memory counter): the items of a contact colour differ
+            // several-fold in cost — touching or not, one visit or two — and with a fixed deal the stage waited for the warp that
+            // drew the expensive ones (17 % of the settled solver's time was spent between the first and the last CTA's arrival).
+            for (;;) {
+                uint32_t j = 0;
+                if (lane == 0) j = atomicAdd(&s_next, 1u);
+                j = __shfl_sync(0xFFFFFFFFu, j, 0);
+                const uint32_t it = j * gridDim.x + blockIdx.x;
+                if (it >= items) break;
                 const bool head = it < groups;
                 const uint32_t i = head ? it * lanes + lane : n_head + (it - groups) * 32u + lane;
                 if (head ? (lane < lanes && i < n_head) : i < n) run_stage(c, st.kind, st.begin + i, last, s, st.colour, st.begin, head);
             }
             }
-            grid_barrier(barrier_counter, target, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
+            grid_barrier(barrier_counter, target, &s_next, trace ? trace + 2 * (size_t((s - sub_begin) * n_stages + k) * gridDim.x + blockIdx.x) : nullptr);
             if (dbg_nan) {   // debug (SFG_DEBUG_NAN): the first stage after which some body is not finite
                 for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < c.n_bodies; b += gridDim.x * blockDim.x) {
                     if (!(__float_as_uint(ldb(c.MI + b).z) & BF_ALIVE)) continue;
