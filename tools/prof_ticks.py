@@ -9,8 +9,8 @@ from moleengine_b200 import GpuWorld, abi  # noqa: E402
 from tools.bench_configs import build  # noqa: E402
 
 name, warm, n = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-sc, substeps, _ = build(name)
-g = GpuWorld(tuning=abi.default_tuning(substeps=substeps))
+sc, substeps, _rays = build(name)
+g = GpuWorld(tuning=abi.default_tuning(substeps=substeps, flags=int(os.environ.get("SFG_PROF_FLAGS", "0"))))   # e.g. 2 = one launch per stage
 g.load_scene(sc)
 for _ in range(warm):
     g.tick()
@@ -18,6 +18,8 @@ rt = ctypes.CDLL("libcuda.so.1")
 rt.cuProfilerStart()
 for _ in range(n):
     g.tick()
+    if _rays is not None:
+        g.cast_batch(_rays)
 rt.cuProfilerStop()
 st = g.stats()
 print(name, "tick", warm + n, "pairs", int(st["n_pairs"]), "colours", int(st["n_contact_colours"]), "ms", float(st["ms_total"]), file=sys.stderr)
