@@ -51,7 +51,7 @@ typedef struct SfgTuning {
 #define SFG_TUNE_SEPARATE_LAUNCHES 2u /* debug: one launch per colour instead of the persistent kernel */
 #define SFG_TUNE_COUNT_ENTRIES 4u     /* measurement: count the contact entries that found a contact (SfgStats.n_touching_entries); one more
                                       * warp-aggregated atomic per group of touching units in the solver, so off by default */
-#define SFG_MAX_SUBSTEPS 4096u       /* substeps of one tick (after time scaling) are capped: per-substep tables are sized by it */
+#define SFG_MAX_SUBSTEPS 4095u       /* substeps of one tick (after time scaling) are capped: per-substep tables are sized by it, manifold tags carry 12 bits of it */
 
 /* body.rs:7-13 Body. flags carry the Mass enum discriminants (body.rs:105-129). */
 typedef struct SfgBody {

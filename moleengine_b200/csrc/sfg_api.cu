@@ -152,7 +152,9 @@ struct SfgWorld {
     DBuf<float2> LN;
     DBuf<float> RC;
     DBuf<uint32_t> WL, wl_count, near_count, far_min;
-    uint32_t last_substeps = 0;   // substeps of the last tick = tag of a manifold entry written in its last substep
+    uint32_t last_substeps = 0;   // substeps of the last tick: tag_base + last_substeps = tag of a manifold entry written in its last substep
+    uint32_t tick_seq = 0;        // ticks begun so far; its low 12 bits go into the manifold tags
+    float4* m0_cleared = nullptr; // the M0 allocation that was last cleared
     // constraint units
     uint32_t n_kunits = 0, n_k_colours = 0;
     std::vector<uint32_t> k_colour_start;
@@ -1238,7 +1240,12 @@ int build_graph(SfgWorld* w) {
                                                     w->G0.p, w->G1.p, w->L0.p, w->L1.p, w->RC.p, w->tick_counts.p);
         CKL(w); w->launches++;
         CK(cudaMemsetAsync(w->LN.p, 0xFF, size_t(n) * 2 * sizeof(float2), st));
-        CK(cudaMemsetAsync(w->M0.p, 0, size_t(n) * 2 * sizeof(float4), st));
+        // manifold tags carry the tick number (sfg_state.cuh SolverCtx::tag_base): the column is cleared only when the 12-bit tick
+        // counter wraps, or when the buffer is new memory
+        if ((w->tick_seq & 0xFFFu) == 0u || w->M0.p != w->m0_cleared) {
+            CK(cudaMemsetAsync(w->M0.p, 0, w->M0.cap * sizeof(float4), st));
+            w->m0_cleared = w->M0.p;
+        }
     }
     // ---- constraint units
     if (w->n_constraints) {
@@ -1265,6 +1272,7 @@ void fill_ctx(SfgWorld* w, SolverCtx& c, float dt, const SfgForceField* ff) {
     c.H = w->H.p; c.S = w->S.p; c.G0 = w->G0.p; c.G1 = w->G1.p; c.L0 = w->L0.p; c.L1 = w->L1.p;
     c.M0 = w->M0.p; c.M1 = w->M1.p; c.M2 = w->M2.p; c.LN = w->LN.p; c.n_units = w->n_units;
     c.stat_touch = (w->tuning.flags & SFG_TUNE_COUNT_ENTRIES) ? w->tick_counts.p + 2 : nullptr;
+    c.tag_base = (w->tick_seq & 0xFFFu) << 12;
     c.RC = w->RC.p; c.WL = w->WL.p; c.wl_count = w->wl_count.p; c.near_count = w->near_count.p; c.n_colours = w->n_unit_colours;
     c.K0 = w->K0.p; c.K1 = w->K1.p; c.K2 = w->K2.p; c.n_kunits = w->n_kunits;
     c.RU = w->RU.p; c.RD = w->RD.p; c.RPA = w->RPA.p; c.RPB = w->RPB.p; c.rp_body = w->rp_body.p; c.rp_rope = w->rp_rope.p;
@@ -1407,6 +1415,7 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     w->launches = 0;
     w->islands_in_flight = false;
     w->frame_dt = float(frame_dt);
+    w->tick_seq += 1;
     if (w->ropes_dirty) { rc = rebuild_rope_units(w); if (rc != SFG_OK) return rc; }
     CK(cudaEventRecord(w->ev[0], st));
     CK(cudaMemsetAsync(w->tick_counts.p, 0, 4 * sizeof(uint32_t), st));
@@ -2014,7 +2023,7 @@ int sfg_debug_get_manifolds(SfgWorld* w, float* out, size_t capacity_entries, si
     cudaSetDevice(w->device);
     cudaStream_t st = w->stream;
     CK(w->stage.ensure(size_t(n_entries) * 14 * 4));
-    k_export_manifolds<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->last_substeps, w->S.p, w->M0.p, w->M1.p, w->M2.p, (float*)w->stage.p);
+    k_export_manifolds<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, ((w->tick_seq & 0xFFFu) << 12) + w->last_substeps, w->S.p, w->M0.p, w->M1.p, w->M2.p, (float*)w->stage.p);
     CKL(w);
     CK(cudaMemcpyAsync(out, w->stage.p, size_t(n_entries) * 14 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

@@ -314,7 +314,7 @@ SFG_DI void stage_contacts(const SolverCtx& c, uint32_t u, uint32_t colour, uint
     const float reach2 = (bound_radius(sh0) + bound_radius(sh1)) * 1.001f + 1e-3f;
     const float far_sq = fmaxf(reach2 * reach2, 0.0011f);
 
-    const uint32_t tag = (sub + 1u) << 8;
+    const uint32_t tag = (c.tag_base + sub + 1u) << 8;
     bool moved = false;
     SFG_STAMP(3, __float_as_uint(far_sq + l0.x + l1.x + Q0.x + Q1.x + im0 + im1));
     for (int m = 0; m < mult; ++m) {
@@ -441,7 +441,7 @@ SFG_DI void stage_contact_vel(const SolverCtx& c, uint32_t u, uint32_t sub) {
     m0[1] = ldb(c.M0 + e1); m1[1] = ldb(c.M1 + e1); m2[1] = ldb(c.M2 + e1);      // entries [n_units, 2 n_units) exist for every unit
     const uint32_t fl = __float_as_uint(h.z);
     const int mult = (fl & UF_MULT2) ? 2 : 1;
-    const uint32_t tag = sub + 1u;
+    const uint32_t tag = c.tag_base + sub + 1u;
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     const int i0 = max(b0, 0), i1 = max(b1, 0);
     const float mu_d = s.z, rest_mat = s.w;

@@ -28,56 +28,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const uint32_t* __re
     hist[threadIdx.x * n_tiles + blockIdx.x] = sh[threadIdx.x];
 }
 
-// ---- scatter: stable rank inside the tile in shared memory, then a direct write ----
-// Order inside a tile is (warp, round, lane): warp w owns keys [w*256, (w+1)*256) of the tile.
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
-                                                               int shift, const uint32_t* __restrict__ hist_scanned, uint32_t n_tiles) {
-    __shared__ uint32_t warp_hist[SORT_WARPS][256];
-    __shared__ uint32_t digit_base[256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
-    __syncthreads();
-    const uint32_t base = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
-    uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-        const uint32_t i = base + r * 32 + lane;
-        const bool ok = i < n;
-        key[r] = ok ? keys_in[i] : 0xFFFFFFFFu;
-        val[r] = ok ? vals_in[i] : 0u;
-        const uint32_t d = ok ? ((key[r] >> shift) & 255u) : 256u;   // 256 = out of range, ranked nowhere
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-        const int leader = __ffs(peers) - 1;
-        uint32_t b = 0;
-        if (ok && lane == leader) { b = warp_hist[warp][d]; warp_hist[warp][d] = b + __popc(peers); }
-        b = __shfl_sync(0xFFFFFFFFu, b, leader);
-        rank[r] = b + __popc(peers & lt);
-        __syncwarp();
-    }
-    __syncthreads();
-    {   // exclusive scan of each digit over the warps + global base of this tile
-        const int d = threadIdx.x;
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) { uint32_t c = warp_hist[w][d]; warp_hist[w][d] = run; run += c; }
-        digit_base[d] = hist_scanned[d * n_tiles + blockIdx.x];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-        const uint32_t i = base + r * 32 + lane;
-        if (i < n) {
-            const uint32_t d = (key[r] >> shift) & 255u;
-            const uint32_t pos = digit_base[d] + warp_hist[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
-        }
-    }
-}
-
-// ---- exclusive scan (u32), three phases; block sums scanned by one CTA ----
+// ---- exclusive scan helpers (used by the scatter kernel and the scan kernels) ----
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -103,6 +54,76 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
     return res;
 }
 
+
+// ---- scatter: stable rank inside the tile in shared memory, the tile re-ordered there, then a coalesced write ----
+// Order inside a tile is (warp, round, lane): warp w owns keys [w*256, (w+1)*256) of the tile. After the ranking every key knows
+// its place in the tile's digit-sorted order; keys and values are moved there in shared memory, and the tile is written out in
+// that order, so that the threads of a warp store runs of consecutive addresses (one run per digit) instead of 32 scattered words.
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, uint32_t n,
+                                                               int shift, const uint32_t* __restrict__ hist_scanned, uint32_t n_tiles) {
+    __shared__ uint32_t warp_hist[SORT_WARPS][256];
+    __shared__ uint32_t digit_base[256];          // global position of the tile's first key of each digit, minus its place in the tile
+    __shared__ uint32_t s_key[SORT_TILE], s_val[SORT_TILE];
+    __shared__ uint32_t s_tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * SORT_TILE + warp * (32 * SORT_ITEMS);
+    uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        const bool ok = i < n;
+        key[r] = ok ? keys_in[i] : 0xFFFFFFFFu;
+        val[r] = ok ? vals_in[i] : 0u;
+        const uint32_t d = ok ? ((key[r] >> shift) & 255u) : 256u;   // 256 = out of range, ranked nowhere
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t b = 0;
+        if (ok && lane == leader) { b = warp_hist[warp][d]; warp_hist[warp][d] = b + __popc(peers); }
+        b = __shfl_sync(0xFFFFFFFFu, b, leader);
+        rank[r] = b + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // exclusive scan of each digit over the warps, of the digit totals over the digits, + global base of this tile
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) { uint32_t c = warp_hist[w][d]; warp_hist[w][d] = run; run += c; }
+        const uint32_t local = block_exclusive_scan(run, &s_tot);            // where digit d starts inside the sorted tile
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) warp_hist[w][d] += local;
+        digit_base[d] = hist_scanned[d * n_tiles + blockIdx.x] - local;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        const uint32_t i = base + r * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (key[r] >> shift) & 255u;
+            const uint32_t pos = warp_hist[warp][d] + rank[r];
+            s_key[pos] = key[r];
+            s_val[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    const uint32_t tile_n = min(uint32_t(SORT_TILE), n - blockIdx.x * SORT_TILE);
+#pragma unroll
+    for (int r = 0; r < SORT_ITEMS; ++r) {
+        const uint32_t j = r * SORT_THREADS + threadIdx.x;
+        if (j < tile_n) {
+            const uint32_t k = s_key[j];
+            const uint32_t pos = digit_base[(k >> shift) & 255u] + j;
+            keys_out[pos] = k;
+            vals_out[pos] = s_val[j];
+        }
+    }
+}
+
+// ---- exclusive scan (u32), three phases; block sums scanned by one CTA ----
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ sums) {
     __shared__ uint32_t tot;
     uint32_t s = 0;

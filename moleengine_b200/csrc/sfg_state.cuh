@@ -11,8 +11,8 @@
 //             H  (body0, body1, flags, mu_s)   S (hi, lo, mu_d, e)   G0 G1 shapes   L0 L1 local poses
 //             RC float: body centres farther apart than this cannot touch (bounding radii + local offsets + margin)
 //             M0 (count | tag << 8, lambda_n, n.x, n.y)  M1 / M2 point 0 / 1 (off0.xy, off1.xy); entry = copy * n_units + unit
-//                tag = substep + 1 of the visit that wrote the entry: an entry with another tag counts as "no contact",
-//                so visits that find nothing write nothing
+//                tag = (tick mod 4096) << 12 | substep + 1 of the visit that wrote the entry: an entry with another tag counts as
+//                "no contact", so visits that find nothing write nothing and the column is cleared only every 4096 ticks
 //             WL u32: per colour (same ranges as the units) the units that found a contact in the current substep;
 //                wl_count[substep * n_colours + colour] = how many. The velocity sweep walks these lists only.
 //
@@ -90,6 +90,8 @@ struct SolverCtx {
     float2 *EA, *PCD;
     const int *rope_next, *rope_prev;
     uint32_t n_bodies;
+    uint32_t tag_base;            // (tick number mod 4096) << 12: the tag of a manifold entry is tag_base + substep + 1, so an entry written by an
+                                  // earlier tick never reads as this tick's and M0 needs no clearing between ticks (sfg_api.cu build_graph)
     uint32_t bouncy;              // some collider has restitution != 0: only then are old velocities / external accelerations kept (solver.rs:555-576)
     // pair units
     const float4 *H, *S, *G0, *G1, *L0, *L1;

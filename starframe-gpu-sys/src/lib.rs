@@ -17,7 +17,7 @@ pub const SFG_E_STATE: c_int = 5;
 pub const SFG_TUNE_NO_SLEEPING: u32 = 1;
 pub const SFG_TUNE_SEPARATE_LAUNCHES: u32 = 2;
 pub const SFG_TUNE_COUNT_ENTRIES: u32 = 4;
-pub const SFG_MAX_SUBSTEPS: u32 = 4096;
+pub const SFG_MAX_SUBSTEPS: u32 = 4095;
 pub const SFG_BODY_ALIVE: u32 = 1;
 pub const SFG_BODY_IGNORES_GRAVITY: u32 = 2;
 pub const SFG_BODY_MASS_FINITE: u32 = 4;
