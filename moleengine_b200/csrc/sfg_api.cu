@@ -606,8 +606,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, pair_units ? w->U_cls.p : nullptr, w->ckey0.p, near_count);
     CKL(w); w->launches++;
     k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
-    int bits = 5;
-    while ((1u << bits) < n_colours * 32u) ++bits;
+    int bits = 7;
+    while ((1u << bits) < n_colours * 128u) ++bits;
     int launches = 0;
     int where = radix_sort_pairs(w->ckey0.p, w->perm0.p, w->ckey1.p, w->perm1.p, n_units, bits, w->sort_tmp.p, st, &launches);
     w->launches += launches;

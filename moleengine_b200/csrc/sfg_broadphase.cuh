@@ -356,14 +356,17 @@ __global__ void __launch_bounds__(256) k_pair_unit_setup(uint32_t n_units, const
     if (b1 >= 0 && !(__float_as_uint(MI[b1].z) & (BF_MASS | BF_INERTIA))) b1 = -1;
     ub[u] = make_int2(b0, b1);
     prio[u] = sfg_pair_priority(id.x, id.y, near_hint ? 1u : 0u);
-    {   // order inside a colour (k_unit_sort_keys): far units last, the rest grouped by narrowphase path and visit count
-        const uint32_t k0 = s0.kind, k1 = s1.kind;
+    {   // order inside a colour (k_unit_sort_keys): far units last, the rest grouped by the EXACT pair of polygon kinds and the
+        // visit count, so that the lanes of a warp take the same kind switches and loop counts all the way through the SAT
+        // (grouping by edge count alone left rectangles next to segments and triangles next to hexagons: the SAT loops ran at
+        // 8-10 active lanes in the settled pile)
+        const uint32_t k0 = s0.kind, k1 = s1.kind;        // 0 point, 1 segment, 2 rect, 3 triangle, 4 hexagon
         uint32_t path;
         if (k0 == K_POINT && k1 == K_POINT) path = 0;
-        else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: the polygon's kind
-        else path = 5 + (k0 >= K_TRIANGLE ? 1u : 0u) + (k1 >= K_TRIANGLE ? 1u : 0u);     // 5..7: 2-edge vs 3-edge polygons
+        else if (k0 == K_POINT || k1 == K_POINT) path = max(k0, k1);                      // 1..4: circle against that polygon kind
+        else path = 5u + (k0 - 1u) * 4u + (k1 - 1u);                                      // 5..20: polygon against polygon, ordered
         const uint32_t mult2 = (c0.x >= 0 && c1.x >= 0) ? 1u : 0u;
-        ucls[u] = uint8_t(path * 2 + mult2 + (near_hint ? 0u : 16u));
+        ucls[u] = uint8_t(path * 2 + mult2 + (near_hint ? 0u : 64u));
     }
     if (b0 >= 0) atomicAdd(deg + b0, 1u);
     if (b1 >= 0) atomicAdd(deg + b1, 1u);
@@ -413,10 +416,10 @@ __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const 
     if (u < n_units) {
         const uint32_t cls = ucls ? ucls[u] : 0u;            // k_pair_unit_setup; constraints have no classes
         const uint32_t col = colour[u];
-        keys[u] = col * 32u + cls;
+        keys[u] = col * 128u + cls;
         // how many units of each colour sort into its "may touch" head: the solver deals those out a few lanes per warp
         // (sfg_solver.cuh k_solve_persistent). Counted per block in shared memory, one global atomic per colour and block.
-        if (near_count && !(cls & 16u)) {
+        if (near_count && !(cls & 64u)) {
             if (col < 64u) atomicAdd(&s_near[col], 1u);
             else atomicAdd(near_count + col, 1u);
         }

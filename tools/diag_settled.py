@@ -9,7 +9,7 @@ from tools.bench_configs import build  # noqa: E402
 
 name, warm, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 sc, substeps, _ = build(name)
-g = GpuWorld(tuning=abi.default_tuning(substeps=substeps))
+g = GpuWorld(tuning=abi.default_tuning(substeps=substeps, flags=int(os.environ.get("SFG_PROF_FLAGS", "0"))))   # e.g. 1 = no island pass
 g.load_scene(sc)
 for _ in range(warm):
     g.tick()
