@@ -1,6 +1,6 @@
 // CUB-free device primitives for the broadphase / graph build: an LSD radix sort whose ranking runs
-// in shared memory (8-bit digits, warp match-any multisplit, stable) and a three-phase exclusive
-// scan. Written for sm_100a: 256-thread CTAs, 2048-key tiles, grids sized by the tile count.
+// in shared memory (8-bit digits, warp match-any multisplit, stable) and a one-pass exclusive scan
+// (decoupled look-back). Written for sm_100a: 256-thread CTAs, 2048-key tiles, grids sized by the tile count.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -123,57 +123,63 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const uint32_t* _
     }
 }
 
-// ---- exclusive scan (u32), three phases; block sums scanned by one CTA ----
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ sums) {
-    __shared__ uint32_t tot;
-    uint32_t s = 0;
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) s += in[base + k];
-    block_exclusive_scan(s, &tot);
-    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
-}
-// one CTA scans `sums` in place (exclusive) and writes the grand total to *total_out
-__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* __restrict__ sums, uint32_t n, uint32_t* __restrict__ total_out) {
-    __shared__ uint32_t tot;
-    uint32_t carry = 0;
-    for (uint32_t base = 0; base < n; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < n ? sums[i] : 0;
-        uint32_t e = block_exclusive_scan(v, &tot);
-        if (i < n) sums[i] = carry + e;
-        carry += tot;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ sums,
-                                                             uint32_t* __restrict__ out) {
-    __shared__ uint32_t tot;
+// ---- exclusive scan (u32) in ONE pass: decoupled look-back over 2048-element tiles ----
+// Every tile publishes its own sum as soon as it has it (flag AGGREGATE) and, once it knows the sum of everything in front of
+// it, its inclusive prefix (flag PREFIX); a tile finds what is in front of it by walking back over its predecessors' words,
+// adding aggregates until it meets a prefix. Tiles take their numbers from a ticket counter in the order they start running,
+// so a tile's predecessors are always running or done (no deadlock whatever the block scheduling order is). One word per tile:
+// flag << 62 | value. Replaces reduce + scan-of-sums + apply (three launches and two dependent round trips through a tiny kernel).
+constexpr unsigned long long SCAN_FLAG_AGG = 1ull << 62, SCAN_FLAG_PREFIX = 2ull << 62, SCAN_VALUE_MASK = 0xFFFFFFFFull;
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                                                                unsigned long long* __restrict__ state, uint32_t* __restrict__ ticket,
+                                                                uint32_t* __restrict__ total_out) {
+    __shared__ uint32_t s_tile, s_tot, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile, n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     uint32_t v[SCAN_ITEMS], s = 0;
-    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = base + k < n ? in[base + k] : 0; s += v[k]; }
-    uint32_t e = block_exclusive_scan(s, &tot) + sums[blockIdx.x];
+    uint32_t e = block_exclusive_scan(s, &s_tot);
+    if (threadIdx.x == 0) {
+        const uint32_t total = s_tot;
+        uint32_t exclusive = 0;
+        if (tile == 0) {
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(state), "l"(SCAN_FLAG_PREFIX | total) : "memory");
+        } else {
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(state + tile), "l"(SCAN_FLAG_AGG | total) : "memory");
+            for (uint32_t p = tile; p-- > 0;) {
+                unsigned long long w;
+                do { asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(state + p) : "memory"); } while ((w >> 62) == 0ull);
+                exclusive += uint32_t(w & SCAN_VALUE_MASK);
+                if ((w >> 62) == 2ull) break;
+            }
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(state + tile), "l"(SCAN_FLAG_PREFIX | (unsigned long long)(exclusive + total)) : "memory");
+        }
+        s_prefix = exclusive;
+        if (tile + 1 == n_tiles && total_out) *total_out = exclusive + total;
+    }
+    __syncthreads();
+    e += s_prefix;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = e; e += v[k]; }
 }
 
-// Host-side drivers. `tmp` must hold at least scan_tmp_words(n) uint32.
-inline size_t scan_tmp_words(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE + 1; }
+// Host-side drivers. `tmp` must hold at least scan_tmp_words(n) uint32 (8-byte aligned: every caller passes a cudaMalloc'ed block or an even offset into one).
+inline size_t scan_tmp_words(size_t n) { return 2 * ((n + SCAN_TILE - 1) / SCAN_TILE + 2); }
 // exclusive scan of in[0..n) into out[0..n) (in == out allowed); the grand total goes to *total_dev if not null
 inline int scan_exclusive(const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp, uint32_t* total_dev, cudaStream_t st) {
     if (n == 0) { if (total_dev) cudaMemsetAsync(total_dev, 0, 4, st); return 0; }
     const uint32_t nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_reduce<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nb, total_dev);
-    k_scan_apply<<<nb, SCAN_THREADS, 0, st>>>(in, n, tmp, out);
-    return 3;
+    cudaMemsetAsync(tmp, 0, size_t(nb + 1) * 8, st);                       // ticket (first 8 bytes) + one state word per tile
+    k_scan_lookback<<<nb, SCAN_THREADS, 0, st>>>(in, out, n, reinterpret_cast<unsigned long long*>(tmp) + 1, tmp, total_dev);
+    return 1;
 }
 
 inline size_t sort_tmp_words(size_t n) {
     size_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
-    return 256 * tiles + scan_tmp_words(256 * tiles);
+    return 256 * tiles + 2 + scan_tmp_words(256 * tiles);
 }
 // Sorts (keys, vals) by the low `bits` bits of the key, stable. Ping-pongs between (k0, v0) and (k1, v1);
 // returns 0 if the result is in (k0, v0), 1 if in (k1, v1); *launches is incremented by the kernels launched.
@@ -182,7 +188,7 @@ inline int radix_sort_pairs(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* 
     if (n == 0) return 0;
     const uint32_t tiles = (n + SORT_TILE - 1) / SORT_TILE;
     uint32_t* hist = tmp;
-    uint32_t* scan_tmp = tmp + 256 * size_t(tiles);
+    uint32_t* scan_tmp = tmp + ((256 * size_t(tiles) + 1) & ~size_t(1));       // 8-byte aligned (the scan keeps 64-bit words there)
     int cur = 0;
     for (int shift = 0; shift < bits; shift += 8) {
         uint32_t *ki = cur ? k1 : k0, *vi = cur ? v1 : v0, *ko = cur ? k0 : k1, *vo = cur ? v0 : v1;
