@@ -108,3 +108,48 @@ def test_c3_momentum_conserved_without_statics(c3):
     assert moved.sum() > 1000, "no contacts happened: the check would be vacuous"
     assert np.abs(p1 - p0).max() <= 2e-5 * scale
     g.close()
+
+
+def test_c3_settled_pile_statistics_at_full_size(c3, oracle):
+    """The headline window of bench.py — 1 M bodies, 300 ticks in, piles at rest on the shelves — through size-independent
+    statistics, next to the SAME statistics of the f64 oracle's own run of the 1/10-scale world in the reference order
+    (tests/golden/c3_tenth_settled300.npz, tools/make_settled_fixture.py): nothing is lost or non-finite, the pile is at rest, and
+    the penetration-depth distribution over all touching solid pairs (one routine for both: OracleWorld.penetrations) agrees."""
+    import os
+    import longrun
+    sc = c3
+    g = GpuWorld(tuning=abi.default_tuning(substeps=4))
+    g.load_scene(sc)
+    for _ in range(300):
+        g.tick()
+    st = g.stats()
+    b = g.get_bodies()
+    g.close()
+    import parity
+    state = parity.body_state(b)
+    assert np.isfinite(state).all()
+    # nothing fell through: every body is above the lowest shelf
+    floor_y = float(sc["colliders"]["y"][sc["colliders"]["body"] < 0].min())
+    assert (state[:, 1] > floor_y - 0.5).all()
+    speed = np.hypot(state[:, 4], state[:, 5])
+    dev = longrun.sample(sc, state, oracle)
+    # the oracle's settled 1/10-scale world
+    import bench
+    sc10, st10 = bench.settled_fixture()
+    assert st10 is not None, "tests/golden/c3_tenth_settled300.npz is missing"
+    ref = longrun.sample(sc10, st10.astype(np.float64), oracle)
+    n, n10 = len(sc["bodies"]), len(sc10["bodies"])
+    rep = {"device_1M": {k: dev[k] for k in ("pen_n", "pen_p50", "pen_p99", "pen_max", "ke")}, "oracle_100k": {k: ref[k] for k in ("pen_n", "pen_p50", "pen_p99", "pen_max", "ke")},
+           "pairs_per_body": (int(st["n_pairs"]) / n, None), "median_speed": float(np.median(speed)), "p99_speed": float(np.percentile(speed, 99))}
+    print(rep)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        import json
+        json.dump(rep, open(os.path.join(out, "fullsize_settled_stats.json"), "w"), indent=1)
+    assert np.median(speed) < 0.02 and np.percentile(speed, 99) < 0.5, "the pile is not at rest"
+    # kinetic energy per body and deep contacts per body: same order as the reference-order run at 1/10 scale
+    assert dev["ke"] / n < 10.0 * ref["ke"] / n10 + 1e-3
+    assert 0.5 < (dev["pen_n"] / n) / (ref["pen_n"] / n10) < 2.0
+    # penetration depths: median within a factor 2.5 (the coloured order converges a little slower than the DFS order: oracle/longrun.py),
+    # p99 within a factor 3, and nothing deeper than a body is thick
+    assert dev["pen_p50"] < 2.5 * ref["pen_p50"] + 2e-4 and dev["pen_p99"] < 3.0 * ref["pen_p99"] + 2e-3 and dev["pen_max"] < 0.3

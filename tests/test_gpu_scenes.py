@@ -363,3 +363,30 @@ def test_tick_poses_equals_set_tick_get():
     a.tick()
     assert np.array_equal(keep.view(np.uint32), a.get_poses().view(np.uint32))
     a.close(); b.close()
+
+
+def test_time_scale_and_slot_space_edge_cases():
+    """ABI validation (round-1 advisor findings): a negative / NaN time scale gives zero substeps like Rust's saturating float-to-int
+    cast (physics.rs:411-415) instead of undefined behaviour, an absurd one is refused, zero substeps in the tuning are refused at
+    creation too, and shrinking the body slot space invalidates the colliders that may point beyond it."""
+    sc = scenes.parity_mix(60, 2)
+    g = GpuWorld(tuning=abi.default_tuning(substeps=4))
+    g.load_scene(sc)
+    before = g.get_bodies()
+    for ts in (-1.0, float("nan"), 0.0):
+        g.tick(1.0 / 60.0, ts)
+        assert int(g.stats()["substeps"]) == 0
+        after = g.get_bodies()
+        for f in ("x", "y", "vx", "vy", "w"):
+            assert np.array_equal(before[f], after[f]), (ts, f)          # no substep ran: nothing moved
+    g.tick(1.0 / 60.0, 0.3)
+    assert int(g.stats()["substeps"]) == 2                               # ceil(0.3 * 4)
+    with pytest.raises(SfgError):
+        g.tick(1.0 / 60.0, 1e9)
+    with pytest.raises(SfgError):
+        GpuWorld(tuning=abi.default_tuning(substeps=0))
+    # a smaller slot space: the colliders uploaded before have to be uploaded again
+    g.set_bodies(sc["bodies"][:10].copy())
+    g.tick()
+    assert int(g.stats()["n_colliders"]) == 0 and int(g.stats()["n_pairs"]) == 0
+    g.close()
