@@ -146,7 +146,11 @@ def test_c3_settled_pile_statistics_at_full_size(c3, oracle):
     if os.path.isdir(out):
         import json
         json.dump(rep, open(os.path.join(out, "fullsize_settled_stats.json"), "w"), indent=1)
-    assert np.median(speed) < 0.02 and np.percentile(speed, 99) < 0.5, "the pile is not at rest"
+    # "at rest" under 4 substeps of XPBD means a residual jitter of a few cm/s (every substep adds g * dt = 4 cm/s before the contacts
+    # take it out again): the reference-order run shows the same level, and that is what the device is held to
+    speed10 = np.hypot(st10[:, 4], st10[:, 5])
+    rep["oracle_median_speed"], rep["oracle_p99_speed"] = float(np.median(speed10)), float(np.percentile(speed10, 99))
+    assert np.median(speed) < 1.5 * np.median(speed10) + 0.01 and np.percentile(speed, 99) < 1.5 * np.percentile(speed10, 99) + 0.05, "the pile is not at rest"
     # kinetic energy per body and deep contacts per body: same order as the reference-order run at 1/10 scale
     assert dev["ke"] / n < 10.0 * ref["ke"] / n10 + 1e-3
     assert 0.5 < (dev["pen_n"] / n) / (ref["pen_n"] / n10) < 2.0

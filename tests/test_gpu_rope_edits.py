@@ -83,23 +83,33 @@ def test_extend_appends_particles_without_reuploading_the_rope():
     a.load_scene(sc); b.load_scene(sc)
     for _ in range(10):
         a.tick(); b.tick()
-    # Rope::extend_line on rope 1 (NOT the last range of the particle array: it has to move): 5 new particles after its last one
+    # Rope::extend_line, six times on ropes that are NOT the last range of the particle array (each has to move to its end, and the
+    # array outgrows its allocation on the way): two new particles after the rope's last one every time
     lists, params = _host_ropes(sc)
     gb = a.get_bodies()
-    last = lists[1][-1]
-    nb0, nc0 = len(sc["bodies"]), len(sc["colliders"])
+    nb0 = len(sc["bodies"])
     from moleengine_b200 import shapes
-    new_b = np.zeros(5, abi.body_dtype)
-    shapes.fill_bodies_particle(new_b, 0.02, gb["x"][last] + 0.1 * np.arange(1, 6), np.full(5, gb["y"][last]))
-    new_c = np.zeros(5, abi.collider_dtype)
-    shapes.fill_colliders(new_c, shapes.circle(np.full(5, 0.06)), body=nb0 + np.arange(5), layer=abi.ROPE_LAYER, static_friction=None, dynamic_friction=1.5)
+    targets = [1, 2, 3, 0, 4, 1]
+    new_b = np.zeros(2 * len(targets), abi.body_dtype)
+    px, py = [], []
+    tails = {}
+    for k, r in enumerate(targets):
+        last = tails.get(r, lists[r][-1])
+        lx, ly = (float(gb["x"][last]), float(gb["y"][last])) if last < nb0 else (px[last - nb0], py[last - nb0])
+        px += [lx + 0.1, lx + 0.2]; py += [ly, ly]
+        tails[r] = nb0 + 2 * k + 1
+    shapes.fill_bodies_particle(new_b, 0.02, np.array(px), np.array(py))
+    new_c = np.zeros(len(new_b), abi.collider_dtype)
+    shapes.fill_colliders(new_c, shapes.circle(np.full(len(new_b), 0.06)), body=nb0 + np.arange(len(new_b)), layer=abi.ROPE_LAYER, static_friction=None, dynamic_friction=1.5)
     for w in (a, b):
         cur = w.get_bodies()
         cur["flags"] &= 15
         w.set_bodies(np.concatenate([cur, new_b]))            # the slot space GROWS: ropes and constraints stay
         w.set_colliders(np.concatenate([sc["colliders"], new_c]))
-    a.rope_extend(1, nb0 + np.arange(5))
-    lists[1] = lists[1] + list(range(nb0, nb0 + 5))
+    for k, r in enumerate(targets):
+        slots = [nb0 + 2 * k, nb0 + 2 * k + 1]
+        a.rope_extend(r, slots)
+        lists[r] = lists[r] + slots
     b.set_constraints(sc["constraints"])
     _upload(b, lists, params)
     ra, pa = a.get_ropes()
@@ -108,9 +118,9 @@ def test_extend_appends_particles_without_reuploading_the_rope():
         a.tick(); b.tick()
     assert _same(a, b), "device-side extend and host re-upload diverged"
     gb = a.get_bodies()
-    chain = lists[1]
-    d = np.hypot(np.diff(gb["x"][chain].astype(np.float64)), np.diff(gb["y"][chain].astype(np.float64)))
-    assert np.abs(d - 0.1).max() < 0.03, "the extended rope is not a chain"
+    for chain in lists:
+        d = np.hypot(np.diff(gb["x"][chain].astype(np.float64)), np.diff(gb["y"][chain].astype(np.float64)))
+        assert np.abs(d - 0.1).max() < 0.03, "an extended rope is not a chain"
     a.close(); b.close()
 
 
