@@ -307,19 +307,29 @@ SFG_DI int clip_edge(const Edge& target, const Edge& edge, float* enters, float*
 
 // shape_shape.rs:160-349. Everything is kept in named registers (no dynamically indexed arrays): the SAT loop is
 // unrolled over the two owners, and the winning owner's data is picked with selects afterwards.
+// the outward normal of edge i alone (what get_edge(s, i).n is): the SAT loop needs nothing else of the edge
+SFG_DI V2 edge_normal(const Shape& s, int i) {
+    if (s.kind == K_RECT) return i == 0 ? mk(1.f, 0.f) : mk(0.f, 1.f);
+    if (s.kind == K_SEGMENT) return mk(0.f, 1.f);
+    if (s.kind == K_TRIANGLE) return i == 0 ? mk(0.f, -1.f) : (i == 1 ? mk(SFG_PI6_COS, SFG_PI6_SIN) : mk(-SFG_PI6_COS, SFG_PI6_SIN));
+    return i == 0 ? mk(SFG_PI6_COS, SFG_PI6_SIN) : (i == 1 ? mk(0.f, 1.f) : mk(-SFG_PI6_COS, SFG_PI6_SIN));
+}
 SFG_DI void sat_pass(const Shape& own, const Shape& oth, V2 dist, Rot rel_own_r, float r_sum, int pass, float& pen_depth, int& pen_code, bool& separated) {
     const int n = edge_count(own);
     const bool sym = symmetrical(own);
-    for (int ei = 0; ei < n; ++ei) {
-        PEdge e = get_edge(own, ei);
+    const float rc = rel_own_r.s * rel_own_r.s - rel_own_r.b * rel_own_r.b, rsn = 2.0f * rel_own_r.s * rel_own_r.b;   // operator*(Rot, V2), its two products once per pass
+#pragma unroll
+    for (int ei = 0; ei < 3; ++ei) {
+        if (ei >= n) break;
+        V2 en = edge_normal(own, ei);
         bool mir = false;
-        if (!(dot(e.n, dist) >= 0.f)) {
-            if (sym) { e.n = -e.n; mir = true; }
+        if (!(dot(en, dist) >= 0.f)) {
+            if (sym) { en = -en; mir = true; }
             else continue;
         }
         const float ext = edge_extent(own, ei);
-        const V2 axis_o = -(rel_own_r * e.n);
-        const float depth = ext + projected_extent(oth, axis_o) + r_sum - dot(dist, e.n);
+        const V2 axis_o = -mk(rc * en.x + rsn * en.y, rc * en.y - rsn * en.x);
+        const float depth = ext + projected_extent(oth, axis_o) + r_sum - dot(dist, en);
         if (depth <= 0.f) { separated = true; return; }
         if (depth < pen_depth) { pen_depth = depth; pen_code = pass * 8 + ei * 2 + (mir ? 1 : 0); }   // the winner is rebuilt after the loop
     }
