@@ -151,7 +151,7 @@ struct SfgWorld {
     DBuf<float4> H, S, G0, G1, L0, L1, M0, M1, M2;
     DBuf<float2> LN;
     DBuf<float> RC;
-    DBuf<uint32_t> WL, wl_count, near_count, far_min;
+    DBuf<uint32_t> WL, wl_count, near_count, far_min, steal;
     uint32_t last_substeps = 0;   // substeps of the last tick: tag_base + last_substeps = tag of a manifold entry written in its last substep
     uint32_t tick_seq = 0;        // ticks begun so far; its low 12 bits go into the manifold tags
     float4* m0_cleared = nullptr; // the M0 allocation that was last cleared
@@ -1430,7 +1430,12 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
     // islands and colouring both only read the pair list: the island pass runs on a second stream next to the colouring
     // (union-find and the colouring dataflow are latency-bound and leave most of the machine idle on their own); the join is
     // in front of k_build_pair_units, the first reader of the asleep / foreign flags the island pass leaves on the bodies
-    if (w->tick_sleeping) {
+    static const bool islands_inline = getenv("SFG_ISLANDS_INLINE") != nullptr;      // A/B switch: the island pass on the main stream, in front of the colouring
+    if (w->tick_sleeping && islands_inline) {
+        w->island_flags_live = true;
+        rc = island_pass(w, st);
+        if (rc != SFG_OK) return rc;
+    } else if (w->tick_sleeping) {
         CK(cudaEventRecord(w->ev_fork, st));
         CK(cudaStreamWaitEvent(w->stream2, w->ev_fork, 0));
         w->island_flags_live = true;
@@ -1462,6 +1467,12 @@ int sfg_tick_begin(SfgWorld* w, double frame_dt, int has_time_scale, double time
             CK(w->far_min.ensure(size_t(substeps) * w->h_stages.size()));
             CK(cudaMemsetAsync(w->far_min.p, 0xFF, size_t(substeps) * w->h_stages.size() * 4, st));
             w->tick_ctx.far_min = w->far_min.p;
+        }
+        {   // one work-stealing counter per stage and substep (k_solve_persistent deals the tail of a big stage from it)
+            const size_t n_ctr = size_t(substeps) * w->h_stages.size() + 1;
+            CK(w->steal.ensure(n_ctr));
+            CK(cudaMemsetAsync(w->steal.p, 0, n_ctr * 4, st));
+            w->tick_ctx.steal = w->steal.p;
         }
         if (!(w->tuning.flags & SFG_TUNE_SEPARATE_LAUNCHES)) {
             const uint32_t ns = uint32_t(w->h_stages.size());

@@ -32,6 +32,11 @@ constexpr int MAX_LEVELS = 8;
                                     // 512: 0.85 / 4.48 / 15.7, 640 (96 registers, 64 B of spills): 0.87 / 4.59 / 16.5, 768 (80, 176 B): 0.90 / 4.77 / 16.9
 #endif
 
+#ifndef SFG_STEAL_PERCENT
+#define SFG_STEAL_PERCENT 15u       // share of a big stage's items that is not dealt to CTAs up front but taken from one global counter by
+                                    // whichever warp runs out of work first (evens out the CTAs; 0 = off)
+#endif
+
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -100,6 +105,7 @@ struct SolverCtx {
     float2* LN;
     uint32_t* WL;
     uint32_t* wl_count;
+    uint32_t* steal;              // [substep * n_stages + stage]: next item of that stage's stolen tail (k_solve_persistent)
     uint32_t* far_min;            // [substep * n_stages + first stage of a merged far-only run]: the first stage of that run with a surviving unit (0xFFFFFFFF = none)
     uint32_t* stat_touch;         // SFG_TUNE_COUNT_ENTRIES: [0] += units, [1] += entries whose first visit found a contact (nullptr = not counted)
     const uint32_t* near_count;   // per contact colour: units sorted first inside the colour because they may touch this tick
