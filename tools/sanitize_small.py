@@ -1,5 +1,7 @@
-"""A small tour of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck):
+"""A small tour of every kernel family, written for compute-sanitizer (memcheck / racecheck / synccheck):
     compute-sanitizer --tool memcheck python tools/sanitize_small.py
+(compute-sanitizer is closed on the pool this repository is developed on; tests/test_gpu_tour.py runs the same tour plainly, so a
+crash or a CUDA error in any of these paths still fails the GPU suite)
 ticks of a mixed scene (persistent solver and one launch per stage), rope topology edits, casts and queries, batched worlds,
 island shards and slabs exchanged in-process (synchronous and stream-ordered), pose sync."""
 import os
