@@ -464,15 +464,18 @@ __global__ void k_rope_build(uint32_t n_slots, const int* __restrict__ rp_body, 
     RD[rec.rd_off[i % 2] + i / 2] = make_int4(cur, nxt, r, 0);
     rope_next[cur] = nxt; rope_prev[nxt] = cur;
 }
-__global__ void k_rope_assign(uint32_t first, uint32_t count, int rope, int* rp_rope) {      // a range of the particle array changes hands
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) rp_rope[first + i] = rope;
+// rp_rope from the rope table: one warp per rope labels its range of the particle array (the array was set to -1 = hole before)
+__global__ void k_rope_label(uint32_t n_ropes, const RopeBuildRec* __restrict__ recs, int* __restrict__ rp_rope) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (r >= n_ropes) return;
+    const uint32_t first = recs[r].first, count = recs[r].count;
+    for (uint32_t i = lane; i < count; i += 32u) rp_rope[first + i] = int(r);
 }
-__global__ void k_rope_move(uint32_t from, uint32_t to, uint32_t count, int rope, int* rp_body, int* rp_rope) {   // to >= from + count (moves go to the end of the array)
+__global__ void k_rope_move(uint32_t from, uint32_t to, uint32_t count, int* rp_body) {   // to >= from + count (moves go to the end of the array)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    rp_body[to + i] = rp_body[from + i]; rp_rope[to + i] = rope;
-    rp_body[from + i] = -1; rp_rope[from + i] = -1;
+    rp_body[to + i] = rp_body[from + i];
+    rp_body[from + i] = -1;
 }
 // rope.rs:226-286: which particles lost their body? appends their positions in the particle array to `out` (unordered)
 __global__ void k_rope_find_dead(uint32_t n_slots, const int* __restrict__ rp_body, const int* __restrict__ rp_rope, const float4* __restrict__ MI, uint32_t n_bodies,
@@ -816,6 +819,28 @@ int sfg_set_constraints(SfgWorld* w, uint32_t n, const SfgConstraint* c) {
     return SFG_OK;
 }
 
+// rp_rope (particle -> rope, -1 = hole) is derived data: rebuilt from the host table after every edit, in one small upload and
+// two launches whatever the number of ropes
+static int relabel_rope_particles(SfgWorld* w) {
+    cudaStream_t st = w->stream;
+    const uint32_t nr = uint32_t(w->rope_tab.size());
+    w->n_ropes = nr;
+    w->ropes_dirty = true;
+    if (w->n_particles == 0) return SFG_OK;
+    CK(w->rp_rope.ensure(w->n_particles));
+    CK(cudaMemsetAsync(w->rp_rope.p, 0xFF, size_t(w->n_particles) * 4, st));
+    if (nr) {
+        std::vector<RopeBuildRec> recs(nr);
+        for (uint32_t r = 0; r < nr; ++r) { memset(&recs[r], 0, sizeof(RopeBuildRec)); recs[r].first = w->rope_tab[r].first_particle; recs[r].count = w->rope_tab[r].particle_count; }
+        CK(w->rope_build.ensure(nr));
+        CK(cudaMemcpyAsync(w->rope_build.p, recs.data(), size_t(nr) * sizeof(RopeBuildRec), cudaMemcpyHostToDevice, st));
+        k_rope_label<<<nblk(nr * 32u), 256, 0, st>>>(nr, w->rope_build.p, w->rp_rope.p);
+        CKL(w);
+    }
+    CK(cudaStreamSynchronize(st));        // recs is a stack-lifetime host buffer
+    return SFG_OK;
+}
+
 // Rope topology lives in two places: a small table of ranges on the host (one entry per rope: where its particles sit in the
 // device's particle array, and its parameters) and the particle array itself on the device (rp_body: particle -> body slot, -1 =
 // hole). Everything the solver reads — step units (curr, next, after) coloured i mod 3 (solver.rs:118-179 touches particles i,
@@ -843,14 +868,12 @@ int sfg_set_ropes(SfgWorld* w, uint32_t n_ropes, const SfgRope* ropes, uint32_t 
     w->rope_tab.assign(ropes, ropes + n_ropes);
     w->n_ropes = n_ropes; w->n_particles = n_particles;
     w->n_rope_units = w->n_rope_damp = 0;
-    w->ropes_dirty = true;
     if (n_particles) {
-        CK(w->rp_body.ensure(n_particles)); CK(w->rp_rope.ensure(n_particles));
+        CK(w->rp_body.ensure(n_particles));
         CK(cudaMemcpyAsync(w->rp_body.p, rp_body.data(), size_t(n_particles) * 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(w->rp_rope.p, rp_rope.data(), size_t(n_particles) * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
     }
-    CK(cudaStreamSynchronize(st));
-    return SFG_OK;
+    return relabel_rope_particles(w);
 }
 
 // Rope::cut_after (rope.rs:147-165), by position: the rope keeps particles [0, particle_index], the rest becomes a NEW rope with
@@ -863,26 +886,18 @@ int sfg_rope_cut_after(SfgWorld* w, uint32_t rope, uint32_t particle_index, uint
     SfgRope& r = w->rope_tab[rope];
     if (particle_index >= r.particle_count) return fail(w, SFG_E_INVALID, "particle index beyond the rope");
     cudaSetDevice(w->device);
-    cudaStream_t st = w->stream;
     if (particle_index + 1 == r.particle_count) {
-        k_rope_assign<<<1, 32, 0, st>>>(r.first_particle + particle_index, 1, -1, w->rp_rope.p);    // the popped particle leaves the rope (its body lives on)
-        CKL(w);
-        r.particle_count -= 1;
+        r.particle_count -= 1;                // the popped particle leaves the rope (its body lives on): its slot becomes a hole
     } else {
         SfgRope tail = r;
         tail.first_particle = r.first_particle + particle_index + 1;
         tail.particle_count = r.particle_count - particle_index - 1;
         r.particle_count = particle_index + 1;
         const uint32_t idx = uint32_t(w->rope_tab.size());
-        k_rope_assign<<<nblk(tail.particle_count), 256, 0, st>>>(tail.first_particle, tail.particle_count, int(idx), w->rp_rope.p);
-        CKL(w);
         w->rope_tab.push_back(tail);          // (invalidates r)
         if (new_rope_out) *new_rope_out = idx;
     }
-    w->n_ropes = uint32_t(w->rope_tab.size());
-    w->ropes_dirty = true;
-    CK(cudaStreamSynchronize(st));
-    return SFG_OK;
+    return relabel_rope_particles(w);
 }
 
 // Rope::extend_line (rope.rs:88-110): the host spawned `n_new` particle bodies (Rope::build_line) and uploaded them with the
@@ -900,32 +915,24 @@ int sfg_rope_extend(SfgWorld* w, uint32_t rope, uint32_t n_new, const int32_t* p
     const bool at_end = r.first_particle + r.particle_count == w->n_particles;
     const uint32_t new_len = at_end ? w->n_particles + n_new : w->n_particles + r.particle_count + n_new;
     if (new_len > w->rp_body.cap) {          // grow both columns, keeping their contents
-        DBuf<int> nb, nr;
-        nb.yard = w->graveyard; nr.yard = w->graveyard;
-        CK(nb.ensure(size_t(new_len) * 2)); CK(nr.ensure(size_t(new_len) * 2));
-        if (w->n_particles) {
-            CK(cudaMemcpyAsync(nb.p, w->rp_body.p, size_t(w->n_particles) * 4, cudaMemcpyDeviceToDevice, st));
-            CK(cudaMemcpyAsync(nr.p, w->rp_rope.p, size_t(w->n_particles) * 4, cudaMemcpyDeviceToDevice, st));
-        }
+        DBuf<int> nb;                       // (rp_rope is derived data: relabel_rope_particles re-creates it at the new size)
+        nb.yard = w->graveyard;
+        CK(nb.ensure(size_t(new_len) * 2));
+        if (w->n_particles) CK(cudaMemcpyAsync(nb.p, w->rp_body.p, size_t(w->n_particles) * 4, cudaMemcpyDeviceToDevice, st));
         CK(cudaStreamSynchronize(st));
         std::swap(w->rp_body.p, nb.p); std::swap(w->rp_body.cap, nb.cap);
-        std::swap(w->rp_rope.p, nr.p); std::swap(w->rp_rope.cap, nr.cap);
         if (nb.p) { w->graveyard->add(nb.p); nb.p = nullptr; nb.cap = 0; }      // never cudaFree in the middle of a run (DBuf's comment)
-        if (nr.p) { w->graveyard->add(nr.p); nr.p = nullptr; nr.cap = 0; }
     }
     if (!at_end) {
-        k_rope_move<<<nblk(r.particle_count), 256, 0, st>>>(r.first_particle, w->n_particles, r.particle_count, int(rope), w->rp_body.p, w->rp_rope.p);
+        k_rope_move<<<nblk(r.particle_count), 256, 0, st>>>(r.first_particle, w->n_particles, r.particle_count, w->rp_body.p);
         CKL(w);
         r.first_particle = w->n_particles;
     }
     CK(cudaMemcpyAsync(w->rp_body.p + r.first_particle + r.particle_count, particle_bodies, size_t(n_new) * 4, cudaMemcpyHostToDevice, st));
-    k_rope_assign<<<nblk(n_new), 256, 0, st>>>(r.first_particle + r.particle_count, n_new, int(rope), w->rp_rope.p);
-    CKL(w);
+    CK(cudaStreamSynchronize(st));
     r.particle_count += n_new;
     w->n_particles = new_len;
-    w->ropes_dirty = true;
-    CK(cudaStreamSynchronize(st));
-    return SFG_OK;
+    return relabel_rope_particles(w);
 }
 
 // RopeSet::remove_dead_particles (rope.rs:226-286) against the bodies the device holds: a particle whose body slot is no longer
@@ -977,18 +984,10 @@ int sfg_rope_remove_dead_particles(SfgWorld* w, uint32_t* n_ropes_out) {
     std::vector<SfgRope> kept;
     for (const SfgRope& r : w->rope_tab) if (r.particle_count > 0) kept.push_back(r);
     w->rope_tab.swap(kept);
-    // the particle array: dead slots become holes, every piece is re-labelled with its rope's (new) index
-    for (uint32_t d : dead) { k_rope_assign<<<1, 32, 0, st>>>(d, 1, -1, w->rp_rope.p); CKL(w); }
-    for (size_t ri = 0; ri < w->rope_tab.size(); ++ri) {
-        const SfgRope& r = w->rope_tab[ri];
-        k_rope_assign<<<nblk(r.particle_count), 256, 0, st>>>(r.first_particle, r.particle_count, int(ri), w->rp_rope.p);
-        CKL(w);
-    }
-    w->n_ropes = uint32_t(w->rope_tab.size());
-    w->ropes_dirty = true;
+    // the particle array: dead slots become holes, every piece carries its rope's (new) index
+    int rc = relabel_rope_particles(w);
     if (n_ropes_out) *n_ropes_out = w->n_ropes;
-    CK(cudaStreamSynchronize(st));
-    return SFG_OK;
+    return rc;
 }
 
 // The rope table as the library holds it now, compacted: ropes_out[i].first_particle indexes particle_bodies_out (holes removed).

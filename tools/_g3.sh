@@ -1,3 +1,2 @@
 set -x
-timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/r02_sanitizer_memcheck.txt 2>&1; echo "memcheck rc=$?"; tail -5 gpurun_out/r02_sanitizer_memcheck.txt
-timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/r02_sanitizer_racecheck.txt 2>&1; echo "racecheck rc=$?"; tail -5 gpurun_out/r02_sanitizer_racecheck.txt
+timeout 600 python -m pytest tests/test_gpu_rope_edits.py tests/test_gpu_tour.py tests/test_gpu_scenes.py tests/test_gpu_islands.py tests/test_host_cpp.py -m gpu -q > gpurun_out/r02s_pytest.log 2>&1; echo "pytest rc=$?"; tail -6 gpurun_out/r02s_pytest.log
