@@ -1321,8 +1321,15 @@ int island_pass(SfgWorld* w, cudaStream_t st) {
     const uint32_t n_edges = c.n_units + c.n_constraints + c.n_links;
     k_isl_init<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
     if (n_edges) {
-        k_isl_union<<<nblk(n_edges), 256, 0, st>>>(c); CKL(w); w->launches++;
-        k_isl_sums<<<nblk(n_edges), 256, 0, st>>>(c); CKL(w); w->launches++;
+        // SFG_ISL_PHASES (debug): 1 = every edge in one launch, 2 = halves, 3 = 1/4 1/4 1/2, 4 (default) = 1/8 1/8 1/4 1/2
+        static const int n_phases = [] { const char* e = getenv("SFG_ISL_PHASES"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 4 ? 4 : v); }();
+        static const uint32_t plan[4][4][2] = {{{0, 8}}, {{0, 4}, {4, 4}}, {{0, 2}, {2, 2}, {4, 4}}, {{0, 1}, {1, 1}, {2, 2}, {4, 4}}};
+        for (int ph = 0; ph < n_phases; ++ph) {
+            const uint32_t lo = plan[n_phases - 1][ph][0], width = plan[n_phases - 1][ph][1];
+            const uint32_t n_threads = (n_edges + 7u) / 8u * width;
+            k_isl_union<<<nblk(n_threads), 256, 0, st>>>(c, lo, width, n_edges, ph ? 1u : 0u); CKL(w); w->launches++;
+            if (ph + 1 < n_phases) { k_isl_flatten<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++; }   // k_isl_bodies_pre is the last one
+        }
     }
     k_isl_bodies_pre<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;
     k_isl_decide<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;

@@ -106,36 +106,33 @@ __device__ __forceinline__ bool isl_edge(const IslandCtx& c, uint32_t i, int* a,
     }
     return false;
 }
-__global__ void __launch_bounds__(256) k_isl_union(IslandCtx c) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    int a, b; uint32_t ns;
-    if (!isl_edge(c, i, &a, &b, &ns)) return;
-    if (a >= 0 && b >= 0 && a != b) uf_union(c.parent, uint32_t(a), uint32_t(b));
-}
-__global__ void __launch_bounds__(256) k_isl_sums(IslandCtx c) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// The edges are united in phases of growing size (1/8, 1/8, 1/4, 1/2 of them, each phase a stride-8 sample of the whole list, so
+// every phase touches every neighbourhood), with the forest flattened in between: after the first phases almost every edge finds
+// both ends under the same parent in one look and is done, instead of chasing two chains to the root of a pile.
+__global__ void __launch_bounds__(256) k_isl_union(IslandCtx c, uint32_t lo, uint32_t width, uint32_t n_edges, uint32_t fast) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = (t / width) * 8u + lo + (t % width);
+    if (i >= n_edges) return;
     int a, b; uint32_t ns;
     if (!isl_edge(c, i, &a, &b, &ns)) return;
     if (a < 0 && b < 0) return;
-    const uint32_t root = uf_find(c.parent, uint32_t(a >= 0 ? a : b));
-    unsigned long long add;
-    if (a >= 0 && b >= 0) add = 2ull * ((unsigned long long)(a) + 1ull) * ((unsigned long long)(b) + 1ull);
-    else add = (unsigned long long)(a >= 0 ? a : b) + 1ull;
-    // one atomic per group of lanes that share a root (a pile is ONE island: 32 lanes, one address)
-    const uint32_t act = __activemask();
-    const uint32_t peers = __match_any_sync(act, root);
-    const int leader = __ffs(int(peers)) - 1, lane = int(threadIdx.x & 31u);
-    unsigned long long total = 0ull;
-    uint32_t any_ns = 0u;
-    for (uint32_t m = peers; m; m &= m - 1u) {
-        const int src = __ffs(int(m)) - 1;
-        total += __shfl_sync(peers, add, src);
-        any_ns |= __shfl_sync(peers, ns, src);
-    }
-    if (lane == leader) {
-        atomicAdd(c.isl_sum + root, total);
-        if (any_ns && !(__ldcg(c.isl_flags + root) & IF_NO_SLEEP)) atomicOr(c.isl_flags + root, IF_NO_SLEEP);
-    }
+    // edge_sum and "never sleeps" are gathered per BODY here (fire-and-forget reductions on the edge's first dynamic body) and
+    // folded into the island's root by k_isl_bodies_pre: wrapping sums and ORs do not care about the order
+    const uint32_t home = uint32_t(a >= 0 ? a : b);
+    atomicAdd(c.isl_sum + home, a >= 0 && b >= 0 ? 2ull * ((unsigned long long)(a) + 1ull) * ((unsigned long long)(b) + 1ull)
+                                                 : (unsigned long long)(home) + 1ull);
+    if (ns) atomicOr(c.isl_flags + home, IF_NO_SLEEP);
+    if (a < 0 || b < 0 || a == b) return;
+    if (fast && __ldcg(c.parent + a) == __ldcg(c.parent + b)) return;     // same parent: same island already
+    uf_union(c.parent, uint32_t(a), uint32_t(b));
+}
+__global__ void __launch_bounds__(256) k_isl_flatten(IslandCtx c) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.n_bodies) return;
+    const uint32_t p = __ldcg(c.parent + b);
+    if (p == b) return;
+    const uint32_t root = uf_find(c.parent, p);
+    if (root != p) __stcg(c.parent + b, root);
 }
 // per body: final label, island size, "moved between frames" test on the incoming velocities (physics.rs:722-731)
 __global__ void __launch_bounds__(256) k_isl_bodies_pre(IslandCtx c) {
@@ -146,13 +143,21 @@ __global__ void __launch_bounds__(256) k_isl_bodies_pre(IslandCtx c) {
     c.parent[b] = root;
     const float4 v = c.V[b];
     const uint32_t moving = v.x * v.x + v.y * v.y + v.z * v.z >= c.sleep_vel_threshold ? 1u : 0u;
+    // this body's share of the island's edge_sum / no-sleep flag (k_isl_union); the root's own share is already in place
+    const unsigned long long part = b != root ? c.isl_sum[b] : 0ull;
+    const uint32_t part_ns = b != root ? (c.isl_flags[b] & IF_NO_SLEEP) : 0u;
     const uint32_t act = __activemask();
     const uint32_t peers = __match_any_sync(act, root);
     const uint32_t peers_moving = __ballot_sync(act, moving != 0u) & peers;
+    const uint32_t peers_ns = __ballot_sync(act, part_ns != 0u) & peers;
+    unsigned long long total = 0ull;
+    for (uint32_t m = peers; m; m &= m - 1u) total += __shfl_sync(peers, part, __ffs(int(m)) - 1);
     if (int(threadIdx.x & 31u) == __ffs(int(peers)) - 1) {   // lanes run in slot order: the group's leader holds its smallest slot
         atomicAdd(c.isl_count + root, uint32_t(__popc(peers)));
         atomicMin(c.isl_first + root, b);
-        if (peers_moving && !(__ldcg(c.isl_flags + root) & IF_MOVING)) atomicOr(c.isl_flags + root, IF_MOVING);
+        if (total) atomicAdd(c.isl_sum + root, total);
+        const uint32_t want = (peers_moving ? IF_MOVING : 0u) | (peers_ns ? IF_NO_SLEEP : 0u);
+        if (want && (__ldcg(c.isl_flags + root) & want) != want) atomicOr(c.isl_flags + root, want);
     }
 }
 // per island root: the retain() of physics.rs:714-737 and the record clean-up of :739
