@@ -374,11 +374,6 @@ __global__ void k_dbg_geometry(uint32_t op, uint32_t n, const float* args, const
     else if (op == 3) o[0] = point_in_collider(a, mkiso(mk(0.f, 0.f), mkrot(1.f, 0.f)), s) ? 1.f : 0.f;
 }
 
-__global__ void k_iota(uint32_t* p, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = i;
-}
-
 // ---- slab decomposition: one world cut into x-intervals, one per GPU; bodies near a cut are exchanged as 64-byte records
 struct HaloRec { uint32_t slot, pad[3]; float4 P, Q, V; };
 // zone_list[side * zone_cap + k] / zone_count[side]: the owned bodies within `halo` of the cut on that side, i.e. what every
@@ -606,9 +601,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         CK(cudaMemsetAsync(w->near_count.p, 0, size_t(n_colours) * 4, st));
         near_count = w->near_count.p;
     }
-    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, pair_units ? w->U_cls.p : nullptr, w->ckey0.p, near_count);
+    k_unit_sort_keys<<<nblk(n_units), 256, 0, st>>>(n_units, colour.p, pair_units ? w->U_cls.p : nullptr, w->ckey0.p, w->perm0.p, near_count);
     CKL(w); w->launches++;
-    k_iota<<<nblk(n_units), 256, 0, st>>>(w->perm0.p, n_units); CKL(w); w->launches++;
     int bits = 7;
     while ((1u << bits) < n_colours * 128u) ++bits;
     int launches = 0;
@@ -1355,7 +1349,7 @@ int island_post(SfgWorld* w) {
         CKL(w); w->launches++;
     }
     if (n_entries) {
-        k_contacts_append<<<nblk(n_entries), 256, 0, st>>>(n_entries, w->n_units, w->LN.p, w->H.p, w->S.p, w->isl_parent.p, w->isl_first.p, w->isl_sum.p, new_list.p, cursor);
+        k_contacts_append<<<nblk(w->n_units), 256, 0, st>>>(w->n_units, w->LN.p, w->H.p, w->S.p, w->isl_parent.p, w->isl_first.p, w->isl_sum.p, new_list.p, cursor);
         CKL(w); w->launches++;
     }
     k_isl_bodies_post<<<nblk(nb), 256, 0, st>>>(c); CKL(w); w->launches++;

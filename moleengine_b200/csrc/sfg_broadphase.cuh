@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) k_adj_fill(uint32_t n_units, const int2* 
 // and visit count, so the 32 lanes of a warp run the same branches. The order inside a colour cannot change results
 // (no shared dynamic body), only divergence.
 __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const uint32_t* __restrict__ colour, const uint8_t* __restrict__ ucls,
-                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ near_count) {
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ near_count) {
     __shared__ uint32_t s_near[64];
     if (threadIdx.x < 64) s_near[threadIdx.x] = 0u;
     __syncthreads();
@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(256) k_unit_sort_keys(uint32_t n_units, const 
         const uint32_t cls = ucls ? ucls[u] : 0u;            // k_pair_unit_setup; constraints have no classes
         const uint32_t col = colour[u];
         keys[u] = col * 128u + cls;
+        vals[u] = u;                                          // the sort's payload: the unit's index before the sort
         // how many units of each colour sort into its "may touch" head: the solver deals those out a few lanes per warp
         // (sfg_solver.cuh k_solve_persistent). Counted per block in shared memory, one global atomic per colour and block.
         if (near_count && !(cls & 64u)) {

@@ -229,24 +229,41 @@ __global__ void __launch_bounds__(256) k_contacts_retain(uint32_t n_old, const C
     if (r.root >= n_bodies) return;
     if (sl_valid[r.root] && sl_sum[r.root] == r.sum && sl_ticks[r.root] >= fall_asleep_frames) out[atomicAdd(cursor, 1u)] = r;
 }
-// this tick's latched contacts (solver.rs:318-320), tagged with the island they belong to
-__global__ void __launch_bounds__(256) k_contacts_append(uint32_t n_entries, uint32_t n_units, const float2* __restrict__ LN,
+// this tick's latched contacts (solver.rs:318-320), tagged with the island they belong to. One thread per unit looks at both of
+// its entries (the second visit of a body-body pair latches its own normal) and reads the unit's header and island once; the
+// records of a warp go out behind one atomic.
+__global__ void __launch_bounds__(256) k_contacts_append(uint32_t n_units, const float2* __restrict__ LN,
                                                          const float4* __restrict__ H, const float4* __restrict__ S,
                                                          const uint32_t* __restrict__ parent, const uint32_t* __restrict__ isl_first,
                                                          const unsigned long long* __restrict__ isl_sum, ContactRec* __restrict__ out,
                                                          uint32_t* cursor) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_entries) return;
-    const float2 n = LN[e];
-    if (isnan(n.x) && isnan(n.y)) return;
-    const float4 h = H[e % n_units], s = S[e % n_units];
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    float2 n0 = make_float2(0.f, 0.f), n1 = n0;
+    bool t0 = false, t1 = false;
+    if (u < n_units) {
+        n0 = LN[u]; n1 = LN[u + n_units];
+        t0 = !(isnan(n0.x) && isnan(n0.y)); t1 = !(isnan(n1.x) && isnan(n1.y));
+    }
+    const uint32_t cnt = (t0 ? 1u : 0u) + (t1 ? 1u : 0u);
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (int(lane) >= o) incl += v; }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (total == 0u) return;
+    uint32_t base = 0;
+    if (lane == 31u) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - cnt;
+    if (cnt == 0u) return;
+    const float4 h = H[u], s = S[u];
     const int b0 = __float_as_int(h.x), b1 = __float_as_int(h.y);
     ContactRec r;
-    r.c0 = __float_as_uint(s.x); r.c1 = __float_as_uint(s.y); r.nx = n.x; r.ny = n.y; r.pad = 0u;
+    r.c0 = __float_as_uint(s.x); r.c1 = __float_as_uint(s.y); r.pad = 0u;
     const uint32_t rep = parent[b0 >= 0 ? b0 : b1];
     r.root = isl_first[rep];          // IslandId::first_body: where the sleeping record of this island would sit
     r.sum = isl_sum[rep];
-    out[atomicAdd(cursor, 1u)] = r;
+    if (t0) { r.nx = n0.x; r.ny = n0.y; out[base++] = r; }
+    if (t1) { r.nx = n1.x; r.ny = n1.y; out[base] = r; }
 }
 __global__ void __launch_bounds__(256) k_contacts_export(uint32_t n, const ContactRec* __restrict__ list, uint32_t* __restrict__ out4) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
