@@ -530,11 +530,15 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_colour_dataflow, SFG_COLOUR_THREADS, 0));
     const uint32_t grid = std::max(1u, std::min<uint32_t>(uint32_t(per_sm * w->n_sms), nblk(n_units, SFG_COLOUR_THREADS)));
-    // a bucket must span far fewer units than the co-resident threads (progress argument in k_colour_dataflow):
-    // 2^bits buckets of ~n / 2^bits units each (priorities are hashes), kept under 1/8 of the resident threads
+    // a bucket must span fewer units than there are co-resident threads (progress argument in k_colour_dataflow): 2^bits buckets,
+    // the `near` bit is the top bit of the priority and the rest is a hash, so a bucket holds at most n / 2^(bits - 1) units (all
+    // units near, or all far) give or take Poisson noise; that worst case is kept under HALF of the resident threads. (It was an
+    // eighth: the settled C3 pile then needs 16 bits = two radix passes over 4 M keys instead of one, 80 us of a 1.4 ms graph
+    // phase, and the colouring itself is no slower with the wider buckets; measured in a same-box A/B, C5 -155 us.)
+    // SFG_BUCKET_MARGIN (debug) overrides the factor.
     int bucket_bits = 8;
-    // (the `near` bit splits the priority space in two halves that need not be equally full: allow for buckets twice the mean)
-    while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * 8 > size_t(grid) * SFG_COLOUR_THREADS) bucket_bits += 8;
+    static const int margin = [] { const char* e = getenv("SFG_BUCKET_MARGIN"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+    while (bucket_bits < 24 && (size_t(n_units) >> (bucket_bits - 1)) * size_t(margin) > size_t(grid) * SFG_COLOUR_THREADS) bucket_bits += 8;
     w->launches += scan_exclusive(w->deg.p, w->adj_start.p, nb + 1, w->scan_tmp.p, nullptr, st);
     CK(cudaMemsetAsync(w->cursor.p, 0, size_t(nb + 1) * 4, st));
     CK(w->adj_body.ensure(size_t(nr) * 2 + 1)); CK(w->adj_rank.ensure(size_t(nr) + 1));
