@@ -98,6 +98,8 @@ struct SfgWorld {
     cudaEvent_t ev_cast[2] = {nullptr, nullptr};
     cudaEvent_t ev_fence = nullptr;          // sfg_stream_fence
     float last_cast_ms = 0.f;
+    uint32_t* pin = nullptr;                 // 1 KB of page-locked host memory: where the tick's small read-backs land (a pageable
+                                             // target makes cudaMemcpyAsync stage the copy through the driver)
     uint32_t n_k_two = 0;                    // two-body constraints (visited twice per substep)
     std::string err;
     SfgTuning tuning{};
@@ -579,8 +581,8 @@ int colour_units(SfgWorld* w, uint32_t n_units, const uint2* ids, const int2* ub
         }
     }
     // one read-back for the control words and the first 64 colours (a second one only if there are more)
-    uint32_t head[16 + 64];
-    CK(cudaMemcpyAsync(head, w->jp_counters.p, sizeof(head), cudaMemcpyDeviceToHost, st));
+    uint32_t* head = w->pin;                       // 80 words
+    CK(cudaMemcpyAsync(head, w->jp_counters.p, (16 + 64) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint32_t n_colours = head[1];
     w->stats_jp_rounds = head[4];
@@ -655,6 +657,7 @@ int sfg_world_create(const SfgTuning* tuning, const uint64_t mask_matrix[64], in
     for (auto& e : w->ev) cudaEventCreate(&e);
     for (auto& e : w->ev_cast) cudaEventCreate(&e);
     if (w->d_mask.ensure(64) != cudaSuccess || w->hdr.ensure(1) != cudaSuccess || w->tick_counts.ensure(4) != cudaSuccess) { delete w; delete yard; return SFG_E_CUDA; }
+    if (cudaHostAlloc((void**)&w->pin, 1024, cudaHostAllocDefault) != cudaSuccess) { w->pin = nullptr; delete w; delete yard; return SFG_E_CUDA; }
     cudaMemcpyAsync(w->d_mask.p, w->mask, sizeof(w->mask), cudaMemcpyHostToDevice, w->stream);
     cudaStreamSynchronize(w->stream);
     *out = w;
@@ -689,6 +692,7 @@ void sfg_world_destroy(SfgWorld* w) {
     if (w->ev_fork) cudaEventDestroy(w->ev_fork);
     if (w->ev_join) cudaEventDestroy(w->ev_join);
     if (w->stream2) cudaStreamDestroy(w->stream2);
+    if (w->pin) cudaFreeHost(w->pin);
     if (w->stream) cudaStreamDestroy(w->stream);
     Graveyard* yard = w->graveyard;
     delete w;
@@ -1152,7 +1156,8 @@ int broadphase(SfgWorld* w, float frame_dt) {
     const float pad = w->tuning.max_expected_acceleration * frame_dt;
     k_aabb<<<nblk(nc), 256, 0, st>>>(nc, w->CS.p, w->CL.p, w->CI.p, w->P.p, w->Q.p, w->V.p, w->MI.p, frame_dt, pad, w->AABB.p, &w->hdr.p->bounds);
     CKL(w); w->launches++;
-    TickHeader h;
+    static_assert(sizeof(TickHeader) <= 512, "pinned read-back block");
+    TickHeader& h = *reinterpret_cast<TickHeader*>(w->pin);
     CK(cudaMemcpyAsync(&h, w->hdr.p, sizeof(h), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     w->n_live = h.bounds.n_live;
@@ -1164,9 +1169,9 @@ int broadphase(SfgWorld* w, float frame_dt) {
     k_cell_count<<<nblk(nc), 256, 0, st>>>(g, nc, w->AABB.p, w->cell_cnt.p);
     CKL(w); w->launches++;
     w->launches += scan_exclusive(w->cell_cnt.p, w->cell_off.p, nc, w->scan_tmp.p, &w->hdr.p->n_entries, st);
-    uint32_t ne = 0;
-    CK(cudaMemcpyAsync(&ne, &w->hdr.p->n_entries, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(w->pin + 200, &w->hdr.p->n_entries, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    const uint32_t ne = w->pin[200];
     w->n_entries = ne;
     if (ne == 0) { w->n_live = 0; return SFG_OK; }
     CK(w->keys0.ensure(ne)); CK(w->keys1.ensure(ne)); CK(w->vals0.ensure(ne)); CK(w->vals1.ensure(ne));
@@ -1198,9 +1203,9 @@ int broadphase(SfgWorld* w, float frame_dt) {
         CK(cudaMemsetAsync(&w->hdr.p->n_pairs, 0, 4, st));
         k_pairs<<<nblk(n_warps * 32), 256, 0, st>>>(g, w->n_live, w->SA.p, w->SI.p, keys, w->cell_start.p, w->d_mask.p, &w->hdr.p->n_pairs, w->U_ids.p, cap);
         CKL(w); w->launches++;
-        uint32_t n_pairs = 0;
-        CK(cudaMemcpyAsync(&n_pairs, &w->hdr.p->n_pairs, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(w->pin + 201, &w->hdr.p->n_pairs, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
+        const uint32_t n_pairs = w->pin[201];
         w->n_units = n_pairs;
         w->prev_pairs = n_pairs;
         if (n_pairs <= cap) break;
@@ -1606,10 +1611,11 @@ static int tick_end_impl(SfgWorld* w, float* poses_out) {
         CK(cudaMemcpyAsync(poses_out, w->stage2.p, size_t(w->n_bodies) * 16, cudaMemcpyDeviceToHost, w->stream2));
     }
     if (sleeping) { rc = island_post(w); if (rc != SFG_OK) return rc; }
-    uint32_t isl_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (sleeping && w->n_bodies) CK(cudaMemcpyAsync(isl_counts, w->isl_counters.p, sizeof(isl_counts), cudaMemcpyDeviceToHost, st));
-    uint32_t tick_counts[4] = {0, 0, 0, 0};
-    if (w->tick_counts.p) CK(cudaMemcpyAsync(tick_counts, w->tick_counts.p, sizeof(tick_counts), cudaMemcpyDeviceToHost, st));
+    uint32_t* isl_counts = w->pin + 208;           // 8 words
+    uint32_t* tick_counts = w->pin + 216;          // 4 words
+    memset(isl_counts, 0, 12 * 4);
+    if (sleeping && w->n_bodies) CK(cudaMemcpyAsync(isl_counts, w->isl_counters.p, 8 * 4, cudaMemcpyDeviceToHost, st));
+    if (w->tick_counts.p) CK(cudaMemcpyAsync(tick_counts, w->tick_counts.p, 4 * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(w->ev[4], st));
     CK(cudaStreamSynchronize(st));
     if (poses_out) CK(cudaStreamSynchronize(w->stream2));
