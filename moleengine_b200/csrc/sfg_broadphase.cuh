@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = s < n_units;
     uint2 id = make_uint2(0u, 0u);
-    if (in) id = ids[perm[s]];
+    if (in) id = ids[__ldcs(perm + s)];
     {   // statistics: how many units are body-body pairs (visited twice per substep, physics.rs:641,651) -> counts[0]
         const bool two = in && __float_as_int(__ldg(CREC + size_t(id.x) * 4 + 3).x) >= 0 && __float_as_int(__ldg(CREC + size_t(id.y) * 4 + 3).x) >= 0;
         const uint32_t n2 = __syncthreads_count(two);
@@ -664,17 +664,19 @@ __global__ void __launch_bounds__(256) k_build_pair_units(uint32_t n_units, cons
         if (bf & BF_ASLEEP) fl |= UF_ASLEEP;
         if (rope_next && rope_next[c1.x] >= 0 && rope_prev[c1.x] >= 0) fl |= UF_ROPE1;
     }
-    H[s] = make_float4(__int_as_float(c0.x), __int_as_float(c1.x), __uint_as_float(fl), (m0.x + m1.x) / 2.0f);
-    S[s] = make_float4(__uint_as_float(id.x), __uint_as_float(id.y), (m0.y + m1.y) / 2.0f, fmaxf(m0.z, m1.z));
-    G0[s] = g0; G1[s] = g1;
-    L0[s] = l0; L1[s] = l1;
+    // 100 bytes per unit stream out here (0.4 GB in the settled C3 pile) while the 64-byte collider records are gathered at random:
+    // the stores are marked streaming (evict-first) so that they do not push the records out of L2
+    __stcs(H + s, make_float4(__int_as_float(c0.x), __int_as_float(c1.x), __uint_as_float(fl), (m0.x + m1.x) / 2.0f));
+    __stcs(S + s, make_float4(__uint_as_float(id.x), __uint_as_float(id.y), (m0.y + m1.y) / 2.0f, fmaxf(m0.z, m1.z)));
+    __stcs(G0 + s, g0); __stcs(G1 + s, g1);
+    __stcs(L0 + s, l0); __stcs(L1 + s, l1);
     // bodies (or static collider origins) farther apart than this cannot touch: the colliders' bounding radii, never less
     // than circle_circle's "closer than sqrt(0.001) always collides" distance, plus how far each collider sits from its
     // body, plus an f32 safety margin (sfg_solver.cuh stage_contacts)
     float reach = fmaxf(bound_radius(mkshape(g0)) + bound_radius(mkshape(g1)), 0.0332f);
     if (c0.x >= 0) reach += sqrtf(l0.x * l0.x + l0.y * l0.y);
     if (c1.x >= 0) reach += sqrtf(l1.x * l1.x + l1.y * l1.y);
-    RC[s] = reach * 1.001f + 2e-3f;
+    __stcs(RC + s, reach * 1.001f + 2e-3f);
 }
 __global__ void __launch_bounds__(256) k_build_constraint_units(uint32_t n_units, const uint32_t* __restrict__ perm, const int4* __restrict__ KI,
                                                                 const float4* __restrict__ KA, const float4* __restrict__ KB,
