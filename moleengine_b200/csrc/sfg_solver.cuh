@@ -668,7 +668,10 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
             else if (st.kind == ST_CONTACTS) n_head = min(__ldg(c.near_count + st.colour), n);
             if (st.kind == ST_INTEGRATE || st.kind == ST_DERIVE) {
                 // streaming stages: all four columns of BODY_ILP chunks are in flight before the first body is touched
-                constexpr uint32_t BODY_ILP = 2;
+                #ifndef SFG_BODY_ILP
+#define SFG_BODY_ILP 2
+#endif
+                constexpr uint32_t BODY_ILP = SFG_BODY_ILP;
                 const uint32_t chunks = (n + 31u) / 32u, items = (chunks + BODY_ILP - 1u) / BODY_ILP;
                 for (uint32_t it = first_chunk; it < items; it += chunk_stride) {
                     float4 mi[BODY_ILP], p[BODY_ILP], q[BODY_ILP], v[BODY_ILP];
@@ -695,10 +698,10 @@ __global__ void __launch_bounds__(SFG_SOLVER_THREADS, 1) k_solve_persistent(cons
             // drew the expensive ones (17 % of the settled solver's time was spent between the first and the last CTA's arrival).
             // The last SFG_STEAL_PERCENT of a big stage's items are not dealt to CTAs at all: a warp whose CTA has run out takes them
             // one by one from a global counter, so the CTAs that drew cheap items help finish the stage (the sums of ~100 item
-            // costs per CTA still differ by 10-15 % between the luckiest and the unluckiest of 148 CTAs). Only for stages with ~100 items
-            // per CTA or more: in smaller ones the global atomics cost more than the balance returns (measured: landing +2 %).
+            // costs per CTA still differ by 10-15 % between the luckiest and the unluckiest of 148 CTAs). Only for stages with
+            // SFG_STEAL_MIN_ITEMS items per CTA or more: in smaller ones the global atomics cost more than the balance returns.
             const uint32_t per_cta = items / gridDim.x;
-            const uint32_t n_static = (SFG_STEAL_PERCENT && per_cta >= 96u) ? (per_cta - per_cta * SFG_STEAL_PERCENT / 100u) * gridDim.x : items;
+            const uint32_t n_static = (SFG_STEAL_PERCENT && per_cta >= SFG_STEAL_MIN_ITEMS) ? (per_cta - per_cta * SFG_STEAL_PERCENT / 100u) * gridDim.x : items;
             uint32_t* steal = c.steal + size_t(s) * n_stages + k;
             bool tail = false;
             for (;;) {

@@ -32,6 +32,9 @@ constexpr int MAX_LEVELS = 8;
                                     // 512: 0.85 / 4.48 / 15.7, 640 (96 registers, 64 B of spills): 0.87 / 4.59 / 16.5, 768 (80, 176 B): 0.90 / 4.77 / 16.9
 #endif
 
+#ifndef SFG_STEAL_MIN_ITEMS
+#define SFG_STEAL_MIN_ITEMS 32u    // items per CTA from which a stage's tail is stolen (smaller stages: the global atomics cost more than they return)
+#endif
 #ifndef SFG_STEAL_PERCENT
 #define SFG_STEAL_PERCENT 15u       // share of a big stage's items that is not dealt to CTAs up front but taken from one global counter by
                                     // whichever warp runs out of work first (evens out the CTAs; 0 = off)
