@@ -118,7 +118,7 @@ public:
         while (have) {
             const Node& n = nodes_[next.node];
             if (!n.leaf) {
-                R tl, tr;
+                R tl = R(0), tr = R(0);      // set by ray_aabb whenever it reports a hit
                 bool hl = ray_aabb(ray, nodes_[n.left].aabb.padded(half), &tl);
                 bool hr = ray_aabb(ray, nodes_[n.right].aabb.padded(half), &tr);
                 if (hl && hr) {
