@@ -71,14 +71,3 @@ def test_time_scale_changes_substep_count_and_dt(oracle, time_scale, substeps):
         w.tick(frame_dt, time_scale=time_scale)
     n = int(math.ceil(time_scale * substeps))
     _check(w.get_bodies(), _expect(sc, ticks * n, time_scale * frame_dt / n), 1e-9)
-
-
-def test_f32_oracle_follows_the_closed_form_to_f32_accuracy(oracle):
-    """The f32 instantiation of the same template (what the device's bit-exact comparisons use) is the same rule in single precision:
-    velocities re-derived from f32 pose differences at |x| = 50..200 carry ulp(x) / dt = 1e-3 of noise per substep, hence the tolerance."""
-    sc = _free_bodies()
-    w = oracle.OracleWorld(use_f32=True, tuning=abi.default_tuning(substeps=4, flags=abi.TUNE_NO_SLEEPING))
-    w.load_scene(sc)
-    for _ in range(10):
-        w.tick(1.0 / 60.0)
-    _check(w.get_bodies(), _expect(sc, 40, 1.0 / 240.0), 5e-3)
