@@ -15,7 +15,8 @@
 //     constraint order"): the same multiset of constraint applications per substep, visited
 //     colour-major. The colouring is defined in include/sfg_hash.h. No sleeping.
 // Parity status: the reference's own tests do not pin tick / solver results —
-// "parity unpinned" for everything above the collision primitives; this restatement is the pin.
+// "parity unpinned" for everything above the collision primitives; this restatement is the pin
+// (held to closed forms of the reference's update rules by tests/test_oracle_physics_kat.py).
 #pragma once
 #include <algorithm>
 #include <array>

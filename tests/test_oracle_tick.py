@@ -1,6 +1,6 @@
 """CPU tests of the oracle's tick: frozen regression fixtures, internal consistency between its two Gauss-Seidel
 orders, conservation laws, colouring validity and sleeping. (The reference has no tests above its collision
-primitives — SURVEY.md §4 — so these are the only pins of the tick-level restatement.)"""
+primitives — SURVEY.md §4 — so these and the closed forms of test_oracle_physics_kat.py are the only pins of the tick-level restatement.)"""
 import os
 
 import numpy as np
