@@ -179,3 +179,27 @@ def test_two_particle_rope_closed_form(oracle, mode_name):
     keep = 1.0 - min(damping * dt, 1.0)
     assert abs(st[0, 4] - keep * moved * w0 / (w0 + w1) / dt) < 1e-4 and abs(st[1, 4] + keep * moved * w1 / (w0 + w1) / dt) < 1e-4
     assert abs(2.0 * st[0, 4] + 0.5 * st[1, 4]) < 1e-6 and np.abs(st[:, 1] - 1.0).max() < 1e-9
+
+
+@pytest.mark.parametrize("e,v_in,field,bounces", [(0.8, -2.0, False, True), (0.5, -0.5, False, True), (0.0, -2.0, False, False),
+                                                   (0.8, -0.30, True, True), (0.8, -0.10, True, False)])
+def test_restitution_closed_form_and_its_resting_threshold(oracle, e, v_in, field, bounces):
+    """solver.rs:555-576: a circle arriving at static ground with normal speed |v| (its velocity AFTER the external acceleration of
+    the substep, `old_velocities`) leaves with e |v| — unless v^2 < dt^2 |a_ext|^2 (solver.rs:569: slower than what one substep of
+    the external field adds counts as resting), then with 0. The restitution of a pair is the larger of the two colliders'."""
+    r, depth, top, dt = 0.5, 0.02, 0.1, 1.0 / 60.0
+    g = G if field else 0.0
+    b = np.zeros(1, abi.body_dtype)
+    shapes.fill_bodies_dynamic(b, 1.0, 0.1, 1.0, 0.0, top + r - depth, vy=v_in - g * dt)     # so that the speed after the field's kick is v_in
+    c = np.zeros(2, abi.collider_dtype)
+    shapes.fill_colliders(c[0:1], shapes.rounded_rect(10.0, 0.2, 0.0), x=0.0, y=0.0)
+    shapes.fill_colliders(c[1:2], shapes.circle(np.full(1, r)), body=np.zeros(1, np.int32), restitution=e)
+    sc = scenes._scene("bounce", b, c, 1)
+    w = oracle.OracleWorld(tuning=abi.default_tuning(substeps=1, flags=abi.TUNE_NO_SLEEPING))
+    w.load_scene(sc)
+    w.tick(dt, forcefield=abi.gravity_field() if field else _no_field())
+    st = w.get_bodies()
+    assert abs(st[0, 1] - (top + r)) < 1e-6                                  # lifted onto the ground
+    want = float(np.float32(e)) * abs(v_in) if bounces else 0.0
+    assert abs(st[0, 5] - want) < 2e-6, (st[0, 5], want)
+    assert abs(st[0, 4]) < 1e-12 and abs(st[0, 6]) < 1e-9
