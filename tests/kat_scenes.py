@@ -115,3 +115,26 @@ def rope_expect(L, spacing, damping, compliance, dt):
     k = (w0 + w1) / (w0 + w1 + float(np.float32(compliance)) / dt ** 2)
     moved = (L - float(np.float32(spacing))) * k
     return moved * w0 / (w0 + w1), moved * w1 / (w0 + w1), 1.0 - min(damping * dt, 1.0)
+
+
+def sliding_particle(v_t, r=0.5, depth=0.02):
+    """A particle body (mass 1, infinite inertia: no lever arms) with a circle collider, sunk `depth` into static ground, sliding at v_t."""
+    b = np.zeros(1, abi.body_dtype)
+    shapes.fill_bodies_particle(b, 1.0, 0.0, GROUND_TOP + r - depth)
+    b["vx"] = v_t
+    c = np.zeros(2, abi.collider_dtype)
+    shapes.fill_colliders(c[0:1], shapes.rounded_rect(10.0, 0.2, 0.0), x=0.0, y=0.0)
+    shapes.fill_colliders(c[1:2], shapes.circle(np.full(1, r)), body=np.zeros(1, np.int32))     # default material: mu_s 1.6, mu_d 1.5
+    return scenes._scene("sliding_particle", b, c, 1)
+
+
+def sliding_expect(v_t, depth, dt, mu_s=1.6, mu_d=1.5):
+    """(x, vx) after one substep without external field, mass 1. Static friction (solver.rs:456-487) is SIGNED in the reference: it
+    engages when lambda_t < mu_s lambda_n with lambda_n = -depth m < 0 and lambda_t = -(tangential motion) m, i.e. only for motion
+    along +left_normal(n) larger than mu_s depth — for a body on the ground that is the +x direction — and then cancels the substep's
+    tangential motion altogether. Otherwise the body slides, and the velocity step (solver.rs:578-592) takes
+    min(|v_t|, mu_d |lambda_n| / dt) off the tangential velocity."""
+    if v_t * dt > mu_s * depth:
+        return 0.0, 0.0
+    cut = min(abs(v_t), mu_d * depth / dt)
+    return v_t * dt, v_t - math.copysign(cut, v_t)

@@ -84,3 +84,12 @@ def test_restitution_closed_form_and_its_resting_threshold(e, v_in, field, bounc
     assert abs(st[0, 1] - (K.GROUND_TOP + r)) < 1e-5, st
     want = float(np.float32(e)) * abs(v_in) if bounces else 0.0
     assert abs(st[0, 5] - want) < 1e-3, (st[0, 5], want)
+
+
+@pytest.mark.parametrize("v_t", [3.0, -3.0, 1.0, -1.0])
+def test_friction_closed_form_including_the_signed_static_rule(v_t):
+    depth, dt = 0.02, 1.0 / 60.0
+    st = _run(K.sliding_particle(v_t, depth=depth), 1, 1, field=K.no_field())
+    x, vx = K.sliding_expect(v_t, depth, dt)
+    assert abs(st[0, 0] - x) < 1e-5 and abs(st[0, 4] - vx) < 1e-3, (st[0], x, vx)
+    assert abs(st[0, 1] - (K.GROUND_TOP + 0.5)) < 1e-5 and abs(st[0, 5]) < 1e-3, st[0]

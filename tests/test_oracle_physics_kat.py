@@ -133,3 +133,22 @@ def test_restitution_closed_form_and_its_resting_threshold(oracle, e, v_in, fiel
     want = float(np.float32(e)) * abs(v_in) if bounces else 0.0
     assert abs(st[0, 5] - want) < 2e-6, (st[0, 5], want)
     assert abs(st[0, 4]) < 1e-12 and abs(st[0, 6]) < 1e-9
+
+
+SLIDING_CASES = [3.0, -3.0, 1.0, -1.0, 1.95, 1.90]
+
+
+@pytest.mark.parametrize("mode_name", ["MODE_REFERENCE", "MODE_COLOURED"])
+@pytest.mark.parametrize("v_t", SLIDING_CASES)
+def test_friction_closed_form_including_the_signed_static_rule(oracle, mode_name, v_t):
+    """kat_scenes.sliding_expect: static friction only for fast motion in ONE direction (the reference compares signed lambdas,
+    solver.rs:462-467), dynamic friction bounded by mu_d |lambda_n| / dt (solver.rs:578-592); threshold at v_t dt = mu_s depth = 1.92 m/s."""
+    depth, dt = 0.02, 1.0 / 60.0
+    sc = K.sliding_particle(v_t, depth=depth)
+    w = oracle.OracleWorld(tuning=abi.default_tuning(substeps=1, flags=abi.TUNE_NO_SLEEPING))
+    w.load_scene(sc)
+    w.tick(dt, forcefield=K.no_field(), mode=getattr(oracle, mode_name))
+    st = w.get_bodies()
+    x, vx = K.sliding_expect(v_t, depth, dt)
+    assert abs(st[0, 0] - x) < 1e-6 and abs(st[0, 4] - vx) < 1e-4, (st[0], x, vx)
+    assert abs(st[0, 1] - (K.GROUND_TOP + 0.5)) < 1e-6 and abs(st[0, 5]) < 1e-4
