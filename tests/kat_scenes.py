@@ -4,7 +4,7 @@ import math
 
 import numpy as np
 
-from moleengine_b200 import abi, scenes, shapes
+from moleengine_b200 import abi, scenes, shapes  # noqa: F401 (re-exported for the tests)
 
 G = float(np.float32(-9.81))      # the force field crosses the ABI as f32
 

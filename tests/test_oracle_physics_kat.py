@@ -152,3 +152,42 @@ def test_friction_closed_form_including_the_signed_static_rule(oracle, mode_name
     x, vx = K.sliding_expect(v_t, depth, dt)
     assert abs(st[0, 0] - x) < 1e-6 and abs(st[0, 4] - vx) < 1e-4, (st[0], x, vx)
     assert abs(st[0, 1] - (K.GROUND_TOP + 0.5)) < 1e-6 and abs(st[0, 5]) < 1e-4
+
+
+def test_kinematic_body_pushes_and_is_never_corrected(oracle):
+    """body.rs:92-97, solver.rs:63,323-331: a body with infinite mass and inertia moves by its velocity alone (no gravity either);
+    in a contact its inverse mass is 0, so the dynamic partner takes the whole correction."""
+    r, depth, dt = 0.5, 0.1, 1.0 / 60.0
+    b = np.zeros(2, abi.body_dtype)
+    K.shapes.fill_bodies_kinematic(b[0:1], -(r - depth / 2), 0.0, vx=0.6)
+    K.shapes.fill_bodies_dynamic(b[1:2], 1.0, 0.1, 1.0, +(r - depth / 2), 0.0)
+    c = np.zeros(2, abi.collider_dtype)
+    K.shapes.fill_colliders(c, K.shapes.circle(np.full(2, r)), body=np.arange(2))
+    sc = K.scenes._scene("pusher", b, c, 1)
+    w = oracle.OracleWorld(tuning=abi.default_tuning(substeps=1, flags=abi.TUNE_NO_SLEEPING))
+    w.load_scene(sc)
+    w.tick(dt)                                                               # default field: gravity acts on the dynamic body only
+    st = w.get_bodies()
+    vk = float(b["vx"][0])                                                   # 0.6 as f32
+    xk = float(b["x"][0]) + vk * dt
+    assert abs(st[0, 0] - xk) < 1e-12 and abs(st[0, 1]) < 1e-12 and abs(st[0, 4] - vk) < 1e-9 and abs(st[0, 5]) < 1e-12     # on rails
+    # the dynamic circle ends exactly touching the kinematic one (the contact normal is the line of centres after the gravity step)
+    d = math.hypot(st[1, 0] - st[0, 0], st[1, 1] - st[0, 1])
+    assert abs(d - 2 * r) < 1e-6
+    assert st[1, 0] > float(b["x"][1]) + depth * 0.9                          # it took (nearly) all of the overlap, plus the pusher's advance
+
+
+def test_sensor_reports_the_contact_but_moves_nothing(oracle):
+    """collider.rs `is_sensor`: a sensor pair is latched as a contact (physics.rs:1097-1122 publishes it) but is skipped by the position
+    and velocity solves (solver.rs:323-331, 511-516)."""
+    r, depth, dt = 0.5, 0.1, 1.0 / 60.0
+    sc = K.two_circles(r, depth)
+    sc["colliders"]["flags"][1] |= abi.COLL_SENSOR
+    b = sc["bodies"]
+    w = oracle.OracleWorld(tuning=abi.default_tuning(substeps=1, flags=abi.TUNE_NO_SLEEPING))
+    w.load_scene(sc)
+    w.tick(dt, forcefield=K.no_field())
+    st = w.get_bodies()
+    assert abs(st[0, 0] - float(b["x"][0])) < 1e-12 and abs(st[1, 0] - float(b["x"][1])) < 1e-12 and np.abs(st[:, 4:7]).max() < 1e-12
+    cs = w.contacts()
+    assert len(cs) >= 1
